@@ -1,0 +1,206 @@
+/*
+ * lsob200.h — C ABI of the B200-native inner solver for LeastSquaresOptim.jl's hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an `int` status
+ * (0 = ok, >0 = LAPACK-style `info`, <0 = argument / CUDA / NCCL error; text via
+ * lso_last_error).  No C++ exception crosses this boundary.  All floating point is IEEE
+ * binary64 ("Float64" on the Julia side).  Dense matrices are column-major with an explicit
+ * leading dimension (Julia `Matrix{Float64}`: ld = size(J,1)).  Sparse matrices are CSC with
+ * Julia's Int64 1-based `colptr` / `rowval` (converted once per pattern on import).
+ *
+ * Each group cites the reference interface it replaces (paths under the reference checkout,
+ * matthieugomez/LeastSquaresOptim.jl v0.8.10).  INTEGRATION.md shows the Julia `ccall`
+ * binding for each.
+ *
+ * Memory model: `double*` arguments named `d_*` are DEVICE pointers obtained from
+ * lso_dev_alloc (resident mode: J, x, f, δ live in HBM across iterations).  The `*_host`
+ * entry points take HOST pointers, borrowed for the duration of the call.
+ * A context is single-caller (not thread-safe), one CUDA stream, one device.
+ */
+#ifndef LSOB200_H
+#define LSOB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lso_ctx lso_ctx;           /* device + stream + scratch + (optional) NCCL comm */
+typedef struct lso_dense_ws lso_dense_ws; /* workspace of DenseQRAllocatedSolver / DenseCholeskyAllocatedSolver */
+typedef struct lso_csc lso_csc;           /* device image of a SparseMatrixCSC{Float64,Int64} (+ CSR mirror) */
+typedef struct lso_lsmr_ws lso_lsmr_ws;   /* workspace of LSMRAllocatedSolver / LSMRDampenedAllocatedSolver */
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define LSO_OK                 0
+#define LSO_ERR_ARG           (-1)   /* DimensionMismatch / ArgumentError on the Julia side   */
+#define LSO_ERR_CUDA          (-2)
+#define LSO_ERR_NCCL          (-3)
+#define LSO_ERR_ALLOC         (-4)
+#define LSO_ERR_UNSUPPORTED   (-5)
+#define LSO_ERR_NOT_FINITE    (-6)   /* IsFiniteException (src/utils/utils.jl:63-78)          */
+/* positive return = LAPACK info: PosDefException(info) (dense_cholesky.jl:57),
+ * RankDeficientException(info) (dense_cholesky.jl:33).                                        */
+
+/* ---- library / context -------------------------------------------------------------- */
+int         lso_version(void);
+int         lso_device_count(int* count);
+int         lso_ctx_create(int device, lso_ctx** out);
+int         lso_ctx_destroy(lso_ctx* ctx);
+const char* lso_last_error(lso_ctx* ctx);          /* ctx may be NULL: last global error */
+int         lso_ctx_sync(lso_ctx* ctx);
+void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-event timing by the caller */
+int         lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value);
+int         lso_ctx_launch_count(lso_ctx* ctx, int64_t* out, int reset); /* kernels launched by this library */
+
+/* ---- device memory (Julia GC owns nothing on the device; finalizers call *_free) ----- */
+int lso_dev_alloc(lso_ctx* ctx, size_t nbytes, void** d_out);
+int lso_dev_free(lso_ctx* ctx, void* d_ptr);
+int lso_host_alloc_pinned(lso_ctx* ctx, size_t nbytes, void** h_out);
+int lso_host_free_pinned(lso_ctx* ctx, void* h_ptr);
+int lso_upload(lso_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);     /* synchronous */
+int lso_download(lso_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes);   /* synchronous */
+int lso_upload_async(lso_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);
+int lso_download_async(lso_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes);
+int lso_upload_matrix(lso_ctx* ctx, double* d_dst, int64_t ld_dst, const double* h_src, int64_t ld_src,
+                      int64_t rows, int64_t cols);
+
+/* ---- vector duck type: src/utils/lsmr.jl:30-44, and what the optimizers call on x / f
+ *      (levenberg_marquardt.jl:60,84-86,89-98,106,111,116-117,127,135; dogleg.jl:68,90,93,105-106,
+ *       114,117,122-145,148-160,168,173-174,190; utils.jl:24,39-55,165-176)               ---- */
+int lso_vec_fill(lso_ctx* ctx, int64_t n, double* d_x, double value);                 /* fill!     */
+int lso_vec_copy(lso_ctx* ctx, int64_t n, double* d_dst, const double* d_src);        /* copyto!   */
+int lso_vec_scal(lso_ctx* ctx, int64_t n, double* d_x, double alpha);                 /* rmul!     */
+int lso_vec_axpy(lso_ctx* ctx, int64_t n, double alpha, const double* d_x, double* d_y);          /* axpy! */
+int lso_vec_axpby(lso_ctx* ctx, int64_t n, double alpha, const double* d_x, double beta, double* d_y);
+int lso_vec_mul(lso_ctx* ctx, int64_t n, double* d_out, const double* d_x, const double* d_y);    /* map!(*,…) */
+int lso_vec_div(lso_ctx* ctx, int64_t n, double* d_out, const double* d_x, const double* d_y);    /* map!(/,…) dogleg.jl:105 */
+int lso_vec_sqrt(lso_ctx* ctx, int64_t n, double* d_x);                                           /* map!(sqrt,…) iterative_lsmr.jl:252 */
+int lso_vec_clamp(lso_ctx* ctx, int64_t n, double* d_x, double lo, double hi);                    /* clamp!    */
+int lso_vec_sum(lso_ctx* ctx, int64_t n, const double* d_x, double* out);                         /* sum       */
+int lso_vec_sumabs2(lso_ctx* ctx, int64_t n, const double* d_x, double* out);                     /* sum(abs2,·) */
+int lso_vec_nrm2(lso_ctx* ctx, int64_t n, const double* d_x, double* out);                        /* norm      */
+int lso_vec_maxabs(lso_ctx* ctx, int64_t n, const double* d_x, double* out);                      /* maximum(abs,·) */
+int lso_vec_dot(lso_ctx* ctx, int64_t n, const double* d_x, const double* d_y, double* out);
+int lso_vec_wdot(lso_ctx* ctx, int64_t n, const double* d_x, const double* d_y, const double* d_w, double* out); /* utils.jl:165-173 */
+int lso_vec_check_finite(lso_ctx* ctx, int64_t n, const double* d_x, int64_t* first_bad /* -1 if none */);      /* utils.jl:70-75 */
+/* box projection of the step: δ[i] = min(δ[i], x[i]-lower[i]); δ[i] = max(δ[i], x[i]-upper[i])
+ * (levenberg_marquardt.jl:89-98, dogleg.jl:148-157). d_lower / d_upper may be NULL. */
+int lso_vec_box_project(lso_ctx* ctx, int64_t n, double* d_delta, const double* d_x,
+                        const double* d_lower, const double* d_upper);
+/* maxabs_projected_gradient (utils.jl:39-55). d_lower / d_upper may be NULL. */
+int lso_vec_maxabs_projected(lso_ctx* ctx, int64_t n, const double* d_g, const double* d_x,
+                             const double* d_lower, const double* d_upper, double* out);
+/* LM damping build, levenberg_marquardt.jl:84-86:
+ *   mean = sum(dtd)/n; clamp!(dtd, min_diag*mean, max_diag*mean); rmul!(dtd, inv_delta)   */
+int lso_lm_damping(lso_ctx* ctx, int64_t n, double* d_dtd, double min_diag, double max_diag, double inv_delta);
+/* Dogleg step blend, dogleg.jl:120-145; returns wnorm_δx. */
+int lso_dogleg_blend(lso_ctx* ctx, int64_t n, double* d_dx, const double* d_gn, const double* d_gr,
+                     const double* d_dtd, double delta, double alpha, double wnorm_gn, double wnorm_gr,
+                     double* wnorm_dx_out);
+
+/* ---- dense operator: mul!(y,J,x,α,β), mul!(x,J',y,α,β), colsumabs2!(x,J)
+ *      (README.md:37-43; utils.jl:139-144; levenberg_marquardt.jl:82,102,114; dogleg.jl:85,99,109,171) */
+int lso_dense_colsumabs2(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld, double* d_out);
+int lso_dense_gemv_n(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const double* d_J, int64_t ld,
+                     const double* d_x, double beta, double* d_y);
+int lso_dense_gemv_t(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const double* d_J, int64_t ld,
+                     const double* d_y, double beta, double* d_x);
+/* fused: dtd = colsumabs2(J) and g = J'f in ONE pass over J (LM:82 + LM:102; dogleg:85 + :99) */
+int lso_dense_colsumabs2_gemv_t(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld,
+                                const double* d_f, double* d_dtd, double* d_g);
+/* fused: fpredict = J*δ - f ; *ssr_out = sum(abs2, fpredict)  (LM:114-117; dogleg:171-174).
+ * d_fpredict may be NULL (only the scalar is wanted). */
+int lso_dense_predicted_ssr(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld,
+                            const double* d_delta, const double* d_f, double* d_fpredict, double* ssr_out);
+
+/* ---- dense solvers: DenseQRAllocatedSolver (src/solver/dense_qr.jl:25-28, 50-54) and
+ *      DenseCholeskyAllocatedSolver (src/solver/dense_cholesky.jl:19-21)                     ---- */
+#define LSO_SOLVER_QR        1
+#define LSO_SOLVER_CHOLESKY  2
+/* damped != 0: LevenbergMarquardt workspace ((m+n) x n augmented system), else Dogleg workspace. */
+int lso_dense_ws_create(lso_ctx* ctx, int64_t m, int64_t n, int solver_kind, int damped, lso_dense_ws** out);
+int lso_dense_ws_destroy(lso_dense_ws* ws);
+/* ldiv!(x, J, y, damp, A::DenseQRAllocatedSolver)  — dense_qr.jl:56-88  (d_damp != NULL)
+ * ldiv!(x, J, y, A::DenseQRAllocatedSolver)        — dense_qr.jl:30-42  (d_damp == NULL)
+ * Solves min ||[J; diag(sqrt(damp))] x - [y; 0]||_2 by Householder QR.  J, y, damp untouched.
+ * rank_out (may be NULL) receives the numerical rank found (dgelsy-style, rcond = min(rows,cols)*eps). */
+int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
+                 const double* d_damp, double* d_x, int* rank_out);
+/* ldiv!(x, J, y, damp, A::DenseCholeskyAllocatedSolver) — dense_cholesky.jl:43-59 (d_damp != NULL)
+ * ldiv!(x, J, y, A::DenseCholeskyAllocatedSolver)       — dense_cholesky.jl:29-35 (d_damp == NULL)
+ * When the context has a communicator (lso_comm_init_rank), J and y are this rank's row shard and
+ * [J'J | J'y] is all-reduced over NCCL before the (replicated) factorisation.
+ * Returns info > 0 when the matrix is not positive definite / rank deficient. */
+int lso_chol_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
+                   const double* d_damp, double* d_x);
+/* Host-buffer forms (what `ldiv!` on plain Julia Arrays binds): copy J, y, damp H2D, solve, copy x D2H. */
+int lso_qr_solve_host(lso_dense_ws* ws, const double* h_J, int64_t ld, const double* h_y,
+                      const double* h_damp, double* h_x, int* rank_out);
+int lso_chol_solve_host(lso_dense_ws* ws, const double* h_J, int64_t ld, const double* h_y,
+                        const double* h_damp, double* h_x);
+/* introspection for tests: copy the n x n upper-triangular factor (column-major, ld = n) to the host */
+int lso_dense_ws_get_factor(lso_dense_ws* ws, double* h_R);
+
+/* ---- multi-GPU (row-sharded dense J): one process per GPU, NCCL over NVLink.
+ *      No reference counterpart (the reference is single-process); see DESIGN.md §multi-GPU. ---- */
+int lso_comm_unique_id(void* id128 /* 128 bytes out */);
+int lso_comm_init_rank(lso_ctx* ctx, int nranks, int rank, const void* id128);
+int lso_comm_destroy(lso_ctx* ctx);
+int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count);
+/* TSQR over row shards for the QR path: every rank passes its shard of J and y; all ranks get x. */
+int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
+                         const double* d_damp, double* d_x, int* rank_out);
+
+/* ---- sparse operator: SparseMatrixCSC mul! both ways + colsumabs2! (utils.jl:146-151;
+ *      lsmr.jl:73,76,118,122; levenberg_marquardt.jl:82,102,114)                             ---- */
+int lso_csc_create(lso_ctx* ctx, int64_t m, int64_t n, int64_t nnz,
+                   const int64_t* h_colptr_1based, const int64_t* h_rowval_1based, lso_csc** out);
+int lso_csc_destroy(lso_csc* A);
+int lso_csc_set_values_host(lso_csc* A, const double* h_nzval);     /* after g!(J,x) wrote nonzeros(J) */
+int lso_csc_set_values_dev(lso_csc* A, const double* d_nzval);
+double* lso_csc_values(lso_csc* A);                                  /* device nzval (CSC order), writable by device g! */
+int lso_csc_values_changed(lso_csc* A);                              /* refresh the CSR mirror after writing lso_csc_values */
+int lso_csc_mul_n(lso_csc* A, double alpha, const double* d_x, double beta, double* d_y);   /* y = α J x + β y  */
+int lso_csc_mul_t(lso_csc* A, double alpha, const double* d_y, double beta, double* d_x);   /* x = α J'y + β x  */
+int lso_csc_colsumabs2(lso_csc* A, double* d_out);
+
+/* ---- LSMR solvers: src/solver/iterative_lsmr.jl:161-198 (undamped) and :221-259 (damped),
+ *      running src/utils/lsmr.jl:53-238 on the device.  Exactly one of (A_csc) or (d_J, ld) is
+ *      given: the operator is the CSC image or a dense column-major J.                        ---- */
+int lso_lsmr_ws_create(lso_ctx* ctx, int64_t m, int64_t n, int damped, lso_lsmr_ws** out);
+int lso_lsmr_ws_destroy(lso_lsmr_ws* ws);
+/* d_damp == NULL: ldiv!(x,J,y,A::LSMRAllocatedSolver) (atol=btol=1e-6 by default);
+ * d_damp != NULL: ldiv!(x,J,y,damp,A::LSMRDampenedAllocatedSolver) (btol=0.5 at iterative_lsmr.jl:255);
+ *                 damp is overwritten by sqrt(damp) exactly as at iterative_lsmr.jl:252.
+ * maxiter <= 0 selects the reference default max(rows, cols) (lsmr.jl:55).
+ * iters_out: LSMR iterations (the reference returns mvps = 2*iters); istop_out: lsmr.jl:224-231. */
+int lso_lsmr_solve(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_J, int64_t ld,
+                   const double* d_y, double* d_damp, double* d_x,
+                   double atol, double btol, double conlim, int64_t maxiter,
+                   int64_t* iters_out, int* istop_out);
+
+/* ---- synthetic workload generators and residual models used by bench.py / tests
+ *      (counter-based hash, bit-identical on CPU and GPU).  Harness, not boundary. ---- */
+int lso_synth_dense_matrix(lso_ctx* ctx, int64_t m, int64_t n, int64_t row_offset, uint64_t seed,
+                           double* d_A, int64_t ld);
+int lso_synth_vector(lso_ctx* ctx, int64_t n, int64_t offset, uint64_t seed, double scale, double* d_x);
+/* r = t + c t^2 - b with t = A x ;  J = diag(1 + 2 c t) A */
+int lso_synth_residual(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, int64_t ld, const double* d_x,
+                       const double* d_b, double c, double* d_t, double* d_r);
+int lso_synth_jacobian(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, int64_t ld, const double* d_t,
+                       double c, double* d_J, int64_t ldJ);
+int lso_synth_csc_pattern(int64_t m, int64_t n, int64_t nnz_per_col, uint64_t seed,
+                          int64_t* h_colptr_1based, int64_t* h_rowval_1based); /* host, deterministic */
+int lso_synth_csc_jacobian(lso_csc* A, const double* d_Aval, const double* d_t, double c); /* nzval = (1+2c t[row]) * Aval */
+
+/* ---- micro-benchmarks that give the roofline denominators this library reports against ---- */
+int lso_bench_fp64_mma_peak(lso_ctx* ctx, int iters, double* tflops_out);   /* DMMA m8n8k4 issue-bound loop */
+int lso_bench_fp64_fma_peak(lso_ctx* ctx, int iters, double* tflops_out);   /* DFMA issue-bound loop */
+int lso_bench_hbm_copy(lso_ctx* ctx, size_t nbytes, int iters, double* gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSOB200_H */

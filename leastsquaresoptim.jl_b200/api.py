@@ -1,0 +1,457 @@
+"""Host-side mirror of the reference's public API for the hot path (src/types.jl, src/optimizer/*.jl).
+
+Same names, argument meaning and error behaviour as LeastSquaresOptim.jl:
+  LeastSquaresProblem(x=..., f_=..., g_=..., J=..., y=..., output_length=...)     types.jl:7-68
+  QR() / Cholesky() / LSMR()            solver markers                            types.jl:79-86
+  Dogleg(solver) / LevenbergMarquardt(solver)                                     types.jl:89-98
+  optimize_(nls, optimizer; x_tol, f_tol, g_tol, iterations, Δ, lower, upper)     `optimize!`  types.jl:207-209
+  optimize(f, x0, optimizer)                                                      types.jl:182-184
+  LeastSquaresResult                                                              types.jl:220-237
+
+The trust-region outer loops below are literal restatements of levenberg_marquardt.jl:39-144 and
+dogleg.jl:41-203 (control flow and scalars on the host, exactly what stays in Julia), but every vector /
+matrix operation they issue runs on the device through the C ABI.  `f_` / `g_` are the user's `f!` / `g!`:
+  * host mode  (default): f_(out: np.ndarray, x: np.ndarray), g_(J: np.ndarray | scipy csc, x) — as in Julia;
+    the driver moves x down and f / J up around each call (this is the e2e path with host buffers);
+  * device mode (`device_callbacks=True`): f_(out: DeviceVector, x: DeviceVector), g_(J, x) write HBM directly.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import numpy as np
+
+from .device import Context, CSCMatrix, DenseMatrix, DeviceVector, wdot, wnorm
+from .solvers import (DenseCholeskyAllocatedSolver, DenseQRAllocatedSolver, LSMRAllocatedSolver,
+                      LSMRDampenedAllocatedSolver)
+
+# shared constants, types.jl:107-111
+MIN_DELTA = 1e-16
+MAX_DELTA = 1e16
+MIN_STEP_QUALITY = 1e-3
+MIN_DIAGONAL = 1e-6
+MAX_DIAGONAL = 1e32
+# dogleg.jl:38-39
+DECREASE_THRESHOLD = 0.25
+INCREASE_THRESHOLD = 0.75
+
+
+# ---- solver / optimizer markers (types.jl:79-98) ----------------------------------------------------
+class AbstractSolver:
+    pass
+
+
+class QR(AbstractSolver):
+    pass
+
+
+class Cholesky(AbstractSolver):
+    pass
+
+
+class LSMR(AbstractSolver):
+    pass
+
+
+class AbstractOptimizer:
+    def __init__(self, solver: Optional[AbstractSolver] = None):
+        self.solver = solver
+
+
+class Dogleg(AbstractOptimizer):
+    pass
+
+
+class LevenbergMarquardt(AbstractOptimizer):
+    pass
+
+
+def _is_sparse(J) -> bool:
+    return hasattr(J, "tocsc") or isinstance(J, CSCMatrix)
+
+
+def default_solver(solver, J):
+    """types.jl:114-121"""
+    if solver is not None:
+        if isinstance(solver, QR) and _is_sparse(J):
+            raise ValueError("solver QR() is not available for sparse Jacobians. Choose between Cholesky() and LSMR()")
+        return solver
+    return LSMR() if _is_sparse(J) else QR()
+
+
+def default_optimizer(optimizer, solver):
+    """types.jl:124-127"""
+    if isinstance(optimizer, Dogleg):
+        return Dogleg(solver)
+    if isinstance(optimizer, LevenbergMarquardt):
+        return LevenbergMarquardt(solver)
+    return LevenbergMarquardt(LSMR()) if isinstance(solver, LSMR) else Dogleg(solver)
+
+
+# ---- problem (types.jl:7-68) ---------------------------------------------------------------------------
+class LeastSquaresProblem:
+    def __init__(self, x=None, y=None, f_: Callable = None, g_: Callable = None, J=None, output_length: int = 0,
+                 device_callbacks: bool = False, ctx: Context | None = None):
+        if x is None:
+            raise ValueError("initial x required")
+        if f_ is None:
+            raise ValueError("initial f! required")
+        self.ctx = ctx or Context.default()
+        self.device_callbacks = device_callbacks
+        if device_callbacks:
+            assert isinstance(x, DeviceVector) and isinstance(y, DeviceVector) and J is not None and g_ is not None
+            self.x, self.y, self.J = x, y, J
+            self.f_, self.g_ = f_, g_
+            m, n = J.shape
+        else:
+            self.x = np.array(x, dtype=np.float64)     # optimize! mutates nls.x in place (types.jl:189)
+            if y is None:
+                if output_length == 0:
+                    if J is None:
+                        raise ValueError("specify J or output_length")
+                    output_length = J.shape[0]
+                y = np.zeros(output_length)
+            self.y = np.asarray(y, dtype=np.float64)
+            if J is None:
+                J = np.zeros((self.y.size, self.x.size), order="F")
+            self.J = J
+            self.f_ = f_
+            if g_ is None:
+                g_ = _central_difference_jacobian(f_, self.y.size)
+            self.g_ = g_
+            m, n = J.shape
+        if len(self.x) != n:
+            raise ValueError("DimensionMismatch: x must have length size(J, 2)")
+        if len(self.y) != m:
+            raise ValueError("DimensionMismatch: y must have length size(J, 1)")
+
+
+def _central_difference_jacobian(f_, m):
+    """Stand-in for the FiniteDiff closure at types.jl:56-58 (host-only helper, off the hot path)."""
+    def g_(J, x):
+        n = x.size
+        fp, fm = np.empty(m), np.empty(m)
+        xx = x.copy()
+        for j in range(n):
+            h = np.cbrt(np.finfo(float).eps) * max(1.0, abs(x[j]))
+            xx[j] = x[j] + h
+            f_(fp, xx)
+            xx[j] = x[j] - h
+            f_(fm, xx)
+            xx[j] = x[j]
+            J[:, j] = (fp - fm) / (2 * h)
+    return g_
+
+
+@dataclass
+class OptimizationState:
+    iteration: int
+    value: float
+    g_norm: float
+
+
+@dataclass
+class LeastSquaresResult:
+    optimizer: str
+    minimizer: np.ndarray
+    ssr: float
+    iterations: int
+    converged: bool
+    x_converged: bool
+    x_tol: float
+    f_converged: bool
+    f_tol: float
+    g_converged: bool
+    g_tol: float
+    tr: list = field(default_factory=list)
+    f_calls: int = 0
+    g_calls: int = 0
+    mul_calls: int = 0
+    deltas: list = field(default_factory=list)   # per-solve δ (only when record_steps=True; parity tests)
+
+
+# ---- device-side problem state -------------------------------------------------------------------------
+class _Allocated:
+    """LeastSquaresProblemAllocated (types.jl:141-157): device mirrors of x, y, J + optimizer/solver workspaces."""
+
+    def __init__(self, nls: LeastSquaresProblem, optimizer: AbstractOptimizer):
+        self.nls = nls
+        ctx = self.ctx = nls.ctx
+        self.host = not nls.device_callbacks
+        if self.host:
+            m, n = nls.J.shape
+            self.x = DeviceVector(ctx, n, nls.x)
+            self.fcur = DeviceVector(ctx, m)
+            self.sparse = _is_sparse(nls.J)
+            if self.sparse:
+                nls.J = nls.J.tocsc()
+                nls.J.sort_indices()
+                self.J = CSCMatrix.from_scipy(ctx, nls.J)
+            else:
+                self.J = DenseMatrix(ctx, m, n)
+            self._hx = np.empty(n)
+            self._hf = np.empty(m)
+        else:
+            self.x, self.fcur, self.J = nls.x, nls.y, nls.J
+            self.sparse = isinstance(self.J, CSCMatrix)
+            m, n = self.J.shape
+        self.m, self.n = m, n
+        solver = optimizer.solver
+        damped = isinstance(optimizer, LevenbergMarquardt)
+        if isinstance(solver, QR):
+            self.solver = DenseQRAllocatedSolver(ctx, m, n, damped)
+        elif isinstance(solver, Cholesky):
+            if self.sparse:
+                raise TypeError("MethodError: no Cholesky solver for sparse Jacobians (dense_cholesky.jl:19)")
+            self.solver = DenseCholeskyAllocatedSolver(ctx, m, n, damped)
+        elif isinstance(solver, LSMR):
+            self.solver = LSMRDampenedAllocatedSolver(ctx, m, n) if damped else LSMRAllocatedSolver(ctx, m, n)
+        else:
+            raise TypeError(f"unknown solver {solver!r}")
+
+    # f!(out, x) and g!(J, x) with the data movement each mode needs
+    def f(self, out: DeviceVector, x: DeviceVector):
+        if self.host:
+            x.download(self._hx)
+            self.nls.f_(self._hf, self._hx)
+            out.upload(self._hf)
+        else:
+            self.nls.f_(out, x)
+
+    def g(self, x: DeviceVector):
+        if self.host:
+            x.download(self._hx)
+            self.nls.g_(self.nls.J, self._hx)
+            if self.sparse:
+                self.J.set_values(self.nls.J.data)
+            else:
+                self.J.upload(self.nls.J)
+        else:
+            self.nls.g_(self.J, x)
+
+    def finish(self, x: DeviceVector):
+        if self.host:
+            x.download(self.nls.x)
+            self.fcur.download(self.nls.y)
+            return self.nls.x
+        return x
+
+
+def _bounds(ctx, x: DeviceVector, lower, upper):
+    n = len(x)
+    lo = np.asarray(lower, dtype=np.float64) if lower is not None and len(lower) else None
+    hi = np.asarray(upper, dtype=np.float64) if upper is not None and len(upper) else None
+    if (lo is not None and lo.size != n) or (hi is not None and hi.size != n):
+        raise ValueError("Bounds must either be empty or of the same length as the number of parameters.")
+    xh = x.download()
+    if (lo is not None and not np.all(xh >= lo)) or (hi is not None and not np.all(xh <= hi)):
+        raise ValueError("Initial guess must be within bounds.")
+    dlo = DeviceVector(ctx, n, lo) if lo is not None else None
+    dhi = DeviceVector(ctx, n, hi) if hi is not None else None
+    return dlo, dhi
+
+
+def _box_project(ctx, dx, x, dlo, dhi):
+    if dlo is None and dhi is None:
+        return
+    from ._lib import check, lib
+    check(lib().lso_vec_box_project(ctx.handle, len(x), dx.ptr, x.ptr, dlo.ptr if dlo else None,
+                                    dhi.ptr if dhi else None), ctx.handle)
+
+
+def _maxabs_projected_gradient(ctx, g, x, dlo, dhi) -> float:
+    import ctypes as C
+    from ._lib import check, lib
+    out = C.c_double()
+    check(lib().lso_vec_maxabs_projected(ctx.handle, len(g), g.ptr, x.ptr, dlo.ptr if dlo else None,
+                                         dhi.ptr if dhi else None, C.byref(out)), ctx.handle)
+    return out.value
+
+
+def assess_convergence(dx: DeviceVector, maxabs_gr, ssr, trial_ssr, xtol, ftol, grtol, step_accepted):
+    """src/utils/utils.jl:7-31 — an if / elseif chain: at most one flag is set."""
+    x_c = f_c = g_c = False
+    if step_accepted and abs(trial_ssr - ssr) <= ftol * (abs(ssr) + ftol):
+        f_c = True
+    elif dx.maxabs() <= xtol:
+        x_c = True
+    elif maxabs_gr <= grtol:
+        g_c = True
+    return x_c, f_c, g_c, (x_c or f_c or g_c)
+
+
+def _lm_damping(ctx, dtd: DeviceVector, inv_delta: float):
+    from ._lib import check, lib
+    check(lib().lso_lm_damping(ctx.handle, len(dtd), dtd.ptr, MIN_DIAGONAL, MAX_DIAGONAL, inv_delta), ctx.handle)
+
+
+# ---- LevenbergMarquardt (levenberg_marquardt.jl:39-144) ----------------------------------------------------
+def _optimize_lm(anls: _Allocated, x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, iterations=1000, Δ=10.0, store_trace=False,
+                 lower=None, upper=None, record_steps=False):
+    ctx, n, m = anls.ctx, anls.n, anls.m
+    x, fcur, J = anls.x, anls.fcur, anls.J
+    dx, dtd = DeviceVector(ctx, n), DeviceVector(ctx, n)
+    ftrial, fpredict = DeviceVector(ctx, m), DeviceVector(ctx, m)
+    dlo, dhi = _bounds(ctx, x, lower, upper)
+    decrease_factor = 2.0
+    f_calls = g_calls = mul_calls = 0
+    converged = x_converged = f_converged = g_converged = False
+    anls.f(fcur, x)
+    f_calls += 1
+    ssr = fcur.sumabs2()
+    maxabs_gr = math.inf
+    need_jacobian = True
+    it = 0
+    tr = [OptimizationState(0, ssr, maxabs_gr)] if store_trace else []
+    deltas = []
+    while not converged and it < iterations:
+        it += 1
+        x.check_finite()
+        if need_jacobian:
+            anls.g(x)
+            g_calls += 1
+            need_jacobian = False
+        J.colsumabs2(dtd)                                 # :82
+        _lm_damping(ctx, dtd, 1 / Δ)                      # :84-86
+        _, lmiter = anls.solver.ldiv(dx, J, fcur, dtd)    # :87
+        if record_steps:
+            deltas.append(dx.download())
+        _box_project(ctx, dx, x, dlo, dhi)                # :89-98
+        mul_calls += lmiter
+        J.mul_t(dtd, fcur, 1.0, 0.0)                      # :102 gradient J'f
+        mul_calls += 1
+        maxabs_gr = _maxabs_projected_gradient(ctx, dtd, x, dlo, dhi)
+        x.axpy(-1.0, dx)                                  # :106
+        anls.f(ftrial, x)
+        f_calls += 1
+        trial_ssr = ftrial.sumabs2()
+        predicted_ssr = J.predicted_ssr(dx, fcur, fpredict)   # :114-117 fused
+        mul_calls += 1
+        predicted_reduction = abs(ssr - predicted_ssr)
+        ρ = (ssr - trial_ssr) / predicted_reduction if predicted_reduction > 0 else 0.0
+        step_accepted = ρ > MIN_STEP_QUALITY
+        x_converged, f_converged, g_converged, converged = assess_convergence(
+            dx, maxabs_gr, ssr, trial_ssr, x_tol, f_tol, g_tol, step_accepted)
+        if step_accepted:
+            fcur.copyto(ftrial)
+            ssr = trial_ssr
+            t = 2.0 * ρ - 1.0
+            Δ = min(Δ / max(1 / 3, 1.0 - t * t * t), MAX_DELTA)
+            decrease_factor = 2.0
+            need_jacobian = True
+        else:
+            x.axpy(1.0, dx)
+            Δ = max(Δ / decrease_factor, MIN_DELTA)
+            decrease_factor *= 2.0
+        if store_trace:
+            tr.append(OptimizationState(it, ssr, maxabs_gr))
+    xmin = anls.finish(x)
+    return LeastSquaresResult("LevenbergMarquardt", xmin, ssr, it, converged, x_converged, x_tol, f_converged,
+                              f_tol, g_converged, g_tol, tr, f_calls, g_calls, mul_calls, deltas)
+
+
+# ---- Dogleg (dogleg.jl:41-203) ---------------------------------------------------------------------------------
+def _optimize_dogleg(anls: _Allocated, x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, iterations=1000, Δ=1.0,
+                     store_trace=False, lower=None, upper=None, record_steps=False):
+    import ctypes as C
+    from ._lib import check, lib
+    ctx, n, m = anls.ctx, anls.n, anls.m
+    x, fcur, J = anls.x, anls.fcur, anls.J
+    dgn, dgr, dx, dtd = (DeviceVector(ctx, n) for _ in range(4))
+    ftrial, fpredict = DeviceVector(ctx, m), DeviceVector(ctx, m)
+    dlo, dhi = _bounds(ctx, x, lower, upper)
+    reuse = False
+    wnorm_dgn = wnorm_dgr = 0.0
+    α = 0.0
+    f_calls = g_calls = mul_calls = 0
+    converged = x_converged = f_converged = g_converged = False
+    anls.f(fcur, x)
+    f_calls += 1
+    ssr = fcur.sumabs2()
+    maxabs_gr = math.inf
+    it = 0
+    tr = [OptimizationState(0, ssr, maxabs_gr)] if store_trace else []
+    deltas = []
+    while not converged and it < iterations:
+        it += 1
+        x.check_finite()
+        if not reuse:
+            anls.g(x)
+            g_calls += 1
+            J.colsumabs2(dtd)                               # :85
+            dtd.clamp(MIN_DIAGONAL, MAX_DIAGONAL)           # :90  (absolute floor, unlike LM)
+            if it == 1:
+                wnorm_x = wnorm(x, dtd)
+                if wnorm_x > 0:
+                    Δ *= wnorm_x
+            J.mul_t(dgr, fcur, 1.0, 0.0)                    # :99
+            mul_calls += 1
+            maxabs_gr = _maxabs_projected_gradient(ctx, dgr, x, dlo, dhi)
+            dgr.div_(dgr, dtd)                              # :105  δgr = D⁻¹ g
+            wnorm_dgr = wnorm(dgr, dtd)
+            J.mul(fpredict, dgr, 1.0, 0.0)                  # :109
+            mul_calls += 1
+            denom = fpredict.sumabs2()
+            α = wnorm_dgr ** 2 / denom if denom != 0 else (math.nan if wnorm_dgr == 0 else math.inf)   # :111 (0/0 -> NaN)
+            dgn.fill(0.0)                                   # :114
+            _, ls_iter = anls.solver.ldiv(dgn, J, fcur)     # :115
+            if record_steps:
+                deltas.append(dgn.download())
+            mul_calls += ls_iter
+            wnorm_dgn = wnorm(dgn, dtd)
+        # δx: Gauss-Newton inside / scaled Cauchy / dogleg blend (:120-145)
+        out = C.c_double()
+        check(lib().lso_dogleg_blend(ctx.handle, n, dx.ptr, dgn.ptr, dgr.ptr, dtd.ptr, Δ, α, wnorm_dgn, wnorm_dgr,
+                                     C.byref(out)), ctx.handle)
+        wnorm_dx = out.value
+        _box_project(ctx, dx, x, dlo, dhi)                  # :148-157
+        x.axpy(-1.0, dx)                                    # :160
+        anls.f(ftrial, x)
+        f_calls += 1
+        trial_ssr = ftrial.sumabs2()
+        predicted_ssr = J.predicted_ssr(dx, fcur, fpredict)  # :171-174
+        mul_calls += 1
+        predicted_reduction = abs(ssr - predicted_ssr)
+        ρ = (ssr - trial_ssr) / predicted_reduction if predicted_reduction > 0 else 0.0
+        step_accepted = ρ >= MIN_STEP_QUALITY
+        x_converged, f_converged, g_converged, converged = assess_convergence(
+            dx, maxabs_gr, ssr, trial_ssr, x_tol, f_tol, g_tol, step_accepted)
+        if step_accepted:
+            reuse = False
+            fcur.copyto(ftrial)
+            ssr = trial_ssr
+        else:
+            reuse = True
+            x.axpy(1.0, dx)
+        if ρ < DECREASE_THRESHOLD:
+            Δ = max(MIN_DELTA, Δ * 0.5)
+        elif ρ > INCREASE_THRESHOLD:
+            Δ = max(Δ, 3.0 * wnorm_dx)
+        if store_trace:
+            tr.append(OptimizationState(it, ssr, maxabs_gr))
+    xmin = anls.finish(x)
+    return LeastSquaresResult("Dogleg", xmin, ssr, it, converged, x_converged, x_tol, f_converged, f_tol,
+                              g_converged, g_tol, tr, f_calls, g_calls, mul_calls, deltas)
+
+
+def optimize_(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, **kwargs) -> LeastSquaresResult:
+    """`optimize!(nls, optimizer; kwargs...)` — types.jl:207-209 + LeastSquaresProblemAllocated (:152-157)."""
+    solver = default_solver(optimizer.solver if optimizer is not None else None, nls.J)
+    optimizer = default_optimizer(optimizer, solver)
+    anls = _Allocated(nls, optimizer)
+    if isinstance(optimizer, LevenbergMarquardt):
+        return _optimize_lm(anls, **kwargs)
+    return _optimize_dogleg(anls, **kwargs)
+
+
+def optimize(f: Callable, x0, optimizer: AbstractOptimizer, **kwargs) -> LeastSquaresResult:
+    """`optimize(f, x, t)` — types.jl:182-184: wraps f into f!(out, x) = copyto!(out, f(x))."""
+    x0 = np.array(x0, dtype=np.float64)
+    m = np.atleast_1d(f(x0)).size
+
+    def f_(out, x):
+        out[:] = np.atleast_1d(f(x))
+
+    return optimize_(LeastSquaresProblem(x=x0.copy(), f_=f_, output_length=m), optimizer, **kwargs)

@@ -1,0 +1,421 @@
+// chol.cu — DenseCholeskyAllocatedSolver (src/solver/dense_cholesky.jl:29-59) on the device:
+//   C-a  syrk   cholm = J'J            (dense_cholesky.jl:31,48)  — fp64 tensor pipe (DMMA), split-K
+//        gemv   x = J'y                (dense_cholesky.jl:32,56)
+//   C-b  one NCCL all-reduce of [J'J | J'y] when J is row-sharded over ranks
+//   C-c  cholm[i,i] += damp[i] (:51-53), upper Cholesky (:33,57), two triangular solves
+#include "chol.cuh"
+#include "qr.cuh"
+#include <limits.h>
+
+// ---------------------------------------------------------------------------------------------------
+// syrk on the tensor pipe.  CTA tile 128 x 128 of C, 8 warps each 64 x 32 (8 x 4 DMMA accumulators),
+// K (rows of J) streamed in chunks of 16 through a 4-stage cp.async ring.  Both operands are slices of
+// J itself: column-major J makes them "K-major", so the 4x8 / 8x4 DMMA fragments are 4 consecutive
+// rows of 8 columns; the padded column stride SY_SK = 20 doubles spreads them over 16 distinct banks.
+// ---------------------------------------------------------------------------------------------------
+#define SY_TS 128
+#define SY_KC 16
+#define SY_SK 20
+#define SY_NST 4
+#define SY_STAGE_DOUBLES (2 * SY_TS * SY_SK)
+#define SY_SMEM_BYTES (SY_NST * SY_STAGE_DOUBLES * 8)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void dmma2(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void decode_pair(int p, int& bi, int& bj) {
+    int j = 0;
+    while ((j + 1) * (j + 2) / 2 <= p) ++j;
+    bj = j;
+    bi = p - j * (j + 1) / 2;
+}
+
+template <bool ALIGN16>
+__global__ void __launch_bounds__(256, 1)
+syrk_mma_kernel(long long m, long long n, const double* __restrict__ J, long long ld, long long rows_per_split,
+                double* __restrict__ out, long long ldc, long long slab_stride) {
+    extern __shared__ __align__(16) double sysm[];
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wi = wrp >> 2, wj = wrp & 3;
+    int bi, bj;
+    decode_pair(blockIdx.x, bi, bj);
+    const long long r_begin = (long long)blockIdx.y * rows_per_split;
+    long long r_end = r_begin + rows_per_split;
+    if (r_end > m) r_end = m;
+    const int niter = (r_end > r_begin) ? (int)((r_end - r_begin + SY_KC - 1) / SY_KC) : 0;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(sysm);
+
+    auto load_stage = [&](int it) {
+        const int s = it % SY_NST;
+        const long long rk = r_begin + (long long)it * SY_KC;
+        const uint32_t sbase = smem_base + (uint32_t)(s * SY_STAGE_DOUBLES) * 8u;
+        if (ALIGN16) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + 256 * u;
+                const int col = e >> 3, part = e & 7;
+                const int which = col >> 7, cc = col & 127;
+                const long long gcol = (long long)(which ? bj : bi) * SY_TS + cc;
+                const long long row = rk + 2 * part;
+                long long rem = (r_end - row) * 8;
+                int bytes = (gcol < n && rem > 0) ? (int)(rem > 16 ? 16 : rem) : 0;
+                const double* src = bytes ? (J + gcol * ld + row) : J;
+                cp_async16(sbase + (uint32_t)(which * SY_TS * SY_SK + cc * SY_SK + 2 * part) * 8u, src, bytes);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int e = tid + 256 * u;
+                const int col = e >> 4, part = e & 15;
+                const int which = col >> 7, cc = col & 127;
+                const long long gcol = (long long)(which ? bj : bi) * SY_TS + cc;
+                const long long row = rk + part;
+                int bytes = (gcol < n && row < r_end) ? 8 : 0;
+                const double* src = bytes ? (J + gcol * ld + row) : J;
+                cp_async8(sbase + (uint32_t)(which * SY_TS * SY_SK + cc * SY_SK + part) * 8u, src, bytes);
+            }
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < SY_NST - 1; ++s) {
+        if (s < niter) load_stage(s);
+        cp_async_commit();
+    }
+    for (int it = 0; it < niter; ++it) {
+        cp_async_wait<SY_NST - 2>();
+        __syncthreads();
+        if (it + SY_NST - 1 < niter) load_stage(it + SY_NST - 1);
+        cp_async_commit();
+        const double* As = sysm + (it % SY_NST) * SY_STAGE_DOUBLES;
+        const double* Bs = As + SY_TS * SY_SK;
+#pragma unroll
+        for (int ks = 0; ks < SY_KC / 4; ++ks) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = As[(64 * wi + 8 * mi + g) * SY_SK + 4 * ks + t];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(32 * wj + 8 * ni + g) * SY_SK + 4 * ks + t];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma2(acc[mi][ni], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    double* __restrict__ o = out + (long long)blockIdx.y * slab_stride;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        const long long i = (long long)bi * SY_TS + 64 * wi + 8 * mi + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const long long j = (long long)bj * SY_TS + 32 * wj + 8 * ni + 2 * t;
+            if (i < n) {
+                if (j < n) o[j * ldc + i] = acc[mi][ni][0];
+                if (j + 1 < n) o[(j + 1) * ldc + i] = acc[mi][ni][1];
+            }
+        }
+    }
+}
+
+// plain-FMA syrk (cross-check path; ctx option syrk = 0): 64 x 64 tile, 4 x 4 per thread
+__global__ void __launch_bounds__(256)
+syrk_fma_kernel(long long m, long long n, const double* __restrict__ J, long long ld, long long rows_per_split,
+                double* __restrict__ out, long long ldc, long long slab_stride) {
+    __shared__ double As[16][65], Bs[16][65];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    int bi, bj;
+    decode_pair(blockIdx.x, bi, bj);
+    const long long r_begin = (long long)blockIdx.y * rows_per_split;
+    long long r_end = r_begin + rows_per_split;
+    if (r_end > m) r_end = m;
+    double acc[4][4] = {};
+    for (long long rk = r_begin; rk < r_end; rk += 16) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u;
+            const int k = e & 15, c = e >> 4;
+            const long long row = rk + k;
+            const long long ca = (long long)bi * 64 + c, cb = (long long)bj * 64 + c;
+            As[k][c] = (row < r_end && ca < n) ? J[ca * ld + row] : 0.0;
+            Bs[k][c] = (row < r_end && cb < n) ? J[cb * ld + row] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[k][4 * ty + u]; b[u] = Bs[k][4 * tx + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+    }
+    double* __restrict__ o = out + (long long)blockIdx.y * slab_stride;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const long long i = (long long)bi * 64 + 4 * ty + u, j = (long long)bj * 64 + 4 * tx + v;
+            if (i < n && j < n) o[j * ldc + i] = acc[u][v];
+        }
+}
+
+__global__ void slab_reduce_kernel(long long count, int nslab, const double* __restrict__ part, long long slab_stride,
+                                   double* __restrict__ C) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        double a = 0.0;
+        for (int z = 0; z < nslab; ++z) a += part[z * slab_stride + i];
+        C[i] = a;
+    }
+}
+
+__global__ void add_diag_kernel(long long n, double* __restrict__ C, long long ldc, const double* __restrict__ damp) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) C[i * ldc + i] += damp[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// blocked right-looking upper Cholesky:  for each 32-column block k:
+//   panel kernel : R11 = chol(C11) (every CTA redundantly, one warp), R12 = R11^{-T} C12 (thread per column)
+//   update kernel: C22 -= R12' R12 on the upper 64 x 64 tiles
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+potrf_panel_kernel(int n, double* __restrict__ C, long long ldc, int k0, int* __restrict__ info) {
+    __shared__ double Dm[32][33];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = (n - k0 < 32) ? (n - k0) : 32;
+    for (int e = tid; e < 32 * 32; e += 256) {
+        const int r = e & 31, c = e >> 5;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < w && c < w && r <= c) v = C[(long long)(k0 + c) * ldc + k0 + r];
+        else if (r < w && c < w) v = 0.0;
+        Dm[r][c] = v;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        // lane = column c of the block
+        for (int j = 0; j < 32; ++j) {
+            double d = Dm[j][j];
+            if (j < w && !(d > 0.0)) {
+                if (blockIdx.x == 0 && lane == 0) atomicMin(info, k0 + j + 1);
+                d = 1.0;
+            }
+            d = sqrt(d);
+            __syncwarp();
+            if (lane == j) Dm[j][j] = d;
+            double rjc = 0.0;
+            if (lane > j) { rjc = Dm[j][lane] / d; Dm[j][lane] = rjc; }
+            __syncwarp();
+            if (lane > j) {
+                for (int i = j + 1; i <= lane; ++i) Dm[i][lane] = fma(-Dm[j][i], rjc, Dm[i][lane]);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int e = tid; e < 32 * 32; e += 256) {
+            const int r = e & 31, c = e >> 5;
+            if (r < w && c < w && r <= c) C[(long long)(k0 + c) * ldc + k0 + r] = Dm[r][c];
+        }
+    }
+    const int c = k0 + w + blockIdx.x * 256 + tid;
+    if (c < n) {
+        double* __restrict__ col = C + (long long)c * ldc + k0;
+        double y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = (j < w) ? col[j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            double a = y[j];
+#pragma unroll
+            for (int i = 0; i < j; ++i) a = fma(-Dm[i][j], y[i], a);
+            y[j] = a / Dm[j][j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < w) col[j] = y[j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+potrf_update_kernel(int n, double* __restrict__ C, long long ldc, int k0, int w) {
+    __shared__ double Ri[32][65], Rj[32][65];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    int bi, bj;
+    decode_pair(blockIdx.x, bi, bj);
+    const int t0 = k0 + w;
+    const int i0 = t0 + bi * 64, j0 = t0 + bj * 64;
+    for (int e = tid; e < 32 * 64; e += 256) {
+        const int k = e & 31, c = e >> 5;
+        Ri[k][c] = (k < w && i0 + c < n) ? C[(long long)(i0 + c) * ldc + k0 + k] : 0.0;
+        Rj[k][c] = (k < w && j0 + c < n) ? C[(long long)(j0 + c) * ldc + k0 + k] : 0.0;
+    }
+    __syncthreads();
+    double acc[4][4] = {};
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = Ri[k][4 * ty + u]; b[u] = Rj[k][4 * tx + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + 4 * ty + u, j = j0 + 4 * tx + v;
+            if (i < n && j < n && i <= j) C[(long long)j * ldc + i] -= acc[u][v];
+        }
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p) {
+    *p = CholPlan();
+    LSO_REQUIRE(ctx, n <= 46000, "Cholesky path: n too large");
+    p->n = n;
+    p->ldc = roundup64(n, 32);
+    size_t cbytes = (size_t)(p->ldc * n + roundup64(n, 32)) * sizeof(double);
+    cudaError_t e = cudaMalloc(&p->C, cbytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return lso_set_error(ctx, LSO_ERR_ALLOC, "Cholesky workspace: cudaMalloc(%zu): %s", cbytes, cudaGetErrorString(e));
+    }
+    LSO_CHECK_CUDA(ctx, cudaMemsetAsync(p->C, 0, cbytes, ctx->stream));
+    p->rhs = p->C + p->ldc * n;
+    int64_t ntb = cdiv64(n, SY_TS);
+    int64_t pairs = ntb * (ntb + 1) / 2;
+    int64_t ksplit = ctx->num_sms / pairs;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 8) ksplit = 8;
+    p->part_cap = ksplit > 1 ? ksplit : 0;
+    if (p->part_cap) {
+        size_t pb = (size_t)p->part_cap * p->ldc * n * sizeof(double);
+        e = cudaMalloc(&p->part, pb);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return lso_set_error(ctx, LSO_ERR_ALLOC, "syrk split-K workspace: cudaMalloc(%zu): %s", pb, cudaGetErrorString(e));
+        }
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(p->part, 0, pb, ctx->stream));
+    }
+    LSO_CHECK_CUDA(ctx, cudaMalloc(&p->d_info, sizeof(int)));
+    static bool attr_done = false;
+    if (!attr_done) {
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(syrk_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(syrk_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+        attr_done = true;
+    }
+    return LSO_OK;
+}
+
+void chol_plan_destroy(CholPlan* p) {
+    if (!p) return;
+    cudaFree(p->C);
+    cudaFree(p->part);
+    cudaFree(p->d_info);
+    *p = CholPlan();
+}
+
+int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld) {
+    const int64_t slab = p->ldc * n;
+    int64_t ksplit = p->part_cap > 1 ? p->part_cap : 1;
+    // keep every split at least a few chunks long
+    while (ksplit > 1 && cdiv64(m, ksplit) < 4 * SY_KC) --ksplit;
+    int64_t rows_per_split = roundup64(cdiv64(m, ksplit), SY_KC);
+    ksplit = cdiv64(m, rows_per_split);
+    if (ksplit < 1) ksplit = 1;
+    double* out = (ksplit > 1) ? p->part : p->C;
+    if (ctx->opt_syrk) {
+        int64_t ntb = cdiv64(n, SY_TS);
+        dim3 grid((unsigned)(ntb * (ntb + 1) / 2), (unsigned)ksplit);
+        const bool al = (((uintptr_t)d_J & 15) == 0) && (ld % 2 == 0);
+        if (al) syrk_mma_kernel<true><<<grid, 256, SY_SMEM_BYTES, ctx->stream>>>(m, n, d_J, ld, rows_per_split, out, p->ldc, slab);
+        else syrk_mma_kernel<false><<<grid, 256, SY_SMEM_BYTES, ctx->stream>>>(m, n, d_J, ld, rows_per_split, out, p->ldc, slab);
+    } else {
+        int64_t ntb = cdiv64(n, 64);
+        dim3 grid((unsigned)(ntb * (ntb + 1) / 2), (unsigned)ksplit);
+        syrk_fma_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, d_J, ld, rows_per_split, out, p->ldc, slab);
+    }
+    LSO_CHECK_LAUNCH(ctx);
+    if (ksplit > 1) {
+        int64_t g = cdiv64(slab, 256);
+        if (g > (int64_t)ctx->num_sms * 8) g = (int64_t)ctx->num_sms * 8;
+        slab_reduce_kernel<<<(unsigned)g, 256, 0, ctx->stream>>>(slab, (int)ksplit, p->part, slab, p->C);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    return LSO_OK;
+}
+
+int potrf_upper(lso_ctx* ctx, CholPlan* p, int* info_out) {
+    const int n = (int)p->n;
+    set_int_kernel<<<1, 1, 0, ctx->stream>>>(p->d_info, INT_MAX);
+    LSO_CHECK_LAUNCH(ctx);
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int w = (n - k0 < 32) ? (n - k0) : 32;
+        const int rest = n - k0 - w;
+        int g = rest > 0 ? (rest + 255) / 256 : 1;
+        potrf_panel_kernel<<<g, 256, 0, ctx->stream>>>(n, p->C, p->ldc, k0, p->d_info);
+        LSO_CHECK_LAUNCH(ctx);
+        if (rest > 0) {
+            int nt = (rest + 63) / 64;
+            potrf_update_kernel<<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(n, p->C, p->ldc, k0, w);
+            LSO_CHECK_LAUNCH(ctx);
+        }
+    }
+    int info = 0;
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(&info, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *info_out = (info == INT_MAX) ? 0 : info;
+    return LSO_OK;
+}
+
+extern "C" int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count);
+extern "C" int lso_dense_gemv_t(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const double* d_J, int64_t ld,
+                                const double* d_y, double beta, double* d_x);
+
+int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
+               const double* d_damp, double* d_x) {
+    LSO_TRY(syrk_upper(ctx, p, m, n, d_J, ld));                               // mul!(cholm, J', J)
+    LSO_TRY(lso_dense_gemv_t(ctx, m, n, 1.0, d_J, ld, d_y, 0.0, p->rhs));      // mul!(x, J', y)
+    if (ctx->nranks > 1) LSO_TRY(lso_comm_allreduce_sum(ctx, p->C, p->ldc * n + n));
+    if (d_damp) {                                                             // cholm[i,i] += damp[i]
+        add_diag_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, ctx->stream>>>(n, p->C, p->ldc, d_damp);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    int info = 0;
+    LSO_TRY(potrf_upper(ctx, p, &info));
+    if (info > 0) {
+        lso_set_error(ctx, info, d_damp ? "PosDefException: matrix is not positive definite; Cholesky factorization failed (info=%d)"
+                                        : "RankDeficientException(%d)", info);
+        return info;
+    }
+    LSO_TRY(tri_solve(ctx, n, p->C, p->ldc, p->rhs, d_x, 1));   // R' z = J'y
+    LSO_TRY(tri_solve(ctx, n, p->C, p->ldc, d_x, d_x, 0));      // R x = z
+    return LSO_OK;
+}

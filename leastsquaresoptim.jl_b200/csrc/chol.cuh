@@ -1,0 +1,22 @@
+// chol.cuh — normal-equations path: J'J (syrk) + Cholesky + two triangular solves.
+#pragma once
+#include "common.cuh"
+
+struct CholPlan {
+    int64_t n = 0;
+    int64_t ldc = 0;          // roundup(n, 32)
+    double* C = nullptr;      // ldc x n : J'J (+damp), overwritten by the upper factor R (R'R = C)
+    double* rhs = nullptr;    // n : J'y.  C and rhs are contiguous ([C | rhs]) so one all-reduce covers both
+    double* part = nullptr;   // split-K partial tiles
+    int64_t part_cap = 0;     // number of n*ldc slabs available in part
+    int* d_info = nullptr;
+};
+
+int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p);
+void chol_plan_destroy(CholPlan* p);
+int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
+               const double* d_damp, double* d_x);
+// C (upper tiles) = J'J for the m x n column-major J
+int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld);
+// in-place upper Cholesky of p->C ; returns LAPACK info (0 ok, k>0: leading minor k not positive definite)
+int potrf_upper(lso_ctx* ctx, CholPlan* p, int* info_out);

@@ -1,0 +1,112 @@
+// common.cuh — context, error plumbing and device-side reduction helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "../../include/lsob200.h"
+
+#define LSO_NUM_SMS_DEFAULT 148
+
+struct lso_ctx {
+    int device = 0;
+    int num_sms = LSO_NUM_SMS_DEFAULT;
+    cudaStream_t stream = nullptr;
+    // scratch for two-stage deterministic reductions
+    double* d_partials = nullptr;      // LSO_PARTIALS doubles
+    unsigned int* d_counters = nullptr; // ticket counters for last-block reductions (zeroed)
+    double* d_scalars = nullptr;       // small device scalar slots
+    double* h_scalars = nullptr;       // pinned mirror
+    int64_t launches = 0;
+    std::string last_error;
+    // options
+    int64_t opt_qr_apply = 1;          // 0 = plain-FMA apply kernel, 1 = DMMA apply kernel
+    int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
+    // NCCL (lazily loaded)
+    void* nccl_comm = nullptr;
+    int nranks = 1;
+    int rank = 0;
+};
+
+#define LSO_PARTIALS (1 << 20)
+#define LSO_NSCALARS 256
+
+extern std::string g_lso_last_error;
+
+int lso_set_error(lso_ctx* ctx, int code, const char* fmt, ...);
+
+#define LSO_CHECK_CUDA(ctx, expr)                                                               \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return lso_set_error((ctx), LSO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define LSO_CHECK_LAUNCH(ctx)                                                                   \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return lso_set_error((ctx), LSO_ERR_CUDA, "kernel launch failed: %s (%s:%d)",       \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define LSO_REQUIRE(ctx, cond, msg)                                                             \
+    do {                                                                                        \
+        if (!(cond)) return lso_set_error((ctx), LSO_ERR_ARG, "%s (%s:%d)", msg, __FILE__, __LINE__); \
+    } while (0)
+
+#define LSO_TRY(expr)                                                                           \
+    do {                                                                                        \
+        int _s = (expr);                                                                        \
+        if (_s != 0) return _s;                                                                 \
+    } while (0)
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t roundup64(int64_t a, int64_t b) { return cdiv64(a, b) * b; }
+
+#ifdef __CUDACC__
+// ---- warp / block reductions (fixed order => deterministic) ------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// NaN-propagating max of |x| (Julia's maximum(abs, x) returns NaN if any element is NaN)
+__device__ __forceinline__ double nanmax(double a, double b) {
+    return (a != a) ? a : ((b != b) ? b : (a > b ? a : b));
+}
+__device__ __forceinline__ double warp_nanmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Block-wide sum; result valid in thread 0 (and all threads of warp 0). blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* sm /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect sm reuse
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+__device__ __forceinline__ double block_nanmax(double v, double* sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_nanmax(v);
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_nanmax(v);
+    return v;
+}
+#endif

@@ -1,0 +1,302 @@
+// dense_solve.cu — the two dense `AbstractAllocatedSolver`s of the reference behind the C ABI:
+//   DenseQRAllocatedSolver        src/solver/dense_qr.jl:6-88
+//   DenseCholeskyAllocatedSolver  src/solver/dense_cholesky.jl:7-59
+#include "qr.cuh"
+#include "chol.cuh"
+
+struct lso_dense_ws {
+    lso_ctx* ctx = nullptr;
+    int64_t m = 0, n = 0;
+    int kind = 0;
+    int damped = 0;
+    // QR
+    QRPlan plan;          // local factorisation of [J; sqrt(D) | y; 0]
+    QRPlan plan_stack;    // multi-GPU: QR of the stacked R factors (created on first sharded solve)
+    bool have_stack = false;
+    double* d_gather = nullptr;   // multi-GPU: nranks * (n x (n+1)) gathered [R | Q'y]
+    // Cholesky
+    CholPlan chol;
+    // host-buffer staging
+    double* d_J = nullptr;
+    double* d_y = nullptr;
+    double* d_damp = nullptr;
+    double* d_x = nullptr;
+    int last_rank = 0;
+};
+
+// ---- Q-a: build [J; diag(sqrt(damp)) | y; 0] in the padded workspace (dense_qr.jl:32-36, 64-80) ----
+__global__ void qr_assemble_kernel(long long m, long long n, long long M, const double* __restrict__ J, long long ldJ,
+                                   const double* __restrict__ y, const double* __restrict__ damp,
+                                   double* __restrict__ A, long long ld, long long Npad) {
+    const long long col = blockIdx.y;
+    double* __restrict__ dst = A + col * ld;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < ld; r += (long long)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (col < n) {
+            if (r < m) v = J[col * ldJ + r];
+            else if (damp != nullptr && r == m + col) v = sqrt(damp[col]);
+        } else if (col == Npad) {
+            if (r < m) v = y[r];
+        }
+        dst[r] = v;
+    }
+}
+
+__global__ void extract_rhs_kernel(long long n, const double* __restrict__ A, long long ld, long long Npad,
+                                   double* __restrict__ c) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) c[i] = A[Npad * ld + i];
+}
+
+// min/max of |R_ii| : cheap screen for numerical rank deficiency of the unpivoted factor
+__global__ void diag_minmax_kernel(int n, const double* __restrict__ R, long long ld, double* __restrict__ out) {
+    __shared__ double smn[32], smx[32];
+    double mn = INFINITY, mx = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = fabs(R[(long long)i * ld + i]);
+        if (!(v >= 0.0)) v = 0.0;   // NaN -> 0 => flagged
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fmin(mn, smn[w]); mx = fmax(mx, smx[w]); }
+        out[0] = mn;
+        out[1] = mx;
+    }
+}
+
+static int qr_assemble(lso_ctx* ctx, QRPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ldJ, const double* d_y,
+                       const double* d_damp) {
+    dim3 grid((unsigned)std::min<int64_t>(cdiv64(p->ld, 256), 64), (unsigned)p->Nc);
+    qr_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, p->M, d_J, ldJ, d_y, d_damp, p->A, p->ld, p->Npad);
+    LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}
+
+int small_qr_finish(lso_ctx* ctx, int64_t n, double* d_R, int64_t ld, double* d_c, double* d_x, int* rank_out);
+
+// R (n x n upper, in plan->A) and c = Q'y (column Npad) -> x.  Full-rank fast path: back substitution.
+static int qr_finish(lso_dense_ws* ws, QRPlan* p, double* d_x, int* rank_out) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    double* c = p->A + p->Npad * p->ld;
+    // screen: the reference's pivoted QR + incremental condition estimation declares rank deficiency when
+    // cond(R(1:k,1:k)) > 1/(min(rows,cols)*eps).  max|r_ii|/min|r_ii| is a lower bound of cond(R); when it is
+    // comfortably below that threshold the matrix is treated as full rank; otherwise take the pivoted,
+    // rank-revealing small-R finish (Q-d), which reproduces the reference's minimum-norm solution.
+    diag_minmax_kernel<<<1, 256, 0, ctx->stream>>>((int)n, p->A, p->ld, ctx->d_scalars + 8);
+    LSO_CHECK_LAUNCH(ctx);
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 8, ctx->d_scalars + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double mn = ctx->h_scalars[8], mx = ctx->h_scalars[9];
+    const double rcond = (double)std::min<int64_t>(p->M, n) * 2.220446049250313e-16;
+    const bool suspicious = !(mn > 1e3 * rcond * mx);   // also true for NaN / zero matrix
+    if (!suspicious) {
+        LSO_TRY(tri_solve(ctx, n, p->A, p->ld, c, d_x, 0));
+        ws->last_rank = (int)n;
+        if (rank_out) *rank_out = (int)n;
+        return LSO_OK;
+    }
+    int rk = 0;
+    LSO_TRY(small_qr_finish(ctx, n, p->A, p->ld, c, d_x, &rk));
+    ws->last_rank = rk;
+    if (rank_out) *rank_out = rk;
+    return LSO_OK;
+}
+
+extern "C" {
+
+int lso_dense_ws_create(lso_ctx* ctx, int64_t m, int64_t n, int solver_kind, int damped, lso_dense_ws** out) {
+    LSO_REQUIRE(ctx, ctx && out, "ctx/out is NULL");
+    *out = nullptr;
+    LSO_REQUIRE(ctx, m >= 1 && n >= 1, "m and n must be positive");
+    LSO_REQUIRE(ctx, solver_kind == LSO_SOLVER_QR || solver_kind == LSO_SOLVER_CHOLESKY, "unknown solver kind");
+    LSO_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    lso_dense_ws* ws = new (std::nothrow) lso_dense_ws();
+    if (!ws) return lso_set_error(ctx, LSO_ERR_ALLOC, "host allocation failed");
+    ws->ctx = ctx; ws->m = m; ws->n = n; ws->kind = solver_kind; ws->damped = damped;
+    int st = LSO_OK;
+    if (solver_kind == LSO_SOLVER_QR) {
+        // LM: (m+n) x n augmented system (dense_qr.jl:50-54); Dogleg: m x n (dense_qr.jl:25-28)
+        st = qr_plan_create(ctx, damped ? m + n : m, n, &ws->plan);
+    } else {
+        st = chol_plan_create(ctx, n, &ws->chol);
+    }
+    if (st != LSO_OK) { lso_dense_ws_destroy(ws); return st; }
+    *out = ws;
+    return LSO_OK;
+}
+
+int lso_dense_ws_destroy(lso_dense_ws* ws) {
+    if (!ws) return LSO_OK;
+    lso_ctx* ctx = ws->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    qr_plan_destroy(&ws->plan);
+    if (ws->have_stack) qr_plan_destroy(&ws->plan_stack);
+    chol_plan_destroy(&ws->chol);
+    cudaFree(ws->d_gather);
+    cudaFree(ws->d_J); cudaFree(ws->d_y); cudaFree(ws->d_damp); cudaFree(ws->d_x);
+    delete ws;
+    return LSO_OK;
+}
+
+int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
+                 double* d_x, int* rank_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR, "workspace was not created for QR");
+    LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
+    LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
+    // dense_qr.jl:61 — the damped form needs the (m+n)-row workspace, the undamped form the m-row one
+    LSO_REQUIRE(ctx, (d_damp != nullptr) == (ws->damped != 0), "length(u) should equal length(x) + length(y)");
+    LSO_REQUIRE(ctx, ws->plan.M >= ws->n, "QR path requires rows >= columns (underdetermined systems are not supported)");
+    LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, ws->n, d_J, ld, d_y, d_damp));
+    LSO_TRY(qr_factor(ctx, &ws->plan));
+    return qr_finish(ws, &ws->plan, d_x, rank_out);
+}
+
+static int ensure_staging(lso_dense_ws* ws, int64_t ld) {
+    lso_ctx* ctx = ws->ctx;
+    if (!ws->d_J) {
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_J, (size_t)ws->m * ws->n * sizeof(double)));
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_y, (size_t)ws->m * sizeof(double)));
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_damp, (size_t)ws->n * sizeof(double)));
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_x, (size_t)ws->n * sizeof(double)));
+    }
+    (void)ld;
+    return LSO_OK;
+}
+
+int lso_qr_solve_host(lso_dense_ws* ws, const double* h_J, int64_t ld, const double* h_y, const double* h_damp,
+                      double* h_x, int* rank_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, h_J && h_y && h_x, "NULL pointer");
+    LSO_TRY(ensure_staging(ws, ld));
+    LSO_TRY(lso_upload_matrix(ctx, ws->d_J, ws->m, h_J, ld, ws->m, ws->n));
+    LSO_TRY(lso_upload_async(ctx, ws->d_y, h_y, ws->m * sizeof(double)));
+    if (h_damp) LSO_TRY(lso_upload_async(ctx, ws->d_damp, h_damp, ws->n * sizeof(double)));
+    LSO_TRY(lso_qr_solve(ws, ws->d_J, ws->m, ws->d_y, h_damp ? ws->d_damp : nullptr, ws->d_x, rank_out));
+    return lso_download(ctx, h_x, ws->d_x, ws->n * sizeof(double));
+}
+
+int lso_chol_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
+                   double* d_x) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_CHOLESKY, "workspace was not created for Cholesky");
+    LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
+    LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
+    return chol_solve(ctx, &ws->chol, ws->m, ws->n, d_J, ld, d_y, d_damp, d_x);
+}
+
+int lso_chol_solve_host(lso_dense_ws* ws, const double* h_J, int64_t ld, const double* h_y, const double* h_damp,
+                        double* h_x) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, h_J && h_y && h_x, "NULL pointer");
+    LSO_TRY(ensure_staging(ws, ld));
+    LSO_TRY(lso_upload_matrix(ctx, ws->d_J, ws->m, h_J, ld, ws->m, ws->n));
+    LSO_TRY(lso_upload_async(ctx, ws->d_y, h_y, ws->m * sizeof(double)));
+    if (h_damp) LSO_TRY(lso_upload_async(ctx, ws->d_damp, h_damp, ws->n * sizeof(double)));
+    int st = lso_chol_solve(ws, ws->d_J, ws->m, ws->d_y, h_damp ? ws->d_damp : nullptr, ws->d_x);
+    if (st != LSO_OK) return st;
+    return lso_download(ctx, h_x, ws->d_x, ws->n * sizeof(double));
+}
+
+int lso_dense_ws_get_factor(lso_dense_ws* ws, double* h_R) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, h_R != nullptr, "NULL pointer");
+    const int64_t n = ws->n;
+    const double* src = (ws->kind == LSO_SOLVER_QR) ? ws->plan.A : ws->chol.C;
+    const int64_t ld = (ws->kind == LSO_SOLVER_QR) ? ws->plan.ld : ws->chol.ldc;
+    LSO_CHECK_CUDA(ctx, cudaMemcpy2DAsync(h_R, n * sizeof(double), src, ld * sizeof(double), n * sizeof(double), n,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t i = j + 1; i < n; ++i) h_R[j * n + i] = 0.0;
+    return LSO_OK;
+}
+
+// ---- multi-GPU QR: TSQR over row shards ----------------------------------------------------------
+int lso_comm_allgather(lso_ctx* ctx, const double* d_send, double* d_recv, int64_t count);
+
+__global__ void pack_R_kernel(long long n, const double* __restrict__ A, long long ld, long long Npad,
+                              double* __restrict__ out /* n x (n+1), ld = n */) {
+    const long long col = blockIdx.y;   // 0..n  (n = rhs)
+    const long long src_col = (col < n) ? col : Npad;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        double v = A[src_col * ld + r];
+        if (col < n && r > col) v = 0.0;
+        out[col * n + r] = v;
+    }
+}
+
+// stack: rows [k*n, (k+1)*n) = R_k ; rows [P*n, P*n + n) = diag(sqrt(damp)); rhs column = [c_0; ...; c_{P-1}; 0]
+__global__ void stack_assemble_kernel(long long n, int P, const double* __restrict__ gathered,
+                                      const double* __restrict__ damp, double* __restrict__ A, long long ld,
+                                      long long Npad) {
+    const long long col = blockIdx.y;
+    double* __restrict__ dst = A + col * ld;
+    const long long rowsR = (long long)P * n;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < ld; r += (long long)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (col < n || col == Npad) {
+            const long long scol = (col < n) ? col : n;
+            if (r < rowsR) {
+                const long long k = r / n, rr = r - k * n;
+                v = gathered[k * n * (n + 1) + scol * n + rr];
+            } else if (col < n && damp != nullptr && r == rowsR + col) {
+                v = sqrt(damp[col]);
+            }
+        }
+        dst[r] = v;
+    }
+}
+
+int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
+                         double* d_x, int* rank_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    if (ctx->nranks <= 1) return lso_qr_solve(ws, d_J, ld, d_y, d_damp, d_x, rank_out);
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR, "workspace was not created for QR");
+    LSO_REQUIRE(ctx, ws->damped == 0, "sharded QR: create the workspace with damped = 0 (damping rows join the stack)");
+    LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
+    LSO_REQUIRE(ctx, ws->m >= ws->n, "sharded QR: each shard needs rows >= columns");
+    const int64_t n = ws->n;
+    const int P = ctx->nranks;
+    if (!ws->have_stack) {
+        LSO_TRY(qr_plan_create(ctx, (int64_t)P * n + n, n, &ws->plan_stack));
+        ws->have_stack = true;
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_gather, (size_t)(P + 1) * n * (n + 1) * sizeof(double)));
+    }
+    // local QR of [J_k | y_k]
+    LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, n, d_J, ld, d_y, nullptr));
+    LSO_TRY(qr_factor(ctx, &ws->plan));
+    double* sendbuf = ws->d_gather + (size_t)P * n * (n + 1);
+    {
+        dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 64), (unsigned)(n + 1));
+        pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, ws->plan.A, ws->plan.ld, ws->plan.Npad, sendbuf);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    LSO_TRY(lso_comm_allgather(ctx, sendbuf, ws->d_gather, n * (n + 1)));
+    {
+        QRPlan* ps = &ws->plan_stack;
+        dim3 grid((unsigned)std::min<int64_t>(cdiv64(ps->ld, 256), 64), (unsigned)ps->Nc);
+        stack_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(n, P, ws->d_gather, d_damp, ps->A, ps->ld, ps->Npad);
+        LSO_CHECK_LAUNCH(ctx);
+        LSO_TRY(qr_factor(ctx, ps));
+    }
+    return qr_finish(ws, &ws->plan_stack, d_x, rank_out);
+}
+
+}  // extern "C"

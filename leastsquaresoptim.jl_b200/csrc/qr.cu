@@ -1,0 +1,716 @@
+// qr.cu — communication-avoiding blocked Householder QR for tall dense systems (Q-a..Q-d in
+// SURVEY.md Appendix B).  Replaces `ldiv!(qr!(qrm, ColumnNorm()), u)` at
+// src/solver/dense_qr.jl:37,83 for the full-rank case (the damped LM system is full rank by
+// construction, levenberg_marquardt.jl:85).
+//
+// Only R and Q'b are needed for the least-squares solve, so the right-hand side rides along as an
+// extra column and V is discarded after each panel:
+//   for each panel of QB columns:
+//     level 0 : every QH-row block is factorised independently by one CTA (leaf kernel, registers)
+//     level l : the QB-row heads (R factors) of QG blocks of level l-1 are stacked and factorised
+//               the same way (TSQR reduction tree), until one R remains
+//     then every level's block reflectors  I - V T' V'  are applied to the trailing columns, one
+//     pass over the trailing matrix per level (level 0 touches every row once; level l touches
+//     1/QG^l of the rows).  No global reduction, no grid-wide sync.
+// The trailing update is the flop carrier (4*QB flop per 8-byte element) and runs on the fp64
+// tensor pipe (mma.sync m8n8k4 -> DMMA), fed by cp.async.bulk (TMA unit, UBLKCP) through an mbarrier
+// ring with a dedicated producer warp.  tcgen05.mma has no f64 kind, see DESIGN.md.
+#include "qr.cuh"
+#include <math.h>
+
+struct TileMap {
+    long long r0;          // first active matrix row of this panel
+    long long seg_stride;  // matrix rows between consecutive items
+    long long n_items;     // items available at this level
+    int seg_shift;         // log2(rows per segment): 8 (level 0: one 256-row segment) or 5 (heads)
+    int nseg;              // segments per block: 1 or QG
+};
+
+__device__ __forceinline__ bool tm_row(const TileMap& tm, long long blk, int p, long long& mrow) {
+    const int q = p >> tm.seg_shift;
+    const int t = p - (q << tm.seg_shift);
+    const long long item = blk * tm.nseg + q;
+    mrow = tm.r0 + item * tm.seg_stride + t;
+    return item < tm.n_items;
+}
+
+// =================================================================================================
+// leaf kernel: Householder QR of one QH x QB block.  256 threads: lane = column, warp = 32-row group,
+// each thread keeps its 32 column entries in registers.
+// =================================================================================================
+#define LEAF_XS (QH + 1)
+#define LEAF_SMEM_BYTES ((QB * LEAF_XS + 2 * QH + 2 * QB + 8 * QB + QB + QB * 33 + QB + QB * 33) * 8)
+
+template <bool MASKED>
+__device__ __forceinline__ void leaf_step(double (&x)[32], int j, int lane, int grp, const double* colbuf,
+                                          const double* rowbuf, double* red, double* zbuf, double* taus) {
+    // masked pivot column: rows r > j participate in the reflector
+    double pc[32];
+    double d = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double v = colbuf[grp * 32 + i];
+        if (MASKED) v = (i > j) ? v : 0.0;
+        pc[i] = v;
+        d = fma(v, x[i], d);
+    }
+    red[grp * 32 + lane] = d;
+    __syncthreads();   // S2
+    double s_k = 0.0, s_j = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        s_k += red[g * 32 + lane];
+        s_j += red[g * 32 + j];
+    }
+    const double alpha = colbuf[j];
+    const double rowk = rowbuf[lane];
+    double beta, tau, scale;
+    if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
+        beta = alpha; tau = 0.0; scale = 0.0;
+    } else {
+        beta = -copysign(sqrt(fma(alpha, alpha, s_j)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+    const double wz = fma(scale, s_k, rowk);    // v_j' a_k  (k > j)   or   v_k' v_j (k < j)
+    if (lane > j) {
+        const double coef = tau * wz;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            double vf = pc[i] * scale;
+            if (MASKED) vf = (i == j) ? 1.0 : vf;
+            x[i] = fma(-coef, vf, x[i]);
+        }
+    } else if (lane == j) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (MASKED) x[i] = (i > j) ? pc[i] * scale : ((i == j) ? beta : x[i]);
+            else x[i] = pc[i] * scale;
+        }
+        if (grp == 0) taus[j] = tau;
+    } else if (grp == 0) {
+        zbuf[lane] = wz;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
+               double* __restrict__ Tout) {
+    extern __shared__ double lsm[];
+    double* Xs = lsm;                      // [QB][LEAF_XS]
+    double* colbuf = Xs + QB * LEAF_XS;    // [2][QH]
+    double* rowbuf = colbuf + 2 * QH;      // [2][QB]
+    double* red = rowbuf + 2 * QB;         // [8][QB]
+    double* zbuf = red + 8 * QB;           // [QB]
+    double* Ts = zbuf + QB;                // [QB][33]   Ts[i*33 + k] = T[k][i]  (column i of T)
+    double* taus = Ts + QB * 33;           // [QB]
+    double* Rs = taus + QB;                // [QB][33]   Rs[r*33 + k]
+
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+    const long long blk = blockIdx.x;
+
+    // ---- gather the block (coalesced along rows) ----
+    for (int col = grp; col < QB; col += 8) {
+        const double* __restrict__ src = A + (c0 + col) * ld;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int p = q * 32 + lane;
+            long long mrow;
+            const bool ok = tm_row(tm, blk, p, mrow);
+            Xs[col * LEAF_XS + p] = ok ? src[mrow] : 0.0;
+        }
+    }
+    for (int i = tid; i < QB * 33; i += 256) Ts[i] = 0.0;
+    __syncthreads();
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = Xs[lane * LEAF_XS + grp * 32 + i];
+
+    // ---- QB Householder steps ----
+    for (int j = 0; j < QB; ++j) {
+        double* cb = colbuf + (j & 1) * QH;
+        double* rb = rowbuf + (j & 1) * QB;
+        if (lane == j) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cb[grp * 32 + i] = x[i];
+        }
+        if (grp == 0) {
+            double xj = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xj = (i == j) ? x[i] : xj;
+            rb[lane] = xj;
+        }
+        __syncthreads();   // S1
+        // T column j-1 (larft): T[0:jm, jm] = -tau_jm * T[0:jm,0:jm] * (V[:,0:jm]' v_jm)
+        if (grp == 7 && j > 0) {
+            const int jm = j - 1;
+            const double tj = taus[jm];
+            if (lane < jm) {
+                double acc = 0.0;
+                for (int i = lane; i < jm; ++i) acc = fma(Ts[i * 33 + lane], zbuf[i], acc);
+                Ts[jm * 33 + lane] = -tj * acc;
+            } else if (lane == jm) {
+                Ts[jm * 33 + jm] = tj;
+            }
+        }
+        if (grp == 0) leaf_step<true>(x, j, lane, grp, cb, rb, red, zbuf, taus);
+        else leaf_step<false>(x, j, lane, grp, cb, rb, red, zbuf, taus);
+    }
+    __syncthreads();
+    if (grp == 7) {
+        const int jm = QB - 1;
+        const double tj = taus[jm];
+        if (lane < jm) {
+            double acc = 0.0;
+            for (int i = lane; i < jm; ++i) acc = fma(Ts[i * 33 + lane], zbuf[i], acc);
+            Ts[jm * 33 + lane] = -tj * acc;
+        } else if (lane == jm) {
+            Ts[jm * 33 + jm] = tj;
+        }
+    }
+    // ---- stage V (explicit unit diagonal, zeros above) and R ----
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int r = grp * 32 + i;
+        Xs[lane * LEAF_XS + r] = (r > lane) ? x[i] : ((r == lane) ? 1.0 : 0.0);
+        if (grp == 0) Rs[i * 33 + lane] = (i <= lane) ? x[i] : 0.0;
+    }
+    __syncthreads();
+    double* __restrict__ Vb = Vout + blk * (long long)(QB * QS);
+    for (int col = grp; col < QB; col += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int p = q * 32 + lane;
+            Vb[col * QS + p] = Xs[col * LEAF_XS + p];
+        }
+        // head of the block: R in the upper triangle, zeros below
+        long long mrow;
+        const bool ok = tm_row(tm, blk, lane, mrow);
+        if (ok) A[(c0 + col) * ld + mrow] = Rs[lane * 33 + col];
+    }
+    double* __restrict__ Tb = Tout + blk * (long long)(QB * QB);
+    for (int e = tid; e < QB * QB; e += 256) {
+        const int k = e & 31, i = e >> 5;       // T[k][i], column-major
+        Tb[e] = Ts[i * 33 + k];
+    }
+}
+
+// =================================================================================================
+// trailing update, plain-FMA version (debug / cross-check path; ctx option qr_apply = 0)
+// =================================================================================================
+#define AF_SMEM_BYTES ((QB * QS + QB * 33 + QCT * QS + 2 * QB * (QCT + 1)) * 8)
+__global__ void __launch_bounds__(256, 1)
+qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int ntiles, int tiles_per_cta,
+                    TileMap tm, const double* __restrict__ V, const double* __restrict__ T) {
+    extern __shared__ double asmem[];
+    double* Vs = asmem;                // [QB][QS]
+    double* Ts = Vs + QB * QS;         // Ts[i*33 + k] = T[k][i]
+    double* Xs = Ts + QB * 33;         // [QCT][QS]
+    double* W = Xs + QCT * QS;         // [QB][QCT+1]
+    double* W2 = W + QB * (QCT + 1);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const long long blk = blockIdx.x;
+    const double* __restrict__ Vb = V + blk * (long long)(QB * QS);
+    const double* __restrict__ Tb = T + blk * (long long)(QB * QB);
+    for (int e = tid; e < QB * QS; e += 256) Vs[e] = Vb[e];
+    for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * 33 + k] = Tb[e]; }
+    const int t0 = blockIdx.y * tiles_per_cta;
+    int t1 = t0 + tiles_per_cta;
+    if (t1 > ntiles) t1 = ntiles;
+    for (int tile = t0; tile < t1; ++tile) {
+        const long long cbase = ctrail + (long long)tile * QCT;
+        __syncthreads();
+        for (int col = wrp; col < QCT; col += 8) {
+            const double* __restrict__ src = A + (cbase + col) * ld;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int p = q * 32 + lane;
+                long long mrow;
+                const bool ok = tm_row(tm, blk, p, mrow);
+                Xs[col * QS + p] = ok ? src[mrow] : 0.0;
+            }
+        }
+        __syncthreads();
+        // W = V' X   (QB x QCT)
+        for (int o = tid; o < QB * QCT; o += 256) {
+            const int i = o & 31, c = o >> 5;
+            double acc = 0.0;
+            for (int r = 0; r < QH; ++r) acc = fma(Vs[i * QS + r], Xs[c * QS + r], acc);
+            W[i * (QCT + 1) + c] = acc;
+        }
+        __syncthreads();
+        // W2 = T' W
+        for (int o = tid; o < QB * QCT; o += 256) {
+            const int i = o & 31, c = o >> 5;
+            double acc = 0.0;
+            for (int k = 0; k <= i; ++k) acc = fma(Ts[i * 33 + k], W[k * (QCT + 1) + c], acc);
+            W2[i * (QCT + 1) + c] = acc;
+        }
+        __syncthreads();
+        // X -= V W2 ; thread = row
+        {
+            const int r = tid;
+            long long mrow;
+            const bool ok = tm_row(tm, blk, r, mrow);
+            for (int c = 0; c < QCT; ++c) {
+                double acc = Xs[c * QS + r];
+                for (int i = 0; i < QB; ++i) acc = fma(-Vs[i * QS + r], W2[i * (QCT + 1) + c], acc);
+                if (ok) A[(cbase + c) * ld + mrow] = acc;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// trailing update, tensor-pipe version: persistent CTAs, producer warp + 8 consumer warps.
+// =================================================================================================
+#define AM_NST 3
+#define AM_VS_BYTES (QB * QS * 8)
+#define AM_XS_BYTES (QCT * QS * 8)
+#define AM_WP_BYTES (QCT * QWS * 8)
+#define AM_SMEM_BYTES (AM_VS_BYTES + AM_NST * AM_XS_BYTES + 10 * AM_WP_BYTES + QB * 33 * 8 + 64)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(288, 1)
+qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int ntiles, long long nblocks,
+                    TileMap tm, const double* __restrict__ V, const double* __restrict__ T) {
+    extern __shared__ __align__(128) unsigned char amsm[];
+    double* Vs = (double*)amsm;                                           // [QB][QS]
+    double* Xs = (double*)(amsm + AM_VS_BYTES);                           // [AM_NST][QCT][QS]
+    double* Wp = (double*)(amsm + AM_VS_BYTES + AM_NST * AM_XS_BYTES);    // [8][QCT][QWS] partial W
+    double* Wsum = Wp + 8 * QCT * QWS;                                    // [QCT][QWS]
+    double* Wfin = Wsum + QCT * QWS;                                      // [QCT][QWS]   T' W
+    double* Ts = Wfin + QCT * QWS;                                        // Ts[i*33 + k] = T[k][i]
+    uint64_t* bars = (uint64_t*)(Ts + QB * 33);                           // full[3], done[3], vfull
+    const uint32_t bar_full = smem_u32(bars), bar_done = smem_u32(bars + AM_NST), bar_v = smem_u32(bars + 2 * AM_NST);
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const long long jtot = nblocks * ntiles;
+    const long long q_begin = (jtot * blockIdx.x) / gridDim.x;
+    const long long q_end = (jtot * (blockIdx.x + 1)) / gridDim.x;
+    const int njobs = (int)(q_end - q_begin);
+
+    if (tid == 0) {
+        for (int s = 0; s < AM_NST; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_done + 8 * s, 256);
+        }
+        mbar_init(bar_v, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    __syncthreads();
+    if (njobs <= 0) return;
+
+    const int seg_rows = 1 << tm.seg_shift;
+    const uint32_t seg_bytes = (uint32_t)seg_rows * 8u;
+
+    if (wrp == 8) {
+        // =========================== producer warp ===========================
+        int stored = 0;
+        long long cur_blk = -1;
+        auto store_job = [&](int v) {
+            const long long q = q_begin + v;
+            const long long blk = q / ntiles;
+            const int tile = (int)(q - blk * ntiles);
+            const int s = v % AM_NST;
+            mbar_wait(bar_done + 8 * s, (uint32_t)((v / AM_NST) & 1));
+            const uint32_t xs = smem_u32(Xs + s * QCT * QS);
+            const long long cbase = ctrail + (long long)tile * QCT;
+            for (int e = lane; e < QCT * tm.nseg; e += 32) {
+                const int col = e / tm.nseg, qq = e - col * tm.nseg;
+                const long long item = blk * tm.nseg + qq;
+                if (item < tm.n_items) {
+                    double* dst = A + (cbase + col) * ld + tm.r0 + item * tm.seg_stride;
+                    bulk_s2g(dst, xs + (uint32_t)(col * QS + qq * seg_rows) * 8u, seg_bytes);
+                }
+            }
+            bulk_commit();
+            bulk_wait_read0();
+            __syncwarp();
+        };
+        for (int u = 0; u < njobs; ++u) {
+            const long long q = q_begin + u;
+            const long long blk = q / ntiles;
+            const int tile = (int)(q - blk * ntiles);
+            const int s = u % AM_NST;
+            if (blk != cur_blk) {
+                while (stored < u) { store_job(stored); ++stored; }   // consumers are done with the old V
+                cur_blk = blk;
+                if (lane == 0) {
+                    mbar_expect_tx(bar_v, AM_VS_BYTES);
+                    bulk_g2s(smem_u32(Vs), V + blk * (long long)(QB * QS), AM_VS_BYTES, bar_v);
+                }
+            }
+            while (stored <= u - AM_NST) { store_job(stored); ++stored; }
+            // ---- load tile u into stage s ----
+            double* xst = Xs + s * QCT * QS;
+            long long nvalid = tm.n_items - blk * tm.nseg;
+            if (nvalid > tm.nseg) nvalid = tm.nseg;
+            if (nvalid < tm.nseg) {
+                for (int e = lane; e < QCT * tm.nseg; e += 32) {
+                    const int col = e / tm.nseg, qq = e - col * tm.nseg;
+                    if (qq >= nvalid)
+                        for (int r = 0; r < seg_rows; ++r) xst[col * QS + qq * seg_rows + r] = 0.0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)(QCT * nvalid) * seg_bytes);
+            __syncwarp();
+            const long long cbase = ctrail + (long long)tile * QCT;
+            const uint32_t xs = smem_u32(xst);
+            for (int e = lane; e < QCT * tm.nseg; e += 32) {
+                const int col = e / tm.nseg, qq = e - col * tm.nseg;
+                const long long item = blk * tm.nseg + qq;
+                if (item < tm.n_items) {
+                    const double* src = A + (cbase + col) * ld + tm.r0 + item * tm.seg_stride;
+                    bulk_g2s(xs + (uint32_t)(col * QS + qq * seg_rows) * 8u, src, seg_bytes, bar_full + 8 * s);
+                }
+            }
+        }
+        while (stored < njobs) { store_job(stored); ++stored; }
+        bulk_wait0();
+        return;
+    }
+
+    // =============================== consumer warps ===============================
+    const int g = lane >> 2, t = lane & 3;
+    long long cur_blk = -1;
+    int seg_i = -1;
+    for (int u = 0; u < njobs; ++u) {
+        const long long q = q_begin + u;
+        const long long blk = q / ntiles;
+        const int s = u % AM_NST;
+        if (blk != cur_blk) {
+            cur_blk = blk;
+            ++seg_i;
+            const double* __restrict__ Tb = T + blk * (long long)(QB * QB);
+            for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * 33 + k] = Tb[e]; }
+            mbar_wait(bar_v, (uint32_t)(seg_i & 1));
+        }
+        mbar_wait(bar_full + 8 * s, (uint32_t)((u / AM_NST) & 1));
+        double* Xst = Xs + s * QCT * QS;
+
+        // ---- GEMM1: partial W_w = V[32w:32w+32, :]' X[32w:32w+32, :]  (QB x QCT) ----
+        {
+            double c1[4][2][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) c1[mi][ni][0] = c1[mi][ni][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int k0 = 32 * wrp + 4 * ks + t;
+                double a[4], b[2];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = Vs[(8 * mi + g) * QS + k0];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) b[ni] = Xst[(8 * ni + g) * QS + k0];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma(c1[mi][ni], a[mi], b[ni]);
+            }
+            double* wp = Wp + wrp * QCT * QWS;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    wp[(8 * ni + 2 * t + 0) * QWS + 8 * mi + g] = c1[mi][ni][0];
+                    wp[(8 * ni + 2 * t + 1) * QWS + 8 * mi + g] = c1[mi][ni][1];
+                }
+        }
+        consumer_sync();
+        // ---- reduce the 8 partials: Wsum[c][k] ----
+        {
+            const int c = tid >> 4, k = tid & 15;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                s0 += Wp[w * QCT * QWS + c * QWS + k];
+                s1 += Wp[w * QCT * QWS + c * QWS + k + 16];
+            }
+            Wsum[c * QWS + k] = s0;
+            Wsum[c * QWS + k + 16] = s1;
+        }
+        consumer_sync();
+        // ---- Wfin = -T' Wsum   (negated so GEMM2 is a plain accumulate) ----
+        {
+            const int c = tid >> 4, i0 = tid & 15;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < QB; ++k) {
+                const double wv = Wsum[c * QWS + k];
+                s0 = fma(Ts[i0 * 33 + k], wv, s0);
+                s1 = fma(Ts[(i0 + 16) * 33 + k], wv, s1);
+            }
+            Wfin[c * QWS + i0] = -s0;
+            Wfin[c * QWS + i0 + 16] = -s1;
+        }
+        consumer_sync();
+        // ---- GEMM2: X[32w:32w+32, :] += V[32w:32w+32, :] * Wfin ----
+        {
+            double c2[4][2][2];
+            const int rbase = 32 * wrp + g;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    c2[mi][ni][0] = Xst[(8 * ni + 2 * t + 0) * QS + rbase + 8 * mi];
+                    c2[mi][ni][1] = Xst[(8 * ni + 2 * t + 1) * QS + rbase + 8 * mi];
+                }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int k0 = 4 * ks + t;
+                double a[4], b[2];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = Vs[k0 * QS + rbase + 8 * mi];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) b[ni] = Wfin[(8 * ni + g) * QWS + k0];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    Xst[(8 * ni + 2 * t + 0) * QS + rbase + 8 * mi] = c2[mi][ni][0];
+                    Xst[(8 * ni + 2 * t + 1) * QS + rbase + 8 * mi] = c2[mi][ni][1];
+                }
+        }
+        fence_async_smem();
+        mbar_arrive(bar_done + 8 * s);
+    }
+}
+
+// =================================================================================================
+// upper-triangular solve (single CTA; n is at most a few thousand on this path)
+// =================================================================================================
+#define TRI_THREADS 1024
+template <int TRANS>
+__global__ void __launch_bounds__(TRI_THREADS, 1)
+tri_solve_kernel(int n, const double* __restrict__ R, long long ld, const double* c, double* xout) {
+    extern __shared__ double tsm[];
+    double* xs = tsm;             // [n]
+    double* D = tsm + n;          // [32][33] diagonal block
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n; i += TRI_THREADS) xs[i] = c[i];
+    const int nb = (n + 31) / 32;
+    for (int bi = 0; bi < nb; ++bi) {
+        const int jb = TRANS ? bi : (nb - 1 - bi);
+        const int j0 = jb * 32;
+        const int w = (n - j0 < 32) ? (n - j0) : 32;
+        __syncthreads();
+        {   // diagonal block into smem: D[r*33 + cc] = R[j0+r][j0+cc]
+            const int r = tid & 31, cc = tid >> 5;
+            if (r < w && cc < w) D[r * 33 + cc] = R[(long long)(j0 + cc) * ld + j0 + r];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double xi = (lane < w) ? xs[j0 + lane] : 0.0;
+            if (!TRANS) {
+                for (int jj = w - 1; jj >= 0; --jj) {
+                    double xj = __shfl_sync(0xffffffffu, xi, jj) / D[jj * 33 + jj];
+                    if (lane == jj) xi = xj;
+                    else if (lane < jj) xi = fma(-D[lane * 33 + jj], xj, xi);
+                }
+            } else {   // R' is lower triangular: L[i][j] = R[j][i]
+                for (int jj = 0; jj < w; ++jj) {
+                    double xj = __shfl_sync(0xffffffffu, xi, jj) / D[jj * 33 + jj];
+                    if (lane == jj) xi = xj;
+                    else if (lane > jj && lane < w) xi = fma(-D[jj * 33 + lane], xj, xi);
+                }
+            }
+            if (lane < w) xs[j0 + lane] = xi;
+        }
+        __syncthreads();
+        if (!TRANS) {
+            for (int i = tid; i < j0; i += TRI_THREADS) {
+                double acc = xs[i];
+                for (int jj = 0; jj < w; ++jj) acc = fma(-R[(long long)(j0 + jj) * ld + i], xs[j0 + jj], acc);
+                xs[i] = acc;
+            }
+        } else {
+            for (int i = j0 + w + tid; i < n; i += TRI_THREADS) {
+                double acc = xs[i];
+                const double* __restrict__ col = R + (long long)i * ld + j0;
+                for (int jj = 0; jj < w; ++jj) acc = fma(-col[jj], xs[j0 + jj], acc);
+                xs[i] = acc;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += TRI_THREADS) xout[i] = xs[i];
+}
+
+int tri_solve(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, const double* d_c, double* d_x, int trans) {
+    if (n == 0) return LSO_OK;
+    LSO_REQUIRE(ctx, n <= 24000, "triangular solve: n too large for the single-CTA kernel");
+    size_t smem = (size_t)(n + 32 * 33) * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(tri_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(tri_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    if (trans) tri_solve_kernel<1><<<1, TRI_THREADS, smem, ctx->stream>>>((int)n, d_R, ld, d_c, d_x);
+    else tri_solve_kernel<0><<<1, TRI_THREADS, smem, ctx->stream>>>((int)n, d_R, ld, d_c, d_x);
+    LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}
+
+// =================================================================================================
+// plan + driver
+// =================================================================================================
+int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
+    *plan = QRPlan();
+    plan->M = M;
+    plan->N = N;
+    plan->Npad = roundup64(N > 0 ? N : 1, QB);
+    plan->Nc = plan->Npad + QCT;
+    plan->ld = roundup64(M, QB) + QH;
+    size_t bytes = (size_t)plan->ld * plan->Nc * sizeof(double);
+    cudaError_t e = cudaMalloc(&plan->A, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return lso_set_error(ctx, LSO_ERR_ALLOC, "QR workspace: cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->A, 0, bytes, ctx->stream));
+    int64_t nb = cdiv64(M > 0 ? M : 1, QH);
+    int64_t stride = QH;
+    int L = 0;
+    for (;;) {
+        LSO_REQUIRE(ctx, L < QR_MAX_LEVELS, "too many TSQR levels");
+        QRLevel& lv = plan->lev[L];
+        lv.nblocks = nb;
+        lv.seg_stride = (L == 0) ? QH : stride;
+        size_t vb = (size_t)nb * QB * QS * sizeof(double), tb = (size_t)nb * QB * QB * sizeof(double);
+        e = cudaMalloc(&lv.V, vb);
+        if (e == cudaSuccess) e = cudaMalloc(&lv.T, tb);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return lso_set_error(ctx, LSO_ERR_ALLOC, "QR reflector workspace: %s", cudaGetErrorString(e));
+        }
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(lv.V, 0, vb, ctx->stream));
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(lv.T, 0, tb, ctx->stream));
+        ++L;
+        if (nb <= 1) break;
+        if (L > 1) stride *= QG;   // heads of level L-1 blocks are QH*QG^(L-1) rows apart
+        nb = cdiv64(nb, QG);
+    }
+    plan->nlevels = L;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
+        attr_done = true;
+    }
+    return LSO_OK;
+}
+
+void qr_plan_destroy(QRPlan* plan) {
+    if (!plan) return;
+    cudaFree(plan->A);
+    for (int l = 0; l < plan->nlevels; ++l) {
+        cudaFree(plan->lev[l].V);
+        cudaFree(plan->lev[l].T);
+    }
+    *plan = QRPlan();
+}
+
+int qr_factor(lso_ctx* ctx, QRPlan* plan) {
+    const int64_t M = plan->M;
+    for (int64_t c0 = 0; c0 < plan->Npad; c0 += QB) {
+        const int64_t r0 = c0;
+        if (r0 >= M) break;    // no rows left: remaining columns have no R rows
+        // level sizes for this panel
+        int64_t nblk[QR_MAX_LEVELS];
+        TileMap tms[QR_MAX_LEVELS];
+        int L = 0;
+        int64_t nb = cdiv64(M - r0, QH);
+        int64_t stride = QH;
+        for (;;) {
+            nblk[L] = nb;
+            TileMap& tm = tms[L];
+            tm.r0 = r0;
+            if (L == 0) {
+                tm.seg_stride = QH; tm.n_items = nb; tm.seg_shift = 8; tm.nseg = 1;
+            } else {
+                tm.seg_stride = stride; tm.n_items = nblk[L - 1]; tm.seg_shift = 5; tm.nseg = QG;
+            }
+            ++L;
+            if (nb <= 1) break;
+            if (L > 1) stride *= QG;
+            nb = cdiv64(nb, QG);
+        }
+        for (int l = 0; l < L; ++l) {
+            qr_leaf_kernel<<<(unsigned)nblk[l], 256, LEAF_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, c0, tms[l],
+                                                                                    plan->lev[l].V, plan->lev[l].T);
+            LSO_CHECK_LAUNCH(ctx);
+        }
+        const int64_t ctrail = c0 + QB;
+        const int ntiles = (int)((plan->Nc - ctrail) / QCT);
+        if (ntiles <= 0) continue;
+        for (int l = 0; l < L; ++l) {
+            if (ctx->opt_qr_apply == 0) {
+                int64_t chunks = cdiv64((int64_t)ctx->num_sms * 2, nblk[l]);
+                if (chunks > ntiles) chunks = ntiles;
+                if (chunks < 1) chunks = 1;
+                int tiles_per = (int)cdiv64(ntiles, chunks);
+                dim3 grid((unsigned)nblk[l], (unsigned)cdiv64(ntiles, tiles_per));
+                qr_apply_fma_kernel<<<grid, 256, AF_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, ctrail, ntiles, tiles_per,
+                                                                              tms[l], plan->lev[l].V, plan->lev[l].T);
+            } else {
+                int64_t jtot = nblk[l] * ntiles;
+                int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
+                qr_apply_mma_kernel<<<grid, 288, AM_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, ctrail, ntiles, nblk[l],
+                                                                              tms[l], plan->lev[l].V, plan->lev[l].T);
+            }
+            LSO_CHECK_LAUNCH(ctx);
+        }
+    }
+    return LSO_OK;
+}

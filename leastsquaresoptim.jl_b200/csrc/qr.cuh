@@ -1,0 +1,46 @@
+// qr.cuh — shared declarations of the communication-avoiding Householder QR (qr.cu) used by the
+// QR solve, the TSQR multi-GPU reduction and the tests.
+#pragma once
+#include "common.cuh"
+
+// Tiling constants of the CAQR:
+//   QB  panel width (columns factorised together; reflectors per block reflector)
+//   QH  rows of one leaf block (one CTA factorises a QH x QB block out of shared memory/registers)
+//   QG  fan-in of the reduction tree (QH / QB heads are stacked into the next level's block)
+//   QS  padded column stride (doubles) of V blocks in the workspace and in shared memory:
+//       QS = QH + 4 makes every DMMA fragment load (4 rows x 8 cols, or 8 rows x 4 cols) hit 16
+//       distinct 8-byte banks per half-warp.
+//   QCT columns per trailing-update tile
+#define QB 32
+#define QH 256
+#define QG (QH / QB)
+#define QS (QH + 4)
+#define QCT 16
+#define QWS (QB + 4)
+#define QR_MAX_LEVELS 10
+
+struct QRLevel {
+    int64_t nblocks;     // blocks at this level (for the widest panel, r0 = 0)
+    int64_t seg_stride;  // matrix rows between consecutive items (heads) gathered by this level
+    double* V;           // nblocks * QB*QS doubles
+    double* T;           // nblocks * QB*QB doubles
+};
+
+struct QRPlan {
+    int64_t M = 0;       // rows of the matrix being factorised
+    int64_t N = 0;       // columns to factorise
+    int64_t Npad = 0;    // N rounded up to QB (extra columns are zero => identity reflectors)
+    int64_t Nc = 0;      // total columns incl. right-hand-side tile: Npad + QCT
+    int64_t ld = 0;      // leading dimension: roundup(M, QB) + QH zero rows of padding
+    double* A = nullptr; // ld x Nc, column-major
+    int nlevels = 0;
+    QRLevel lev[QR_MAX_LEVELS];
+};
+
+int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan);
+void qr_plan_destroy(QRPlan* plan);
+// Factorise plan->A in place: on return the leading N x N upper triangle holds R and column Npad
+// rows 0..N-1 hold Q'b (the right-hand side that was stored in column Npad on entry).
+int qr_factor(lso_ctx* ctx, QRPlan* plan);
+// x = R^{-1} c  (TRANS=0)  or  x = R^{-T} c (TRANS=1) for the upper-triangular n x n R at d_R (ld).
+int tri_solve(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, const double* d_c, double* d_x, int trans);

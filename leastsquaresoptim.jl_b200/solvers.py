@@ -1,0 +1,108 @@
+"""Allocated solvers: the `AbstractAllocatedSolver` plugin surface of the reference, backed by the C ABI.
+
+Each class mirrors one reference struct and its `ldiv!` methods; `ldiv` returns `(x, n_mul)` exactly like
+the reference so `mul_calls` bookkeeping in the optimizers is unchanged.
+
+  DenseQRAllocatedSolver        src/solver/dense_qr.jl:6-88
+  DenseCholeskyAllocatedSolver  src/solver/dense_cholesky.jl:7-59
+  LSMRAllocatedSolver           src/solver/iterative_lsmr.jl:161-198
+  LSMRDampenedAllocatedSolver   src/solver/iterative_lsmr.jl:221-259
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+from ._lib import check, lib
+from .device import Context, CSCMatrix, DenseMatrix, DeviceVector
+
+LSO_SOLVER_QR = 1
+LSO_SOLVER_CHOLESKY = 2
+
+
+class _DenseWorkspace:
+    def __init__(self, ctx: Context, m: int, n: int, kind: int, damped: bool):
+        self.ctx, self.m, self.n, self.damped = ctx, m, n, damped
+        self._h = C.c_void_p()
+        check(lib().lso_dense_ws_create(ctx.handle, m, n, kind, int(damped), C.byref(self._h)), ctx.handle)
+        self._fin = weakref.finalize(self, lib().lso_dense_ws_destroy, self._h)
+
+    def factor(self):
+        """n x n upper-triangular factor of the last solve (tests)."""
+        import numpy as np
+
+        R = np.zeros((self.n, self.n), order="F")
+        check(lib().lso_dense_ws_get_factor(self._h, R.ctypes.data), self.ctx.handle)
+        return R
+
+
+class DenseQRAllocatedSolver(_DenseWorkspace):
+    """dense_qr.jl: Dogleg{QR} workspace (m x n, :25-28) or LevenbergMarquardt{QR} workspace ((m+n) x n, :50-54)."""
+
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool):
+        super().__init__(ctx, m, n, LSO_SOLVER_QR, damped)
+        self.last_rank = n
+
+    def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None):
+        rank = C.c_int()
+        fn = lib().lso_qr_solve_sharded if self.ctx_nranks() > 1 else lib().lso_qr_solve
+        check(fn(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr, C.byref(rank)),
+              self.ctx.handle)
+        self.last_rank = rank.value
+        return x, 1
+
+    def ctx_nranks(self) -> int:
+        return getattr(self.ctx, "nranks", 1)
+
+
+class DenseCholeskyAllocatedSolver(_DenseWorkspace):
+    """dense_cholesky.jl:19-21 (one n x n workspace for both optimizers)."""
+
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool):
+        super().__init__(ctx, m, n, LSO_SOLVER_CHOLESKY, damped)
+
+    def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None):
+        check(lib().lso_chol_solve(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr),
+              self.ctx.handle)
+        return x, 1
+
+
+class _LSMRWorkspace:
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool):
+        self.ctx, self.m, self.n, self.damped = ctx, m, n, damped
+        self._h = C.c_void_p()
+        check(lib().lso_lsmr_ws_create(ctx.handle, m, n, int(damped), C.byref(self._h)), ctx.handle)
+        self._fin = weakref.finalize(self, lib().lso_lsmr_ws_destroy, self._h)
+        self.last_iters = 0
+        self.last_istop = 0
+
+    def _solve(self, x, J, y, damp, atol, btol, conlim, maxiter):
+        iters, istop = C.c_int64(), C.c_int()
+        csc = J.handle if isinstance(J, CSCMatrix) else None
+        dj = J.ptr if isinstance(J, DenseMatrix) else None
+        ld = J.ld if isinstance(J, DenseMatrix) else 0
+        check(lib().lso_lsmr_solve(self._h, csc, dj, ld, y.ptr, damp.ptr if damp is not None else None, x.ptr,
+                                   atol, btol, conlim, maxiter, C.byref(iters), C.byref(istop)), self.ctx.handle)
+        self.last_iters, self.last_istop = iters.value, istop.value
+        return x, 2 * iters.value      # ch.mvps = 2 * iter (lsmr.jl:236)
+
+
+class LSMRAllocatedSolver(_LSMRWorkspace):
+    """iterative_lsmr.jl:161-198 — undamped, lsmr! defaults atol = btol = 1e-6, conlim = 1e8 (lsmr.jl:53-55)."""
+
+    def __init__(self, ctx, m, n):
+        super().__init__(ctx, m, n, False)
+
+    def ldiv(self, x, J, y, damp=None):
+        assert damp is None
+        return self._solve(x, J, y, None, 1e-6, 1e-6, 1e8, 0)
+
+
+class LSMRDampenedAllocatedSolver(_LSMRWorkspace):
+    """iterative_lsmr.jl:221-259 — damped, btol = 0.5 (:255); `damp` is overwritten by sqrt(damp) (:252)."""
+
+    def __init__(self, ctx, m, n):
+        super().__init__(ctx, m, n, True)
+
+    def ldiv(self, x, J, y, damp):
+        return self._solve(x, J, y, damp, 1e-6, 0.5, 1e8, 0)
