@@ -23,6 +23,9 @@ struct lso_ctx {
     // options
     int64_t opt_qr_apply = 1;          // 0 = plain-FMA apply kernel, 1 = DMMA apply kernel
     int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
+    // scratch of the rank-revealing small-R finish (qr_finish.cu), grown on demand
+    double* d_finish = nullptr;
+    size_t finish_cap = 0;
     // NCCL (lazily loaded)
     void* nccl_comm = nullptr;
     int nranks = 1;

@@ -69,6 +69,7 @@ int lso_ctx_destroy(lso_ctx* ctx) {
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_scalars);
+    cudaFree(ctx->d_finish);
     cudaFreeHost(ctx->h_scalars);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

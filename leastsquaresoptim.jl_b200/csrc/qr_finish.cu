@@ -1,7 +1,320 @@
-// qr_finish.cu — rank-revealing finish on the small n x n R (Q-d): placeholder until the pivoted path lands.
+// qr_finish.cu — rank-revealing finish on the small n x n triangular factor (Q-d in SURVEY.md App. B).
+//
+// The reference solves with `ldiv!(qr!(qrm, ColumnNorm()), u)` (src/solver/dense_qr.jl:37,83), i.e. [Julia
+// stdlib] column-pivoted QR (LAPACK dgeqp3), rank detection by incremental condition estimation (dlaic1)
+// with rcond = min(rows, cols)*eps, complete orthogonal factorisation of the leading rank rows (dtzrzf) and
+// the MINIMUM-NORM least-squares solution (== dgelsy without scaling).  The tall matrix has already been
+// reduced to R0 (n x n) and c = Q0' b by the CAQR; because (R0 P) has the same column norms / Gram matrix as
+// (A P), pivoted QR of R0 selects the same pivots and yields the same R, so the whole rank-revealing
+// pipeline runs on the small factor: a single CTA, matrix in global memory (L2-resident).
+// This path is taken only when the unpivoted factor looks ill-conditioned (dense_solve.cu: qr_finish).
 #include "qr.cuh"
+#include <math.h>
+
+#define FT 512
+
+__device__ __forceinline__ double f_block_sum(double v, double* sm) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < FT / 32; ++w) r += sm[w];     // every thread: same fixed order
+    return r;
+}
+
+struct Laic1Out { double sestpr, s, c; };
+
+// LAPACK dlaic1 (incremental condition estimation), restated.  job 1: largest, job 2: smallest singular value.
+__device__ Laic1Out laic1(int job, double sest, double alpha, double gamma) {
+    const double eps = 1.1102230246251565e-16;    // dlamch('Epsilon')
+    const double absalp = fabs(alpha), absgam = fabs(gamma), absest = fabs(sest);
+    Laic1Out o;
+    double s, c, tmp, s1, s2;
+    if (job == 1) {
+        if (sest == 0.0) {
+            s1 = fmax(absgam, absalp);
+            if (s1 == 0.0) { o.s = 0; o.c = 1; o.sestpr = 0; }
+            else { s = alpha / s1; c = gamma / s1; tmp = sqrt(s * s + c * c); o.s = s / tmp; o.c = c / tmp; o.sestpr = s1 * tmp; }
+        } else if (absgam <= eps * absest) {
+            o.s = 1; o.c = 0; tmp = fmax(absest, absalp); s1 = absest / tmp; s2 = absalp / tmp;
+            o.sestpr = tmp * sqrt(s1 * s1 + s2 * s2);
+        } else if (absalp <= eps * absest) {
+            s1 = absgam; s2 = absest;
+            if (s1 <= s2) { o.s = 1; o.c = 0; o.sestpr = s2; } else { o.s = 0; o.c = 1; o.sestpr = s1; }
+        } else if (absest <= eps * absalp || absest <= eps * absgam) {
+            s1 = absgam; s2 = absalp;
+            if (s1 <= s2) { tmp = s1 / s2; s = sqrt(1.0 + tmp * tmp); o.sestpr = s2 * s; o.c = (gamma / s2) / s; o.s = copysign(1.0, alpha) / s; }
+            else { tmp = s2 / s1; c = sqrt(1.0 + tmp * tmp); o.sestpr = s1 * c; o.s = (alpha / s1) / c; o.c = copysign(1.0, gamma) / c; }
+        } else {
+            const double zeta1 = alpha / absest, zeta2 = gamma / absest;
+            const double b = (1.0 - zeta1 * zeta1 - zeta2 * zeta2) * 0.5;
+            c = zeta1 * zeta1;
+            double t = (b > 0.0) ? c / (b + sqrt(b * b + c)) : sqrt(b * b + c) - b;
+            const double sine = -zeta1 / t, cosine = -zeta2 / (1.0 + t);
+            tmp = sqrt(sine * sine + cosine * cosine);
+            o.s = sine / tmp; o.c = cosine / tmp; o.sestpr = sqrt(t + 1.0) * absest;
+        }
+    } else {
+        if (sest == 0.0) {
+            o.sestpr = 0;
+            double sine, cosine;
+            if (fmax(absgam, absalp) == 0.0) { sine = 1; cosine = 0; } else { sine = -gamma; cosine = alpha; }
+            s1 = fmax(fabs(sine), fabs(cosine));
+            s = sine / s1; c = cosine / s1; tmp = sqrt(s * s + c * c);
+            o.s = s / tmp; o.c = c / tmp;
+        } else if (absgam <= eps * absest) {
+            o.s = 0; o.c = 1; o.sestpr = absgam;
+        } else if (absalp <= eps * absest) {
+            s1 = absgam; s2 = absest;
+            if (s1 <= s2) { o.s = 0; o.c = 1; o.sestpr = s1; } else { o.s = 1; o.c = 0; o.sestpr = s2; }
+        } else if (absest <= eps * absalp || absest <= eps * absgam) {
+            s1 = absgam; s2 = absalp;
+            if (s1 <= s2) { tmp = s1 / s2; c = sqrt(1.0 + tmp * tmp); o.sestpr = absest * (tmp / c); o.s = -(gamma / s2) / c; o.c = copysign(1.0, alpha) / c; }
+            else { tmp = s2 / s1; s = sqrt(1.0 + tmp * tmp); o.sestpr = absest / s; o.c = (alpha / s1) / s; o.s = -copysign(1.0, gamma) / s; }
+        } else {
+            const double zeta1 = alpha / absest, zeta2 = gamma / absest;
+            const double norma = fmax(1.0 + zeta1 * zeta1 + fabs(zeta1 * zeta2), fabs(zeta1 * zeta2) + zeta2 * zeta2);
+            const double test = 1.0 + 2.0 * (zeta1 - zeta2) * (zeta1 + zeta2);
+            double sine, cosine;
+            if (test >= 0.0) {
+                const double b = (zeta1 * zeta1 + zeta2 * zeta2 + 1.0) * 0.5;
+                c = zeta2 * zeta2;
+                const double t = c / (b + sqrt(fabs(b * b - c)));
+                sine = zeta1 / (1.0 - t); cosine = -zeta2 / t;
+                o.sestpr = sqrt(t + 4.0 * eps * eps * norma) * absest;
+            } else {
+                const double b = (zeta2 * zeta2 + zeta1 * zeta1 - 1.0) * 0.5;
+                c = zeta1 * zeta1;
+                const double t = (b >= 0.0) ? -c / (b + sqrt(b * b + c)) : b - sqrt(b * b + c);
+                sine = -zeta1 / t; cosine = -zeta2 / (1.0 + t);
+                o.sestpr = sqrt(1.0 + t + 4.0 * eps * eps * norma) * absest;
+            }
+            tmp = sqrt(sine * sine + cosine * cosine);
+            o.s = sine / tmp; o.c = cosine / tmp;
+        }
+    }
+    return o;
+}
+
+// W: n x n (ld = ldw) holds R0 (upper triangle; strictly-lower part is ignored and zeroed here).
+// c: n right-hand side Q0'b.  Workspace vectors of length n: y, vn1, vn2, tau, xmin, xmax; jpvt ints.
+__global__ void __launch_bounds__(FT, 1)
+small_qrcp_solve_kernel(int n, double* __restrict__ W, long long ldw, double* __restrict__ c, double* __restrict__ xout,
+                        double* __restrict__ vn1, double* __restrict__ vn2, double* __restrict__ tau,
+                        double* __restrict__ xmin, double* __restrict__ xmax, int* __restrict__ jpvt, double rcond,
+                        int* __restrict__ rank_out) {
+    __shared__ double sm[FT / 32];
+    __shared__ double s_val[FT / 32];
+    __shared__ int s_idx[FT / 32];
+    __shared__ int s_pvt, s_rank;
+    __shared__ double s_a, s_b, s_c;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const double tol3z = sqrt(1.1102230246251565e-16);
+
+    for (int j = tid; j < n; j += FT) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (i > j) W[(long long)j * ldw + i] = 0.0;
+            else { const double v = W[(long long)j * ldw + i]; s = fma(v, v, s); }
+        }
+        vn1[j] = vn2[j] = sqrt(s);
+        jpvt[j] = j;
+    }
+    __syncthreads();
+
+    // ---- phase A: Householder QR with column pivoting (dgeqp3 / dlaqp2 semantics) ----
+    for (int j = 0; j < n; ++j) {
+        // pivot = first index of the maximum partial norm
+        double bv = -1.0; int bi = n;
+        for (int k = j + tid; k < n; k += FT) { const double v = vn1[k]; if (v > bv) { bv = v; bi = k; } }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wrp] = bv; s_idx[wrp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double v = s_val[0]; int ix = s_idx[0];
+            for (int w = 1; w < FT / 32; ++w) if (s_val[w] > v || (s_val[w] == v && s_idx[w] < ix)) { v = s_val[w]; ix = s_idx[w]; }
+            if (ix >= n) ix = j;
+            s_pvt = ix;
+            if (ix != j) {
+                const int tj = jpvt[ix]; jpvt[ix] = jpvt[j]; jpvt[j] = tj;
+                vn1[ix] = vn1[j]; vn2[ix] = vn2[j];
+            }
+        }
+        __syncthreads();
+        const int pvt = s_pvt;
+        if (pvt != j) {
+            for (int i = tid; i < n; i += FT) {
+                const double a = W[(long long)j * ldw + i];
+                W[(long long)j * ldw + i] = W[(long long)pvt * ldw + i];
+                W[(long long)pvt * ldw + i] = a;
+            }
+        }
+        __syncthreads();
+        // reflector for W[j:n, j]
+        double* colj = W + (long long)j * ldw;
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < n; i += FT) { const double v = colj[i]; part = fma(v, v, part); }
+        const double xn2 = f_block_sum(part, sm);
+        const double alpha = colj[j];
+        double beta, tj, scale;
+        if (xn2 == 0.0) { beta = alpha; tj = 0.0; scale = 0.0; }
+        else { beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha); tj = (beta - alpha) / beta; scale = 1.0 / (alpha - beta); }
+        __syncthreads();
+        for (int i = j + 1 + tid; i < n; i += FT) colj[i] *= scale;
+        if (tid == 0) { colj[j] = beta; tau[j] = tj; }
+        __syncthreads();
+        // apply H_j to the trailing columns and to c (warp per column)
+        for (int k = j + 1 + wrp; k <= n; k += FT / 32) {
+            double* colk = (k < n) ? (W + (long long)k * ldw) : c;
+            double w = 0.0;
+            for (int i = j + 1 + lane; i < n; i += 32) w = fma(colj[i], colk[i], w);
+            w = warp_sum(w) + colk[j];
+            const double tw = tj * w;
+            for (int i = j + 1 + lane; i < n; i += 32) colk[i] = fma(-tw, colj[i], colk[i]);
+            __syncwarp();
+            if (lane == 0) colk[j] -= tw;
+        }
+        __syncthreads();
+        // partial column norm downdate (dlaqp2)
+        for (int k = j + 1 + tid; k < n; k += FT) {
+            if (vn1[k] != 0.0) {
+                double temp = fabs(W[(long long)k * ldw + j]) / vn1[k];
+                temp = fmax(0.0, 1.0 - temp * temp);
+                const double r = vn1[k] / vn2[k];
+                const double temp2 = temp * r * r;
+                if (temp2 <= tol3z) {
+                    double s = 0.0;
+                    for (int i = j + 1; i < n; ++i) { const double v = W[(long long)k * ldw + i]; s = fma(v, v, s); }
+                    vn1[k] = vn2[k] = sqrt(s);
+                } else {
+                    vn1[k] *= sqrt(temp);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase B: numerical rank by incremental condition estimation (Julia stdlib ldiv!(::QRPivoted), dgelsy) ----
+    if (wrp == 0) {
+        int rnk = 0;
+        const double ar = fabs(W[0]);
+        if (ar != 0.0) {
+            rnk = 1;
+            if (lane == 0) { xmin[0] = 1.0; xmax[0] = 1.0; }
+            double tmin = ar, tmax = ar;
+            __syncwarp();
+            while (rnk < n) {
+                const double* wcol = W + (long long)rnk * ldw;
+                double a1 = 0.0, a2 = 0.0;
+                for (int i = lane; i < rnk; i += 32) { a1 = fma(xmin[i], wcol[i], a1); a2 = fma(xmax[i], wcol[i], a2); }
+                a1 = warp_sum(a1); a2 = warp_sum(a2);
+                const double gamma = wcol[rnk];
+                const Laic1Out lo = laic1(2, tmin, a1, gamma);
+                const Laic1Out hi = laic1(1, tmax, a2, gamma);
+                tmin = lo.sestpr; tmax = hi.sestpr;
+                if (tmax * rcond > tmin) break;
+                for (int i = lane; i < rnk; i += 32) { xmin[i] *= lo.s; xmax[i] *= hi.s; }
+                if (lane == 0) { xmin[rnk] = lo.c; xmax[rnk] = hi.c; }
+                __syncwarp();
+                ++rnk;
+            }
+        }
+        if (lane == 0) { s_rank = rnk; *rank_out = rnk; }
+    }
+    __syncthreads();
+    const int r = s_rank;
+    if (r == 0) {
+        for (int i = tid; i < n; i += FT) xout[i] = 0.0;
+        return;
+    }
+    const int l = n - r;
+
+    // ---- phase C: complete orthogonal factorisation [R11 R12] = [T11 0] Z   (dtzrzf / dlatrz) ----
+    if (l > 0) {
+        for (int i = r - 1; i >= 0; --i) {
+            double part = 0.0;
+            for (int k = r + tid; k < n; k += FT) { const double v = W[(long long)k * ldw + i]; part = fma(v, v, part); }
+            const double xn2 = f_block_sum(part, sm);
+            const double alpha = W[(long long)i * ldw + i];
+            double beta, ti, scale;
+            if (xn2 == 0.0) { beta = alpha; ti = 0.0; scale = 0.0; }
+            else { beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha); ti = (beta - alpha) / beta; scale = 1.0 / (alpha - beta); }
+            __syncthreads();
+            for (int k = r + tid; k < n; k += FT) W[(long long)k * ldw + i] *= scale;
+            if (tid == 0) { W[(long long)i * ldw + i] = beta; tau[i] = ti; }
+            __syncthreads();
+            // apply from the right to rows p < i: w = A[p,i] + sum_k A[p,k] v_k
+            for (int p = tid; p < i; p += FT) {
+                double w = W[(long long)i * ldw + p];
+                for (int k = r; k < n; ++k) w = fma(W[(long long)k * ldw + p], W[(long long)k * ldw + i], w);
+                const double tw = ti * w;
+                W[(long long)i * ldw + p] -= tw;
+                for (int k = r; k < n; ++k) W[(long long)k * ldw + p] = fma(-tw, W[(long long)k * ldw + i], W[(long long)k * ldw + p]);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- phase D: y = T11^{-1} c(1:r); x = P Z' [y; 0] ----
+    for (int j = r - 1; j >= 0; --j) {
+        if (tid == 0) c[j] = c[j] / W[(long long)j * ldw + j];
+        __syncthreads();
+        const double yj = c[j];
+        for (int i = tid; i < j; i += FT) c[i] = fma(-W[(long long)j * ldw + i], yj, c[i]);
+        __syncthreads();
+    }
+    for (int i = r + tid; i < n; i += FT) c[i] = 0.0;
+    __syncthreads();
+    if (l > 0) {
+        for (int k = 0; k < r; ++k) {      // dormrz('L','T'): apply Z(1), Z(2), ..., Z(r)
+            double part = 0.0;
+            for (int q = r + tid; q < n; q += FT) part = fma(W[(long long)q * ldw + k], c[q], part);
+            const double w = f_block_sum(part, sm) + c[k];
+            const double tw = tau[k] * w;
+            __syncthreads();
+            for (int q = r + tid; q < n; q += FT) c[q] = fma(-tw, W[(long long)q * ldw + k], c[q]);
+            if (tid == 0) c[k] -= tw;
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += FT) xout[jpvt[i]] = c[i];
+}
+
+__global__ void copy_upper_kernel(int n, const double* __restrict__ R, long long ld, double* __restrict__ W, long long ldw) {
+    const int j = blockIdx.x;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W[(long long)j * ldw + i] = (i <= j) ? R[(long long)j * ld + i] : 0.0;
+}
+
 int small_qr_finish(lso_ctx* ctx, int64_t n, double* d_R, int64_t ld, double* d_c, double* d_x, int* rank_out) {
-    LSO_TRY(tri_solve(ctx, n, d_R, ld, d_c, d_x, 0));
-    *rank_out = (int)n;
+    LSO_REQUIRE(ctx, n <= 4096, "rank-deficient QR finish: n > 4096 is not supported yet");
+    const size_t need = (size_t)n * n + 8 * (size_t)n + 64;
+    if (ctx->finish_cap < need) {
+        LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_finish);
+        ctx->d_finish = nullptr;
+        ctx->finish_cap = 0;
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_finish, need * sizeof(double)));
+        ctx->finish_cap = need;
+    }
+    double* W = ctx->d_finish;
+    double* c = W + (size_t)n * n;
+    double *vn1 = c + n, *vn2 = vn1 + n, *tau = vn2 + n, *xmin = tau + n, *xmax = xmin + n;
+    int* jpvt = (int*)(xmax + n);
+    int* d_rank = jpvt + n;
+    copy_upper_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((int)n, d_R, ld, W, n);
+    LSO_CHECK_LAUNCH(ctx);
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(c, d_c, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    const double rcond = (double)n * 2.220446049250313e-16;
+    small_qrcp_solve_kernel<<<1, FT, 0, ctx->stream>>>((int)n, W, n, c, d_x, vn1, vn2, tau, xmin, xmax, jpvt, rcond, d_rank);
+    LSO_CHECK_LAUNCH(ctx);
+    int rk = 0;
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(&rk, d_rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *rank_out = rk;
     return LSO_OK;
 }

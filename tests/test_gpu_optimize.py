@@ -25,16 +25,38 @@ def _run_pair(f, g, x0, m, opt, solver, J_dense=True, **kw):
     return rg, ro
 
 
+def _replay_solves(ctx, ro, solver, damped):
+    """Per-linear-solve parity on IDENTICAL inputs: every (J, f, damp) the oracle's run solved is handed to the
+    GPU plugin; ||δ_gpu − δ_ref|| / ||δ_ref|| <= 1e-10 (north_star).  (Comparing δ along two separately evolved
+    trajectories is ill-posed near convergence: f(x) is a cancellation of O(1) terms there.)"""
+    import lsob200 as L
+    worst = 0.0
+    for (Jh, fh, damp), dref in zip(ro.solve_inputs, ro.deltas):
+        m, n = Jh.shape
+        cls = {"qr": L.DenseQRAllocatedSolver, "cholesky": L.DenseCholeskyAllocatedSolver}[solver]
+        ws = cls(ctx, m, n, damped)
+        x = L.DeviceVector(ctx, n)
+        ws.ldiv(x, L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, fh),
+                L.DeviceVector(ctx, n, damp) if damp is not None else None)
+        nr = np.linalg.norm(dref)
+        if nr > 0:
+            worst = max(worst, np.linalg.norm(x.download() - dref) / nr)
+    return worst
+
+
 @pytest.mark.parametrize("opt", ["lm", "dogleg"])
-def test_readme_rosenbrock(opt):
-    """config 1 of BASELINE.json: Rosenbrock m=2 n=2 through the plugin; δ checked at every iteration."""
+def test_readme_rosenbrock(ctx, opt):
+    """config 1 of BASELINE.json: Rosenbrock m=2 n=2 through the plugin: same iteration / call counts as the
+    oracle, and δ parity at every linear solve of the run."""
     name, f, g, x0 = P.readme_rosenbrock()
     rg, ro = _run_pair(f, g, x0, 2, opt, "qr")
     assert rg.converged and np.linalg.norm(rg.minimizer - 1.0) <= 1e-6
     assert (rg.iterations, rg.f_calls, rg.g_calls, rg.mul_calls) == (ro.iterations, ro.f_calls, ro.g_calls, ro.mul_calls)
     assert len(rg.deltas) == len(ro.deltas)
-    for dg, do in zip(rg.deltas, ro.deltas):
-        assert np.linalg.norm(dg - do) <= 1e-10 * max(np.linalg.norm(do), 1e-300)
+    # early iterations (trajectories still bit-close): δ agrees directly
+    for dg, do in list(zip(rg.deltas, ro.deltas))[:10]:
+        assert np.linalg.norm(dg - do) <= 1e-10 * np.linalg.norm(do)
+    assert _replay_solves(ctx, ro, "qr", opt == "lm") <= 1e-10
 
 
 @pytest.mark.parametrize("solver,dense", [("qr", True), ("lsmr", True), ("lsmr", False), ("cholesky", True)])

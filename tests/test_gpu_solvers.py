@@ -137,8 +137,13 @@ def test_cholesky_undamped_and_failure(ctx):
 @pytest.mark.parametrize("m,n,damped", [(9, 6, True), (9, 6, False), (400, 60, True), (400, 60, False),
                                         (20000, 3000, True), (5000, 300, False)])
 def test_lsmr(ctx, kind, m, n, damped):
-    """ldiv! for LSMRAllocatedSolver / LSMRDampenedAllocatedSolver (iterative_lsmr.jl:179-198, 238-259):
-    same iteration count and istop as the oracle, iterate within 1e-10."""
+    """ldiv! for LSMRAllocatedSolver / LSMRDampenedAllocatedSolver (iterative_lsmr.jl:179-198, 238-259).
+
+    LSMR is an INEXACT solve (atol = 1e-6; LM uses btol = 0.5): it must stop at the same iteration with the same
+    istop as the oracle, but once the residual is at the 1e-6 level the trailing Golub-Kahan vectors are
+    determined by rounding, so two correct implementations (e.g. this oracle run on the dense and on the CSC form
+    of the same J — see test_lsmr_sensitivity_is_intrinsic) differ by up to ~1e-5 relative in x.  The 1e-10 bar is
+    checked where it is meaningful: on the bidiagonalisation run to full convergence (test_lsmr_tight)."""
     from lsob200 import CSCMatrix, DenseMatrix, DeviceVector, LSMRAllocatedSolver, LSMRDampenedAllocatedSolver
     rng = np.random.default_rng(m + n + damped)
     A = sp.random(m, n, density=min(1.0, 12.0 / n + 0.002), random_state=m + n, format="csc")
@@ -161,5 +166,90 @@ def test_lsmr(ctx, kind, m, n, damped):
         _, nmul = ws.ldiv(x, J, y)
     assert (ws.last_iters, ws.last_istop) == (it_r, istop_r)
     assert nmul == nmul_r
-    assert rel(x.download(), xr) <= TOL
+    assert rel(x.download(), xr) <= 2e-5
     assert np.array_equal(y.download(), yh)
+    # reproducible: same bits on a second call
+    x2 = DeviceVector(ctx, n)
+    if damped:
+        ws.ldiv(x2, J, y, DeviceVector(ctx, n, damp))
+    else:
+        ws.ldiv(x2, J, y)
+    assert np.array_equal(x2.download(), x.download())
+
+
+def test_lsmr_sensitivity_is_intrinsic():
+    """Calibrates the tolerance above: the oracle itself, fed the same J as dense vs CSC (summation order only),
+    moves by 1e-8..1e-5 relative at atol = 1e-6 with identical iteration counts."""
+    rng = np.random.default_rng(461)
+    A = sp.random(400, 60, density=0.2, random_state=460, format="csc")
+    yh = rng.standard_normal(400)
+    x1, _, it1, _ = O.lsmr_ldiv(A, yh)
+    x2, _, it2, _ = O.lsmr_ldiv(A.toarray(), yh)
+    assert it1 == it2
+    assert 1e-12 < rel(x1, x2) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["csc", "dense"])
+@pytest.mark.parametrize("m,n,damped", [(400, 60, True), (400, 60, False), (6000, 500, True)])
+def test_lsmr_tight(ctx, kind, m, n, damped):
+    """Same solver through the C ABI with atol = btol = 1e-15: converged LSMR == the least-squares solution,
+    compared with the oracle's LSMR at the same tolerances (1e-10) and with the direct QR solve (1e-9)."""
+    import ctypes as C
+    from lsob200 import CSCMatrix, DenseMatrix, DeviceVector, LSMRAllocatedSolver, LSMRDampenedAllocatedSolver
+    from lsob200._lib import check, lib
+    rng = np.random.default_rng(m * 3 + n + damped)
+    A = sp.random(m, n, density=min(1.0, 12.0 / n + 0.002), random_state=m + n + 1, format="csc")
+    A.sort_indices()
+    yh = rng.standard_normal(m)
+    damp = np.asarray(A.multiply(A).sum(axis=0)).ravel() / 10 + 1e-3
+    xr, _, it_r, istop_r = O.lsmr_ldiv(A if kind == "csc" else A.toarray(), yh, damp.copy() if damped else None,
+                                       atol=1e-15, btol=1e-15, conlim=0.0)
+    J = CSCMatrix.from_scipy(ctx, A) if kind == "csc" else DenseMatrix(ctx, m, n, A.toarray())
+    y, x = DeviceVector(ctx, m, yh), DeviceVector(ctx, n)
+    ws = (LSMRDampenedAllocatedSolver if damped else LSMRAllocatedSolver)(ctx, m, n)
+    d = DeviceVector(ctx, n, damp) if damped else None
+    iters, istop = C.c_int64(), C.c_int()
+    check(lib().lso_lsmr_solve(ws._h, J.handle if kind == "csc" else None, J.ptr if kind == "dense" else None,
+                               J.ld if kind == "dense" else 0, y.ptr, d.ptr if damped else None, x.ptr,
+                               1e-15, 1e-15, 0.0, 0, C.byref(iters), C.byref(istop)), ctx.handle)
+    assert abs(iters.value - it_r) <= 2
+    assert rel(x.download(), xr) <= 1e-10
+    xq, _ = O.qr_ldiv(A.toarray(), yh, damp if damped else None)
+    assert rel(x.download(), xq) <= 1e-9
+
+
+@pytest.mark.parametrize("m,n,r", [(9, 6, 5), (40, 40, 31), (300, 64, 40), (2000, 130, 100), (500, 33, 1)])
+def test_qr_rank_deficient_minimum_norm(ctx, m, n, r):
+    """Undamped solve on a rank-deficient J (the factor-model situation, test/nonlinearleastsquares.jl:3-6):
+    the reference's pivoted QR + rank detection + complete orthogonal factorisation returns the minimum-norm
+    least-squares solution; so must the plugin (same rank, δ within 1e-10·cond)."""
+    from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    rng = np.random.default_rng(m + n + r)
+    B = rng.standard_normal((m, r)) @ rng.standard_normal((r, n))
+    Jh = np.asfortranarray(B)
+    yh = rng.standard_normal(m)
+    ws = DenseQRAllocatedSolver(ctx, m, n, damped=False)
+    x = DeviceVector(ctx, n)
+    ws.ldiv(x, DenseMatrix(ctx, m, n, Jh), DeviceVector(ctx, m, yh))
+    xr, rank = O.qr_ldiv(Jh, yh)
+    assert rank == r and ws.last_rank == r
+    assert rel(x.download(), xr) <= 1e-9
+    assert rel(x.download(), np.linalg.pinv(Jh) @ yh) <= 1e-9
+
+
+def test_qr_zero_and_tiny_damping(ctx):
+    """Zero Jacobian column with damping (full rank through the clamp) and an all-zero J without damping (rank 0)."""
+    from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    rng = np.random.default_rng(8)
+    Jh = np.asfortranarray(rng.standard_normal((200, 10)))
+    Jh[:, 4] = 0.0
+    yh = rng.standard_normal(200)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0
+    ws = DenseQRAllocatedSolver(ctx, 200, 10, damped=True)
+    x = DeviceVector(ctx, 10)
+    ws.ldiv(x, DenseMatrix(ctx, 200, 10, Jh), DeviceVector(ctx, 200, yh), DeviceVector(ctx, 10, damp))
+    assert rel(x.download(), O.qr_ldiv(Jh, yh, damp)[0]) <= TOL
+    ws0 = DenseQRAllocatedSolver(ctx, 200, 10, damped=False)
+    ws0.ldiv(x, DenseMatrix(ctx, 200, 10, np.zeros((200, 10))), DeviceVector(ctx, 200, yh))
+    assert ws0.last_rank == 0 and np.all(x.download() == 0.0)
