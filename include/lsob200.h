@@ -53,6 +53,9 @@ int         lso_ctx_sync(lso_ctx* ctx);
 void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-event timing by the caller */
 int         lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value);
 int         lso_ctx_launch_count(lso_ctx* ctx, int64_t* out, int reset); /* kernels launched by this library */
+/* With option "profile" = 1 every launch of the dominant kernel of a solve (QR trailing update, syrk, SpMV pair) is
+ * bracketed by CUDA events on the context stream; this returns their summed duration and count, and resets. */
+int         lso_ctx_profile_read(lso_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* ---- device memory (Julia GC owns nothing on the device; finalizers call *_free) ----- */
 int lso_dev_alloc(lso_ctx* ctx, size_t nbytes, void** d_out);

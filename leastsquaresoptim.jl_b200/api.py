@@ -176,8 +176,10 @@ class LeastSquaresResult:
 class _Allocated:
     """LeastSquaresProblemAllocated (types.jl:141-157): device mirrors of x, y, J + optimizer/solver workspaces."""
 
-    def __init__(self, nls: LeastSquaresProblem, optimizer: AbstractOptimizer):
+    def __init__(self, nls: LeastSquaresProblem, optimizer: AbstractOptimizer, sharded: bool = False):
         self.nls = nls
+        self.sharded = sharded
+        self.optimizer = optimizer
         ctx = self.ctx = nls.ctx
         self.host = not nls.device_callbacks
         if self.host:
@@ -200,8 +202,12 @@ class _Allocated:
         self.m, self.n = m, n
         solver = optimizer.solver
         damped = isinstance(optimizer, LevenbergMarquardt)
+        if sharded and getattr(ctx, "nranks", 1) <= 1:
+            raise ValueError("sharded=True needs a communicator on the context (Context.comm_init)")
         if isinstance(solver, QR):
-            self.solver = DenseQRAllocatedSolver(ctx, m, n, damped)
+            # row-sharded J: local QR of [J_k | y_k] needs the undamped m_k x n workspace; the sqrt(damp) rows join
+            # the stack of R factors (lso_qr_solve_sharded)
+            self.solver = DenseQRAllocatedSolver(ctx, m, n, damped and not sharded, sharded=sharded)
         elif isinstance(solver, Cholesky):
             if self.sparse:
                 raise TypeError("MethodError: no Cholesky solver for sparse Jacobians (dense_cholesky.jl:19)")
@@ -210,6 +216,15 @@ class _Allocated:
             self.solver = LSMRDampenedAllocatedSolver(ctx, m, n) if damped else LSMRAllocatedSolver(ctx, m, n)
         else:
             raise TypeError(f"unknown solver {solver!r}")
+
+    def workspace(self, key, make):
+        """AllocatedLevenbergMarquardt / AllocatedDogleg vectors (levenberg_marquardt.jl:8-31, dogleg.jl:7-30):
+        allocated once per problem and reused by every `optimize!` call on it."""
+        if not hasattr(self, "_ws"):
+            self._ws = {}
+        if key not in self._ws:
+            self._ws[key] = make()
+        return self._ws[key]
 
     # f!(out, x) and g!(J, x) with the data movement each mode needs
     def f(self, out: DeviceVector, x: DeviceVector):
@@ -288,68 +303,113 @@ def _lm_damping(ctx, dtd: DeviceVector, inv_delta: float):
 
 
 # ---- LevenbergMarquardt (levenberg_marquardt.jl:39-144) ----------------------------------------------------
-def _optimize_lm(anls: _Allocated, x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, iterations=1000, Δ=10.0, store_trace=False,
-                 lower=None, upper=None, record_steps=False):
-    ctx, n, m = anls.ctx, anls.n, anls.m
-    x, fcur, J = anls.x, anls.fcur, anls.J
-    dx, dtd = DeviceVector(ctx, n), DeviceVector(ctx, n)
-    ftrial, fpredict = DeviceVector(ctx, m), DeviceVector(ctx, m)
-    dlo, dhi = _bounds(ctx, x, lower, upper)
-    decrease_factor = 2.0
-    f_calls = g_calls = mul_calls = 0
-    converged = x_converged = f_converged = g_converged = False
-    anls.f(fcur, x)
-    f_calls += 1
-    ssr = fcur.sumabs2()
-    maxabs_gr = math.inf
-    need_jacobian = True
-    it = 0
-    tr = [OptimizationState(0, ssr, maxabs_gr)] if store_trace else []
-    deltas = []
-    while not converged and it < iterations:
-        it += 1
+class LMRun:
+    """State of one `optimize!` run with LevenbergMarquardt; `iterate()` is one pass of the `while` body
+    (levenberg_marquardt.jl:72-140).  When the context carries a communicator (row-sharded J, one rank per GPU)
+    the m-dimension reductions are all-reduced over NCCL: x, δ, dtd are replicated, f / J are this rank's rows."""
+
+    def __init__(self, anls: "_Allocated", x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, iterations=1000, Δ=10.0,
+                 store_trace=False, lower=None, upper=None, record_steps=False):
+        self.anls = anls
+        ctx, n, m = anls.ctx, anls.n, anls.m
+        self.ctx = ctx
+        self.x_tol, self.f_tol, self.g_tol, self.iterations = x_tol, f_tol, g_tol, iterations
+        self.store_trace, self.record_steps = store_trace, record_steps
+        w = anls.workspace("lm", lambda: dict(dx=DeviceVector(ctx, n), dtd=DeviceVector(ctx, n),
+                                              ftrial=DeviceVector(ctx, m), fpredict=DeviceVector(ctx, m),
+                                              red=DeviceVector(ctx, 8)))
+        self.dx, self.dtd, self.ftrial, self.fpredict, self.red = w["dx"], w["dtd"], w["ftrial"], w["fpredict"], w["red"]
+        self.dlo, self.dhi = _bounds(ctx, anls.x, lower, upper)
+        self.sharded = getattr(ctx, "nranks", 1) > 1
+        self.Δ = float(Δ)
+        self.decrease_factor = 2.0
+        self.f_calls = self.g_calls = self.mul_calls = 0
+        self.converged = self.x_converged = self.f_converged = self.g_converged = False
+        anls.f(anls.fcur, anls.x)
+        self.f_calls += 1
+        self.ssr = self._allsum(anls.fcur.sumabs2())
+        self.maxabs_gr = math.inf
+        self.need_jacobian = True
+        self.it = 0
+        self.tr = [OptimizationState(0, self.ssr, self.maxabs_gr)] if store_trace else []
+        self.deltas = []
+
+    def _allsum(self, *vals):
+        """Sum scalars over ranks (identity on one GPU)."""
+        if not self.sharded:
+            return vals[0] if len(vals) == 1 else vals
+        buf = np.zeros(8)
+        buf[:len(vals)] = vals
+        self.red.upload(buf)
+        self.ctx.allreduce(self.red)
+        out = self.red.download()
+        return float(out[0]) if len(vals) == 1 else tuple(float(v) for v in out[:len(vals)])
+
+    def iterate(self):
+        anls, ctx = self.anls, self.ctx
+        x, fcur, J = anls.x, anls.fcur, anls.J
+        dx, dtd, ftrial, fpredict = self.dx, self.dtd, self.ftrial, self.fpredict
+        self.it += 1
         x.check_finite()
-        if need_jacobian:
+        if self.need_jacobian:
             anls.g(x)
-            g_calls += 1
-            need_jacobian = False
-        J.colsumabs2(dtd)                                 # :82
-        _lm_damping(ctx, dtd, 1 / Δ)                      # :84-86
-        _, lmiter = anls.solver.ldiv(dx, J, fcur, dtd)    # :87
-        if record_steps:
-            deltas.append(dx.download())
-        _box_project(ctx, dx, x, dlo, dhi)                # :89-98
-        mul_calls += lmiter
-        J.mul_t(dtd, fcur, 1.0, 0.0)                      # :102 gradient J'f
-        mul_calls += 1
-        maxabs_gr = _maxabs_projected_gradient(ctx, dtd, x, dlo, dhi)
-        x.axpy(-1.0, dx)                                  # :106
+            self.g_calls += 1
+            self.need_jacobian = False
+        J.colsumabs2(dtd)                                     # :82
+        if self.sharded:
+            ctx.allreduce(dtd)
+        _lm_damping(ctx, dtd, 1 / self.Δ)                     # :84-86
+        _, lmiter = anls.solver.ldiv(dx, J, fcur, dtd)        # :87
+        if self.record_steps:
+            self.deltas.append(dx.download())
+        _box_project(ctx, dx, x, self.dlo, self.dhi)          # :89-98
+        self.mul_calls += lmiter
+        J.mul_t(dtd, fcur, 1.0, 0.0)                          # :102 gradient J'f
+        if self.sharded:
+            ctx.allreduce(dtd)
+        self.mul_calls += 1
+        self.maxabs_gr = _maxabs_projected_gradient(ctx, dtd, x, self.dlo, self.dhi)
+        x.axpy(-1.0, dx)                                      # :106
         anls.f(ftrial, x)
-        f_calls += 1
+        self.f_calls += 1
         trial_ssr = ftrial.sumabs2()
         predicted_ssr = J.predicted_ssr(dx, fcur, fpredict)   # :114-117 fused
-        mul_calls += 1
+        if self.sharded:
+            trial_ssr, predicted_ssr = self._allsum(trial_ssr, predicted_ssr)
+        self.mul_calls += 1
+        ssr = self.ssr
         predicted_reduction = abs(ssr - predicted_ssr)
         ρ = (ssr - trial_ssr) / predicted_reduction if predicted_reduction > 0 else 0.0
         step_accepted = ρ > MIN_STEP_QUALITY
-        x_converged, f_converged, g_converged, converged = assess_convergence(
-            dx, maxabs_gr, ssr, trial_ssr, x_tol, f_tol, g_tol, step_accepted)
+        self.x_converged, self.f_converged, self.g_converged, self.converged = assess_convergence(
+            dx, self.maxabs_gr, ssr, trial_ssr, self.x_tol, self.f_tol, self.g_tol, step_accepted)
         if step_accepted:
             fcur.copyto(ftrial)
-            ssr = trial_ssr
+            self.ssr = trial_ssr
             t = 2.0 * ρ - 1.0
-            Δ = min(Δ / max(1 / 3, 1.0 - t * t * t), MAX_DELTA)
-            decrease_factor = 2.0
-            need_jacobian = True
+            self.Δ = min(self.Δ / max(1 / 3, 1.0 - t * t * t), MAX_DELTA)
+            self.decrease_factor = 2.0
+            self.need_jacobian = True
         else:
             x.axpy(1.0, dx)
-            Δ = max(Δ / decrease_factor, MIN_DELTA)
-            decrease_factor *= 2.0
-        if store_trace:
-            tr.append(OptimizationState(it, ssr, maxabs_gr))
-    xmin = anls.finish(x)
-    return LeastSquaresResult("LevenbergMarquardt", xmin, ssr, it, converged, x_converged, x_tol, f_converged,
-                              f_tol, g_converged, g_tol, tr, f_calls, g_calls, mul_calls, deltas)
+            self.Δ = max(self.Δ / self.decrease_factor, MIN_DELTA)
+            self.decrease_factor *= 2.0
+        if self.store_trace:
+            self.tr.append(OptimizationState(self.it, self.ssr, self.maxabs_gr))
+        return step_accepted
+
+    def result(self):
+        xmin = self.anls.finish(self.anls.x)
+        return LeastSquaresResult("LevenbergMarquardt", xmin, self.ssr, self.it, self.converged, self.x_converged,
+                                  self.x_tol, self.f_converged, self.f_tol, self.g_converged, self.g_tol, self.tr,
+                                  self.f_calls, self.g_calls, self.mul_calls, self.deltas)
+
+
+def _optimize_lm(anls: _Allocated, **kw):
+    run = LMRun(anls, **kw)
+    while not run.converged and run.it < run.iterations:
+        run.iterate()
+    return run.result()
 
 
 # ---- Dogleg (dogleg.jl:41-203) ---------------------------------------------------------------------------------
@@ -436,14 +496,62 @@ def _optimize_dogleg(anls: _Allocated, x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, itera
                               g_converged, g_tol, tr, f_calls, g_calls, mul_calls, deltas)
 
 
+class HostStep:
+    """Hot-path body of one LevenbergMarquardt iteration driven from HOST buffers (the e2e path of bench.py and
+    what the Julia glue does when `J` / `f` are plain host Arrays): H2D of J and f, colsumabs2! + damping (LM:82-86),
+    the damped solve (:87), J'f and its max-norm (:102-104), ||Jδ - f||² (:114-117), then D2H of δ and the scalars."""
+
+    def __init__(self, anls: "_Allocated"):
+        from ._lib import check, lib
+        self.anls, self.ctx = anls, anls.ctx
+        self.lib, self.check = lib(), check
+        ctx, n, m = anls.ctx, anls.n, anls.m
+        w = anls.workspace("lm", lambda: dict(dx=DeviceVector(ctx, n), dtd=DeviceVector(ctx, n),
+                                              ftrial=DeviceVector(ctx, m), fpredict=DeviceVector(ctx, m),
+                                              red=DeviceVector(ctx, 8)))
+        self.dx, self.dtd, self.fpredict, self.red = w["dx"], w["dtd"], w["fpredict"], w["red"]
+        self.sharded = getattr(ctx, "nranks", 1) > 1
+
+    def run(self, hJ_ptr: int, hf_ptr: int, Δ: float, dx_host: np.ndarray):
+        a, ctx, h = self.anls, self.ctx, self.ctx.handle
+        J, fcur, dx, dtd = a.J, a.fcur, self.dx, self.dtd
+        self.check(self.lib.lso_upload_async(h, J.ptr, hJ_ptr, a.m * a.n * 8), h)
+        self.check(self.lib.lso_upload_async(h, fcur.ptr, hf_ptr, a.m * 8), h)
+        ssr = fcur.sumabs2()
+        J.colsumabs2(dtd)
+        if self.sharded:
+            ctx.allreduce(dtd)
+        _lm_damping(ctx, dtd, 1 / Δ)
+        a.solver.ldiv(dx, J, fcur, dtd)
+        J.mul_t(dtd, fcur, 1.0, 0.0)
+        if self.sharded:
+            ctx.allreduce(dtd)
+        maxabs_gr = dtd.maxabs()
+        predicted_ssr = J.predicted_ssr(dx, fcur, self.fpredict)
+        if self.sharded:
+            buf = np.zeros(8)
+            buf[:2] = (ssr, predicted_ssr)
+            self.red.upload(buf)
+            ctx.allreduce(self.red)
+            ssr, predicted_ssr = (float(v) for v in self.red.download()[:2])
+        dx.download(dx_host)
+        return {"ssr": ssr, "predicted_ssr": predicted_ssr, "maxabs_gr": maxabs_gr, "maxabs_dx": float(np.abs(dx_host).max())}
+
+
 def optimize_(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, **kwargs) -> LeastSquaresResult:
     """`optimize!(nls, optimizer; kwargs...)` — types.jl:207-209 + LeastSquaresProblemAllocated (:152-157)."""
-    solver = default_solver(optimizer.solver if optimizer is not None else None, nls.J)
-    optimizer = default_optimizer(optimizer, solver)
-    anls = _Allocated(nls, optimizer)
-    if isinstance(optimizer, LevenbergMarquardt):
+    anls = nls if isinstance(nls, _Allocated) else allocate(nls, optimizer)
+    if isinstance(anls.optimizer, LevenbergMarquardt):
         return _optimize_lm(anls, **kwargs)
     return _optimize_dogleg(anls, **kwargs)
+
+
+def allocate(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, sharded: bool = False) -> "_Allocated":
+    """`LeastSquaresProblemAllocated(nls, optimizer)` — types.jl:152-157: default solver/optimizer dispatch, then the
+    optimizer and solver workspaces.  The result can be passed to `optimize_` repeatedly (no allocation per run)."""
+    solver = default_solver(optimizer.solver if optimizer is not None else None, nls.J)
+    optimizer = default_optimizer(optimizer, solver)
+    return _Allocated(nls, optimizer, sharded=sharded)
 
 
 def optimize(f: Callable, x0, optimizer: AbstractOptimizer, **kwargs) -> LeastSquaresResult:

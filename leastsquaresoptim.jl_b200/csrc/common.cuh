@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 #include "../../include/lsob200.h"
 
 #define LSO_NUM_SMS_DEFAULT 148
@@ -23,6 +24,9 @@ struct lso_ctx {
     // options
     int64_t opt_qr_apply = 1;          // 0 = plain-FMA apply kernel, 1 = DMMA apply kernel
     int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
+    int64_t opt_profile = 0;           // 1 = bracket every launch of the dominant kernel with CUDA events
+    std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
+    size_t prof_used = 0;
     // scratch of the rank-revealing small-R finish (qr_finish.cu), grown on demand
     double* d_finish = nullptr;
     size_t finish_cap = 0;
@@ -66,6 +70,17 @@ int lso_set_error(lso_ctx* ctx, int code, const char* fmt, ...);
         int _s = (expr);                                                                        \
         if (_s != 0) return _s;                                                                 \
     } while (0)
+
+// CUDA-event bracketing of the dominant kernel's launches (bench.py roofline: live, on the launching stream)
+static inline void lso_prof_mark(lso_ctx* ctx) {
+    if (!ctx->opt_profile) return;
+    if (ctx->prof_used == ctx->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->prof_events.push_back(e);
+    }
+    cudaEventRecord(ctx->prof_events[ctx->prof_used++], ctx->stream);
+}
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t roundup64(int64_t a, int64_t b) { return cdiv64(a, b) * b; }

@@ -70,6 +70,7 @@ int lso_ctx_destroy(lso_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_finish);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     cudaFreeHost(ctx->h_scalars);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -90,6 +91,7 @@ int lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value) {
     LSO_REQUIRE(ctx, ctx && key, "ctx/key is NULL");
     if (!strcmp(key, "qr_apply")) ctx->opt_qr_apply = value;
     else if (!strcmp(key, "syrk")) ctx->opt_syrk = value;
+    else if (!strcmp(key, "profile")) { ctx->opt_profile = value; ctx->prof_used = 0; }
     else return lso_set_error(ctx, LSO_ERR_ARG, "unknown option '%s'", key);
     return LSO_OK;
 }
@@ -98,6 +100,21 @@ int lso_ctx_launch_count(lso_ctx* ctx, int64_t* out, int reset) {
     LSO_REQUIRE(ctx, ctx && out, "ctx/out is NULL");
     *out = ctx->launches;
     if (reset) ctx->launches = 0;
+    return LSO_OK;
+}
+
+int lso_ctx_profile_read(lso_ctx* ctx, double* total_ms, int64_t* launches) {
+    LSO_REQUIRE(ctx, ctx && total_ms && launches, "NULL pointer");
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        float ms = 0.f;
+        LSO_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(ctx->prof_used / 2);
+    ctx->prof_used = 0;
     return LSO_OK;
 }
 

@@ -35,163 +35,154 @@ __device__ __forceinline__ bool tm_row(const TileMap& tm, long long blk, int p, 
 }
 
 // =================================================================================================
-// leaf kernel: Householder QR of one QH x QB block.  256 threads: lane = column, warp = 32-row group,
-// each thread keeps its 32 column entries in registers.
+// leaf kernel: Householder QR of one QH x QB block.  256 threads: lane = column, warp = 32-row group; each
+// thread keeps its 32 column entries in registers (its rows are one contiguous 256-byte run in memory at
+// every level, so loads / stores go straight between global memory and registers, 16 bytes at a time).
+// Per Householder step: the owner lane publishes the pivot column, every thread forms its partial
+// v'a_k (or v_k'v_j for the columns already factorised) in ONE pass, a block-wide reduction over the 8 row
+// groups follows, and the rank-1 update is applied from the published column.  The T factor of the compact
+// WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V) (no work on the critical path).
 // =================================================================================================
-#define LEAF_XS (QH + 1)
-#define LEAF_SMEM_BYTES ((QB * LEAF_XS + 2 * QH + 2 * QB + 8 * QB + QB + QB * 33 + QB + QB * 33) * 8)
-
-template <bool MASKED>
-__device__ __forceinline__ void leaf_step(double (&x)[32], int j, int lane, int grp, const double* colbuf,
-                                          const double* rowbuf, double* red, double* zbuf, double* taus) {
-    // masked pivot column: rows r > j participate in the reflector
-    double pc[32];
-    double d = 0.0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        double v = colbuf[grp * 32 + i];
-        if (MASKED) v = (i > j) ? v : 0.0;
-        pc[i] = v;
-        d = fma(v, x[i], d);
-    }
-    red[grp * 32 + lane] = d;
-    __syncthreads();   // S2
-    double s_k = 0.0, s_j = 0.0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        s_k += red[g * 32 + lane];
-        s_j += red[g * 32 + j];
-    }
-    const double alpha = colbuf[j];
-    const double rowk = rowbuf[lane];
-    double beta, tau, scale;
-    if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
-        beta = alpha; tau = 0.0; scale = 0.0;
-    } else {
-        beta = -copysign(sqrt(fma(alpha, alpha, s_j)), alpha);
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
-    }
-    const double wz = fma(scale, s_k, rowk);    // v_j' a_k  (k > j)   or   v_k' v_j (k < j)
-    if (lane > j) {
-        const double coef = tau * wz;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            double vf = pc[i] * scale;
-            if (MASKED) vf = (i == j) ? 1.0 : vf;
-            x[i] = fma(-coef, vf, x[i]);
-        }
-    } else if (lane == j) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (MASKED) x[i] = (i > j) ? pc[i] * scale : ((i == j) ? beta : x[i]);
-            else x[i] = pc[i] * scale;
-        }
-        if (grp == 0) taus[j] = tau;
-    } else if (grp == 0) {
-        zbuf[lane] = wz;
-    }
-}
-
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
                double* __restrict__ Tout) {
-    extern __shared__ double lsm[];
-    double* Xs = lsm;                      // [QB][LEAF_XS]
-    double* colbuf = Xs + QB * LEAF_XS;    // [2][QH]
-    double* rowbuf = colbuf + 2 * QH;      // [2][QB]
-    double* red = rowbuf + 2 * QB;         // [8][QB]
-    double* zbuf = red + 8 * QB;           // [QB]
-    double* Ts = zbuf + QB;                // [QB][33]   Ts[i*33 + k] = T[k][i]  (column i of T)
-    double* taus = Ts + QB * 33;           // [QB]
-    double* Rs = taus + QB;                // [QB][33]   Rs[r*33 + k]
+    __shared__ __align__(16) double colbuf[2][QH];
+    __shared__ double rowbuf[2][QB];
+    __shared__ double red[8][QB];
+    __shared__ double Zs[QB][QB + 1];      // Zs[j][k] = v_k' v_j  (k < j)
+    __shared__ double taus[QB];
 
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const long long blk = blockIdx.x;
+    long long mrow0;
+    const bool valid = tm_row(tm, blk, grp * 32, mrow0);
+    double* __restrict__ gcol = A + (c0 + lane) * ld + mrow0;
 
-    // ---- gather the block (coalesced along rows) ----
-    for (int col = grp; col < QB; col += 8) {
-        const double* __restrict__ src = A + (c0 + col) * ld;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int p = q * 32 + lane;
-            long long mrow;
-            const bool ok = tm_row(tm, blk, p, mrow);
-            Xs[col * LEAF_XS + p] = ok ? src[mrow] : 0.0;
-        }
-    }
-    for (int i = tid; i < QB * 33; i += 256) Ts[i] = 0.0;
-    __syncthreads();
     double x[32];
+    if (valid) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = Xs[lane * LEAF_XS + grp * 32 + i];
+        for (int i = 0; i < 32; i += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(gcol + i);
+            x[i] = v.x; x[i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.0;
+    }
 
-    // ---- QB Householder steps ----
     for (int j = 0; j < QB; ++j) {
-        double* cb = colbuf + (j & 1) * QH;
-        double* rb = rowbuf + (j & 1) * QB;
+        double* cb = colbuf[j & 1];
+        double* rb = rowbuf[j & 1];
         if (lane == j) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) cb[grp * 32 + i] = x[i];
+            for (int i = 0; i < 32; i += 2) {
+                double2 v;
+                // rows above the diagonal (group 0 only) do not take part in the reflector
+                v.x = (grp == 0 && i <= j) ? 0.0 : x[i];
+                v.y = (grp == 0 && i + 1 <= j) ? 0.0 : x[i + 1];
+                *reinterpret_cast<double2*>(cb + grp * 32 + i) = v;
+            }
         }
         if (grp == 0) {
             double xj = 0.0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) xj = (i == j) ? x[i] : xj;
-            rb[lane] = xj;
+            rb[lane] = xj;                   // pivot-row entry of column `lane`
         }
         __syncthreads();   // S1
-        // T column j-1 (larft): T[0:jm, jm] = -tau_jm * T[0:jm,0:jm] * (V[:,0:jm]' v_jm)
-        if (grp == 7 && j > 0) {
-            const int jm = j - 1;
-            const double tj = taus[jm];
-            if (lane < jm) {
-                double acc = 0.0;
-                for (int i = lane; i < jm; ++i) acc = fma(Ts[i * 33 + lane], zbuf[i], acc);
-                Ts[jm * 33 + lane] = -tj * acc;
-            } else if (lane == jm) {
-                Ts[jm * 33 + jm] = tj;
+        double d = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(cb + grp * 32 + i);
+            d = fma(v.x, x[i], d);
+            d = fma(v.y, x[i + 1], d);
+        }
+        red[grp][lane] = d;
+        __syncthreads();   // S2
+        double s_k = 0.0, s_j = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            s_k += red[g][lane];
+            s_j += red[g][j];
+        }
+        const double alpha = rb[j];
+        const double rowk = rb[lane];
+        double beta, tau, scale;
+        if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
+            beta = alpha; tau = 0.0; scale = 0.0;
+        } else {
+            beta = -copysign(sqrt(fma(alpha, alpha, s_j)), alpha);
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        const double wz = fma(scale, s_k, rowk);    // v_j' a_k  (k > j)   or   v_k' v_j  (k < j)
+        if (lane > j) {
+            const double coef = tau * wz;
+            const double cs = -coef * scale;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(cb + grp * 32 + i);
+                x[i] = fma(cs, v.x, x[i]);
+                x[i + 1] = fma(cs, v.y, x[i + 1]);
+            }
+            if (grp == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = (i == j) ? x[i] - coef : x[i];   // pivot row: v_j = 1
+            }
+        } else if (lane == j) {
+            if (grp == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = (i > j) ? x[i] * scale : ((i == j) ? beta : x[i]);
+                taus[j] = tau;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] *= scale;
+            }
+        } else if (grp == 0) {
+            Zs[j][lane] = wz;
+        }
+    }
+    __syncthreads();
+
+    // ---- V (explicit unit diagonal, zeros above) to the workspace; R head back into the matrix ----
+    double* __restrict__ Vb = Vout + blk * (long long)(QB * QS) + lane * QS + grp * 32;
+    if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            double2 v;
+            v.x = (i > lane) ? x[i] : ((i == lane) ? 1.0 : 0.0);
+            v.y = (i + 1 > lane) ? x[i + 1] : ((i + 1 == lane) ? 1.0 : 0.0);
+            *reinterpret_cast<double2*>(Vb + i) = v;
+        }
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                double2 v;
+                v.x = (i <= lane) ? x[i] : 0.0;
+                v.y = (i + 1 <= lane) ? x[i + 1] : 0.0;
+                *reinterpret_cast<double2*>(gcol + i) = v;
             }
         }
-        if (grp == 0) leaf_step<true>(x, j, lane, grp, cb, rb, red, zbuf, taus);
-        else leaf_step<false>(x, j, lane, grp, cb, rb, red, zbuf, taus);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) *reinterpret_cast<double2*>(Vb + i) = make_double2(x[i], x[i + 1]);
     }
-    __syncthreads();
-    if (grp == 7) {
-        const int jm = QB - 1;
-        const double tj = taus[jm];
-        if (lane < jm) {
+
+    // ---- T = (diag(1/tau) + striu(V'V))^{-1}, one column per lane of warp 0 (division-free back substitution) ----
+    if (grp == 0) {
+        double t[32];
+        const double tau_c = taus[lane];
+#pragma unroll
+        for (int k = 31; k >= 0; --k) {
             double acc = 0.0;
-            for (int i = lane; i < jm; ++i) acc = fma(Ts[i * 33 + lane], zbuf[i], acc);
-            Ts[jm * 33 + lane] = -tj * acc;
-        } else if (lane == jm) {
-            Ts[jm * 33 + jm] = tj;
-        }
-    }
-    // ---- stage V (explicit unit diagonal, zeros above) and R ----
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const int r = grp * 32 + i;
-        Xs[lane * LEAF_XS + r] = (r > lane) ? x[i] : ((r == lane) ? 1.0 : 0.0);
-        if (grp == 0) Rs[i * 33 + lane] = (i <= lane) ? x[i] : 0.0;
-    }
-    __syncthreads();
-    double* __restrict__ Vb = Vout + blk * (long long)(QB * QS);
-    for (int col = grp; col < QB; col += 8) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int p = q * 32 + lane;
-            Vb[col * QS + p] = Xs[col * LEAF_XS + p];
+            for (int i = k + 1; i < 32; ++i) acc = fma(Zs[i][k], t[i], acc);
+            const double tk = -acc * taus[k];
+            t[k] = (k == lane) ? tau_c : ((k < lane) ? tk : 0.0);
         }
-        // head of the block: R in the upper triangle, zeros below
-        long long mrow;
-        const bool ok = tm_row(tm, blk, lane, mrow);
-        if (ok) A[(c0 + col) * ld + mrow] = Rs[lane * 33 + col];
-    }
-    double* __restrict__ Tb = Tout + blk * (long long)(QB * QB);
-    for (int e = tid; e < QB * QB; e += 256) {
-        const int k = e & 31, i = e >> 5;       // T[k][i], column-major
-        Tb[e] = Ts[i * 33 + k];
+        double* __restrict__ Tb = Tout + blk * (long long)(QB * QB) + lane * QB;   // column `lane`, column-major
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(Tb + k) = make_double2(t[k], t[k + 1]);
     }
 }
 
@@ -267,8 +258,8 @@ qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
 #define AM_NST 3
 #define AM_VS_BYTES (QB * QS * 8)
 #define AM_XS_BYTES (QCT * QS * 8)
-#define AM_WP_BYTES (QCT * QWS * 8)
-#define AM_SMEM_BYTES (AM_VS_BYTES + AM_NST * AM_XS_BYTES + 10 * AM_WP_BYTES + QB * 33 * 8 + 64)
+#define QWP (QB + 8)    /* stride of the per-warp partial buffers: 16-byte stores of 8 lanes hit 32 distinct banks */
+#define AM_SMEM_BYTES (AM_VS_BYTES + AM_NST * AM_XS_BYTES + 8 * QCT * QWP * 8 + 2 * QCT * QWS * 8 + QB * 33 * 8 + 64)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -317,12 +308,13 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
     extern __shared__ __align__(128) unsigned char amsm[];
     double* Vs = (double*)amsm;                                           // [QB][QS]
     double* Xs = (double*)(amsm + AM_VS_BYTES);                           // [AM_NST][QCT][QS]
-    double* Wp = (double*)(amsm + AM_VS_BYTES + AM_NST * AM_XS_BYTES);    // [8][QCT][QWS] partial W
-    double* Wsum = Wp + 8 * QCT * QWS;                                    // [QCT][QWS]
-    double* Wfin = Wsum + QCT * QWS;                                      // [QCT][QWS]   T' W
+    double* Wp = (double*)(amsm + AM_VS_BYTES + AM_NST * AM_XS_BYTES);    // [8][QCT][QWP] partial (V'X)' per warp
+    double* Wsum = Wp + 8 * QCT * QWP;                                    // [QCT][QWS]
+    double* Wfin = Wsum + QCT * QWS;                                      // [QCT][QWS]   -(T' V'X)
     double* Ts = Wfin + QCT * QWS;                                        // Ts[i*33 + k] = T[k][i]
-    uint64_t* bars = (uint64_t*)(Ts + QB * 33);                           // full[3], done[3], vfull
-    const uint32_t bar_full = smem_u32(bars), bar_done = smem_u32(bars + AM_NST), bar_v = smem_u32(bars + 2 * AM_NST);
+    uint64_t* bars = (uint64_t*)(Ts + QB * 33);                           // full[3], done[3], vfull, vfree
+    const uint32_t bar_full = smem_u32(bars), bar_done = smem_u32(bars + AM_NST), bar_v = smem_u32(bars + 2 * AM_NST),
+                   bar_vfree = smem_u32(bars + 2 * AM_NST + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const long long jtot = nblocks * ntiles;
@@ -336,6 +328,7 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
             mbar_init(bar_done + 8 * s, 256);
         }
         mbar_init(bar_v, 1);
+        mbar_init(bar_vfree, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
@@ -346,44 +339,24 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
     const uint32_t seg_bytes = (uint32_t)seg_rows * 8u;
 
     if (wrp == 8) {
-        // =========================== producer warp ===========================
-        int stored = 0;
+        // =========================== producer warp: TMA-unit bulk loads only ===========================
         long long cur_blk = -1;
-        auto store_job = [&](int v) {
-            const long long q = q_begin + v;
-            const long long blk = q / ntiles;
-            const int tile = (int)(q - blk * ntiles);
-            const int s = v % AM_NST;
-            mbar_wait(bar_done + 8 * s, (uint32_t)((v / AM_NST) & 1));
-            const uint32_t xs = smem_u32(Xs + s * QCT * QS);
-            const long long cbase = ctrail + (long long)tile * QCT;
-            for (int e = lane; e < QCT * tm.nseg; e += 32) {
-                const int col = e / tm.nseg, qq = e - col * tm.nseg;
-                const long long item = blk * tm.nseg + qq;
-                if (item < tm.n_items) {
-                    double* dst = A + (cbase + col) * ld + tm.r0 + item * tm.seg_stride;
-                    bulk_s2g(dst, xs + (uint32_t)(col * QS + qq * seg_rows) * 8u, seg_bytes);
-                }
-            }
-            bulk_commit();
-            bulk_wait_read0();
-            __syncwarp();
-        };
+        int seg_i = -1;
         for (int u = 0; u < njobs; ++u) {
             const long long q = q_begin + u;
             const long long blk = q / ntiles;
             const int tile = (int)(q - blk * ntiles);
             const int s = u % AM_NST;
             if (blk != cur_blk) {
-                while (stored < u) { store_job(stored); ++stored; }   // consumers are done with the old V
+                if (seg_i >= 0) mbar_wait(bar_vfree, (uint32_t)(seg_i & 1));   // consumers are done with the old V
                 cur_blk = blk;
+                ++seg_i;
                 if (lane == 0) {
                     mbar_expect_tx(bar_v, AM_VS_BYTES);
                     bulk_g2s(smem_u32(Vs), V + blk * (long long)(QB * QS), AM_VS_BYTES, bar_v);
                 }
             }
-            while (stored <= u - AM_NST) { store_job(stored); ++stored; }
-            // ---- load tile u into stage s ----
+            if (u >= AM_NST) mbar_wait(bar_done + 8 * s, (uint32_t)(((u / AM_NST) - 1) & 1));   // stage drained
             double* xst = Xs + s * QCT * QS;
             long long nvalid = tm.n_items - blk * tm.nseg;
             if (nvalid > tm.nseg) nvalid = tm.nseg;
@@ -408,67 +381,72 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
                 }
             }
         }
-        while (stored < njobs) { store_job(stored); ++stored; }
-        bulk_wait0();
         return;
     }
 
     // =============================== consumer warps ===============================
+    // warp w owns tile rows [32w, 32w+32): its K-slice in GEMM1 and its output rows in GEMM2.  Both products
+    // are formed transposed (tile columns on the MMA M axis) so that every accumulator fragment is two
+    // consecutive ROWS of one column: 16-byte shared loads and 16-byte global stores.
     const int g = lane >> 2, t = lane & 3;
     long long cur_blk = -1;
     int seg_i = -1;
+    long long wrow0 = 0;      // matrix row of this warp's first tile row
+    bool wvalid = true;
     for (int u = 0; u < njobs; ++u) {
         const long long q = q_begin + u;
         const long long blk = q / ntiles;
+        const int tile = (int)(q - blk * ntiles);
         const int s = u % AM_NST;
         if (blk != cur_blk) {
             cur_blk = blk;
             ++seg_i;
             const double* __restrict__ Tb = T + blk * (long long)(QB * QB);
             for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * 33 + k] = Tb[e]; }
+            wvalid = tm_row(tm, blk, 32 * wrp, wrow0);
             mbar_wait(bar_v, (uint32_t)(seg_i & 1));
         }
+        const bool last_of_seg = (u + 1 == njobs) || ((q + 1) / ntiles != blk);
         mbar_wait(bar_full + 8 * s, (uint32_t)((u / AM_NST) & 1));
-        double* Xst = Xs + s * QCT * QS;
+        const double* Xst = Xs + s * QCT * QS;
 
-        // ---- GEMM1: partial W_w = V[32w:32w+32, :]' X[32w:32w+32, :]  (QB x QCT) ----
+        // ---- GEMM1 (transposed): partial (V'X)'_w = X[32w:32w+32, :]' V[32w:32w+32, :]   (QCT x QB) ----
         {
-            double c1[4][2][2];
+            double c1[2][4][2];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) c1[mi][ni][0] = c1[mi][ni][1] = 0.0;
+                for (int ni = 0; ni < 4; ++ni) c1[mi][ni][0] = c1[mi][ni][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int k0 = 32 * wrp + 4 * ks + t;
-                double a[4], b[2];
+                double a[2], b[4];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) a[mi] = Vs[(8 * mi + g) * QS + k0];
+                for (int mi = 0; mi < 2; ++mi) a[mi] = Xst[(8 * mi + g) * QS + k0];
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) b[ni] = Xst[(8 * ni + g) * QS + k0];
+                for (int ni = 0; ni < 4; ++ni) b[ni] = Vs[(8 * ni + g) * QS + k0];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) dmma(c1[mi][ni], a[mi], b[ni]);
+                    for (int ni = 0; ni < 4; ++ni) dmma(c1[mi][ni], a[mi], b[ni]);
             }
-            double* wp = Wp + wrp * QCT * QWS;
+            double* wp = Wp + wrp * QCT * QWP;
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    wp[(8 * ni + 2 * t + 0) * QWS + 8 * mi + g] = c1[mi][ni][0];
-                    wp[(8 * ni + 2 * t + 1) * QWS + 8 * mi + g] = c1[mi][ni][1];
-                }
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(wp + (8 * mi + g) * QWP + 8 * ni + 2 * t) =
+                        make_double2(c1[mi][ni][0], c1[mi][ni][1]);
         }
         consumer_sync();
-        // ---- reduce the 8 partials: Wsum[c][k] ----
+        // ---- reduce the 8 partials: Wsum[c][k] = (V'X)[k][c] ----
         {
             const int c = tid >> 4, k = tid & 15;
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                s0 += Wp[w * QCT * QWS + c * QWS + k];
-                s1 += Wp[w * QCT * QWS + c * QWS + k + 16];
+                s0 += Wp[w * QCT * QWP + c * QWP + k];
+                s1 += Wp[w * QCT * QWP + c * QWP + k + 16];
             }
             Wsum[c * QWS + k] = s0;
             Wsum[c * QWS + k + 16] = s1;
@@ -488,40 +466,42 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
             Wfin[c * QWS + i0 + 16] = -s1;
         }
         consumer_sync();
-        // ---- GEMM2: X[32w:32w+32, :] += V[32w:32w+32, :] * Wfin ----
+        // ---- GEMM2 (transposed): X[32w:32w+32, :]' += Wfin' V[32w:32w+32, :]' ; results go straight to HBM ----
         {
-            double c2[4][2][2];
-            const int rbase = 32 * wrp + g;
+            double c2[2][4][2];
+            const int rbase = 32 * wrp + 2 * t;
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    c2[mi][ni][0] = Xst[(8 * ni + 2 * t + 0) * QS + rbase + 8 * mi];
-                    c2[mi][ni][1] = Xst[(8 * ni + 2 * t + 1) * QS + rbase + 8 * mi];
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
+                    c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
                 }
+            mbar_arrive(bar_done + 8 * s);          // this thread no longer reads the staged tile
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int k0 = 4 * ks + t;
-                double a[4], b[2];
+                double a[2], b[4];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) a[mi] = Vs[k0 * QS + rbase + 8 * mi];
+                for (int mi = 0; mi < 2; ++mi) a[mi] = Wfin[(8 * mi + g) * QWS + k0];
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) b[ni] = Wfin[(8 * ni + g) * QWS + k0];
+                for (int ni = 0; ni < 4; ++ni) b[ni] = Vs[k0 * QS + 32 * wrp + 8 * ni + g];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
+                    for (int ni = 0; ni < 4; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
             }
+            if (last_of_seg) mbar_arrive(bar_vfree);     // V of this block is dead for this thread
+            if (wvalid) {
+                double* __restrict__ dst = A + (ctrail + (long long)tile * QCT + g) * ld + wrow0 + 2 * t;
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    Xst[(8 * ni + 2 * t + 0) * QS + rbase + 8 * mi] = c2[mi][ni][0];
-                    Xst[(8 * ni + 2 * t + 1) * QS + rbase + 8 * mi] = c2[mi][ni][1];
-                }
+                    for (int ni = 0; ni < 4; ++ni)
+                        *reinterpret_cast<double2*>(dst + (long long)(8 * mi) * ld + 8 * ni) =
+                            make_double2(c2[mi][ni][0], c2[mi][ni][1]);
+            }
         }
-        fence_async_smem();
-        mbar_arrive(bar_done + 8 * s);
     }
 }
 
@@ -643,7 +623,6 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
     plan->nlevels = L;
     static bool attr_done = false;
     if (!attr_done) {
-        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
         attr_done = true;
@@ -687,7 +666,7 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
             nb = cdiv64(nb, QG);
         }
         for (int l = 0; l < L; ++l) {
-            qr_leaf_kernel<<<(unsigned)nblk[l], 256, LEAF_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, c0, tms[l],
+            qr_leaf_kernel<<<(unsigned)nblk[l], 256, 0, ctx->stream>>>(plan->A, plan->ld, c0, tms[l],
                                                                                     plan->lev[l].V, plan->lev[l].T);
             LSO_CHECK_LAUNCH(ctx);
         }
@@ -706,8 +685,10 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
             } else {
                 int64_t jtot = nblk[l] * ntiles;
                 int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
+                lso_prof_mark(ctx);
                 qr_apply_mma_kernel<<<grid, 288, AM_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, ctrail, ntiles, nblk[l],
                                                                               tms[l], plan->lev[l].V, plan->lev[l].T);
+                lso_prof_mark(ctx);
             }
             LSO_CHECK_LAUNCH(ctx);
         }

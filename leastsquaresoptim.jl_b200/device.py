@@ -49,6 +49,12 @@ class Context:
         check(lib().lso_ctx_launch_count(self._h, C.byref(out), int(reset)), self._h)
         return out.value
 
+    def profile_read(self):
+        """(total_ms, launches) of the event-bracketed dominant-kernel launches since the last read."""
+        ms, cnt = C.c_double(), C.c_int64()
+        check(lib().lso_ctx_profile_read(self._h, C.byref(ms), C.byref(cnt)), self._h)
+        return ms.value, cnt.value
+
     # -- raw memory --
     def alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -61,6 +67,16 @@ class Context:
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         check(lib().lso_comm_init_rank(self._h, nranks, rank, buf), self._h)
+        self.nranks, self.rank = nranks, rank
+
+    nranks = 1
+    rank = 0
+
+    def allreduce(self, v: "DeviceVector"):
+        """In-place sum over ranks (NCCL all-reduce on the context stream); identity without a communicator."""
+        if self.nranks > 1:
+            check(lib().lso_comm_allreduce_sum(self._h, v.ptr, v.n), self._h)
+        return v
 
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -39,20 +39,18 @@ class _DenseWorkspace:
 class DenseQRAllocatedSolver(_DenseWorkspace):
     """dense_qr.jl: Dogleg{QR} workspace (m x n, :25-28) or LevenbergMarquardt{QR} workspace ((m+n) x n, :50-54)."""
 
-    def __init__(self, ctx: Context, m: int, n: int, damped: bool):
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool, sharded: bool = False):
         super().__init__(ctx, m, n, LSO_SOLVER_QR, damped)
         self.last_rank = n
+        self.sharded = sharded      # J, y are this rank's row shard: TSQR over the context's communicator
 
     def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None):
         rank = C.c_int()
-        fn = lib().lso_qr_solve_sharded if self.ctx_nranks() > 1 else lib().lso_qr_solve
+        fn = lib().lso_qr_solve_sharded if self.sharded else lib().lso_qr_solve
         check(fn(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr, C.byref(rank)),
               self.ctx.handle)
         self.last_rank = rank.value
         return x, 1
-
-    def ctx_nranks(self) -> int:
-        return getattr(self.ctx, "nranks", 1)
 
 
 class DenseCholeskyAllocatedSolver(_DenseWorkspace):
