@@ -35,76 +35,92 @@ __device__ __forceinline__ bool tm_row(const TileMap& tm, long long blk, int p, 
 }
 
 // =================================================================================================
-// leaf kernel: Householder QR of one QH x QB block.  256 threads: lane = column, warp = 32-row group; each
-// thread keeps its 32 column entries in registers (its rows are one contiguous 256-byte run in memory at
-// every level, so loads / stores go straight between global memory and registers, 16 bytes at a time).
-// Per Householder step: the owner lane publishes the pivot column, every thread forms its partial
-// v'a_k (or v_k'v_j for the columns already factorised) in ONE pass, a block-wide reduction over the 8 row
-// groups follows, and the rank-1 update is applied from the published column.  The T factor of the compact
-// WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V) (no work on the critical path).
+// leaf kernel: Householder QR of one QH x QB block.  256 threads: lane = column, warp g = row group.
+// Each thread keeps 32 entries of its column in registers:
+//     x[0..3]   head rows  g, g+8, g+16, g+24   (the 32 head rows end up holding R; spreading them over the 8
+//               warps makes every warp do the same work and leaves only 4 entries per thread that need a
+//               "row > j" predicate or a runtime-indexed pivot-row read)
+//     x[4..31]  body rows  32 + 28 g ... 32 + 28 g + 27  (one contiguous run; always below the diagonal)
+// Per Householder step: the owner lane publishes the pivot column (zeros above the diagonal), every thread
+// forms its partial v'a_k (or v_k'v_j for already factorised columns) in ONE pass, the 8 row groups are
+// reduced through shared memory, and the rank-1 update is applied from the published column.  The T factor of
+// the compact WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V).
 // =================================================================================================
+__device__ __forceinline__ double* leaf_row_ptr(double* __restrict__ colbase, const TileMap& tm, long long blk, int p,
+                                                bool& ok) {
+    long long mrow;
+    ok = tm_row(tm, blk, p, mrow);
+    return colbase + mrow;
+}
+
 __global__ void __launch_bounds__(256, 2)
 qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
                double* __restrict__ Tout) {
-    __shared__ __align__(16) double colbuf[2][QH];
-    __shared__ double rowbuf[2][QB];
+    __shared__ __align__(16) double colbuf[2][QH];    // published pivot column, thread-major: [grp*32 + i]
+    __shared__ double rowbuf[2][QB];                  // pivot-row entry of every column
     __shared__ double red[8][QB];
-    __shared__ double Zs[QB][QB + 1];      // Zs[j][k] = v_k' v_j  (k < j)
+    __shared__ double Zs[QB][QB + 1];                 // Zs[j][k] = v_k' v_j  (k < j)
     __shared__ double taus[QB];
 
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const long long blk = blockIdx.x;
-    long long mrow0;
-    const bool valid = tm_row(tm, blk, grp * 32, mrow0);
-    double* __restrict__ gcol = A + (c0 + lane) * ld + mrow0;
+    double* __restrict__ colbase = A + (c0 + lane) * ld;
+    const int body0 = 32 + 28 * grp;                  // first body row (tile coordinates)
 
     double x[32];
-    if (valid) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(gcol + i);
-            x[i] = v.x; x[i + 1] = v.y;
-        }
-    } else {
+    for (int i = 0; i < 4; ++i) {
+        bool ok;
+        const double* p = leaf_row_ptr(colbase, tm, blk, grp + 8 * i, ok);
+        x[i] = ok ? *p : 0.0;
+    }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = 0.0;
+    for (int i = 0; i < 28; i += 2) {
+        bool ok;
+        const double* p = leaf_row_ptr(colbase, tm, blk, body0 + i, ok);
+        double2 v = make_double2(0.0, 0.0);
+        if (ok) v = *reinterpret_cast<const double2*>(p);
+        x[4 + i] = v.x; x[5 + i] = v.y;
     }
 
     for (int j = 0; j < QB; ++j) {
         double* cb = colbuf[j & 1];
         double* rb = rowbuf[j & 1];
+        const int jg = j & 7, ji = j >> 3;            // pivot row j lives in warp jg at head index ji
+        // head index i holds row grp + 8 i: below the diagonal  <=>  i > ji  or  (i == ji and grp > jg)
+        const int ilow = (grp > jg) ? ji : ji + 1;    // first head index strictly below the diagonal
         if (lane == j) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                double2 v;
-                // rows above the diagonal (group 0 only) do not take part in the reflector
-                v.x = (grp == 0 && i <= j) ? 0.0 : x[i];
-                v.y = (grp == 0 && i + 1 <= j) ? 0.0 : x[i + 1];
-                *reinterpret_cast<double2*>(cb + grp * 32 + i) = v;
-            }
-        }
-        if (grp == 0) {
-            double xj = 0.0;
+            for (int i = 0; i < 4; i += 2)
+                *reinterpret_cast<double2*>(cb + grp * 32 + i) =
+                    make_double2(i >= ilow ? x[i] : 0.0, i + 1 >= ilow ? x[i + 1] : 0.0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xj = (i == j) ? x[i] : xj;
-            rb[lane] = xj;                   // pivot-row entry of column `lane`
+            for (int i = 4; i < 32; i += 2)
+                *reinterpret_cast<double2*>(cb + grp * 32 + i) = make_double2(x[i], x[i + 1]);
+        }
+        if (grp == jg) {
+            const double xj = (ji == 0) ? x[0] : (ji == 1) ? x[1] : (ji == 2) ? x[2] : x[3];
+            rb[lane] = xj;                            // pivot-row entry of column `lane`
         }
         __syncthreads();   // S1
-        double d = 0.0;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(cb + grp * 32 + i);
-            d = fma(v.x, x[i], d);
-            d = fma(v.y, x[i + 1], d);
+        for (int i = 0; i < 32; i += 8) {
+            const double2 v0 = *reinterpret_cast<const double2*>(cb + grp * 32 + i);
+            const double2 v1 = *reinterpret_cast<const double2*>(cb + grp * 32 + i + 2);
+            const double2 v2 = *reinterpret_cast<const double2*>(cb + grp * 32 + i + 4);
+            const double2 v3 = *reinterpret_cast<const double2*>(cb + grp * 32 + i + 6);
+            d0 = fma(v0.x, x[i], d0);     d0 = fma(v0.y, x[i + 1], d0);
+            d1 = fma(v1.x, x[i + 2], d1); d1 = fma(v1.y, x[i + 3], d1);
+            d2 = fma(v2.x, x[i + 4], d2); d2 = fma(v2.y, x[i + 5], d2);
+            d3 = fma(v3.x, x[i + 6], d3); d3 = fma(v3.y, x[i + 7], d3);
         }
-        red[grp][lane] = d;
+        red[grp][lane] = (d0 + d1) + (d2 + d3);
         __syncthreads();   // S2
-        double s_k = 0.0, s_j = 0.0;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            s_k += red[g][lane];
-            s_j += red[g][j];
-        }
+        const double s_k = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
+                           ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+        const double s_j = ((red[0][j] + red[1][j]) + (red[2][j] + red[3][j])) +
+                           ((red[4][j] + red[5][j]) + (red[6][j] + red[7][j]));
         const double alpha = rb[j];
         const double rowk = rb[lane];
         double beta, tau, scale;
@@ -112,8 +128,10 @@ qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, d
             beta = alpha; tau = 0.0; scale = 0.0;
         } else {
             beta = -copysign(sqrt(fma(alpha, alpha, s_j)), alpha);
-            tau = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
+            const double amb = alpha - beta;
+            const double r = 1.0 / (beta * amb);      // one division: scale = 1/(alpha-beta), tau = (beta-alpha)/beta
+            scale = beta * r;
+            tau = -(amb * amb) * r;
         }
         const double wz = fma(scale, s_k, rowk);    // v_j' a_k  (k > j)   or   v_k' v_j  (k < j)
         if (lane > j) {
@@ -125,48 +143,43 @@ qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, d
                 x[i] = fma(cs, v.x, x[i]);
                 x[i + 1] = fma(cs, v.y, x[i + 1]);
             }
-            if (grp == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = (i == j) ? x[i] - coef : x[i];   // pivot row: v_j = 1
+            if (grp == jg) {       // pivot row: v_j = 1
+                x[0] = (ji == 0) ? x[0] - coef : x[0];
+                x[1] = (ji == 1) ? x[1] - coef : x[1];
+                x[2] = (ji == 2) ? x[2] - coef : x[2];
+                x[3] = (ji == 3) ? x[3] - coef : x[3];
             }
         } else if (lane == j) {
-            if (grp == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = (i > j) ? x[i] * scale : ((i == j) ? beta : x[i]);
+            for (int i = 0; i < 4; ++i) x[i] = (i >= ilow) ? x[i] * scale : x[i];
+#pragma unroll
+            for (int i = 4; i < 32; ++i) x[i] *= scale;
+            if (grp == jg) {
+                x[0] = (ji == 0) ? beta : x[0];
+                x[1] = (ji == 1) ? beta : x[1];
+                x[2] = (ji == 2) ? beta : x[2];
+                x[3] = (ji == 3) ? beta : x[3];
                 taus[j] = tau;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] *= scale;
             }
-        } else if (grp == 0) {
+        } else if (grp == jg) {
             Zs[j][lane] = wz;
         }
     }
-    __syncthreads();
 
     // ---- V (explicit unit diagonal, zeros above) to the workspace; R head back into the matrix ----
-    double* __restrict__ Vb = Vout + blk * (long long)(QB * QS) + lane * QS + grp * 32;
-    if (grp == 0) {
+    double* __restrict__ Vb = Vout + blk * (long long)(QB * QS) + lane * QS;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            double2 v;
-            v.x = (i > lane) ? x[i] : ((i == lane) ? 1.0 : 0.0);
-            v.y = (i + 1 > lane) ? x[i + 1] : ((i + 1 == lane) ? 1.0 : 0.0);
-            *reinterpret_cast<double2*>(Vb + i) = v;
-        }
-        if (valid) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                double2 v;
-                v.x = (i <= lane) ? x[i] : 0.0;
-                v.y = (i + 1 <= lane) ? x[i + 1] : 0.0;
-                *reinterpret_cast<double2*>(gcol + i) = v;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) *reinterpret_cast<double2*>(Vb + i) = make_double2(x[i], x[i + 1]);
+    for (int i = 0; i < 4; ++i) {
+        const int r = grp + 8 * i;                                // head row
+        Vb[r] = (r > lane) ? x[i] : ((r == lane) ? 1.0 : 0.0);
+        bool ok;
+        double* p = leaf_row_ptr(colbase, tm, blk, r, ok);
+        if (ok) *p = (r <= lane) ? x[i] : 0.0;
     }
+#pragma unroll
+    for (int i = 0; i < 28; i += 2)
+        *reinterpret_cast<double2*>(Vb + body0 + i) = make_double2(x[4 + i], x[5 + i]);
+    __syncthreads();
 
     // ---- T = (diag(1/tau) + striu(V'V))^{-1}, one column per lane of warp 0 (division-free back substitution) ----
     if (grp == 0) {
