@@ -268,7 +268,7 @@ qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
 // =================================================================================================
 // trailing update, tensor-pipe version: persistent CTAs, producer warp + 8 consumer warps.
 // =================================================================================================
-#define AM_NST 3
+#define AM_NST 2
 #define AM_VS_BYTES (QB * QS * 8)
 #define AM_XS_BYTES (QCT * QS * 8)
 #define QWP (QB + 8)    /* stride of the per-warp partial buffers: 16-byte stores of 8 lanes hit 32 distinct banks */
@@ -620,20 +620,31 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         lv.nblocks = nb;
         lv.seg_stride = (L == 0) ? QH : stride;
         size_t vb = (size_t)nb * QB * QS * sizeof(double), tb = (size_t)nb * QB * QB * sizeof(double);
-        e = cudaMalloc(&lv.V, vb);
-        if (e == cudaSuccess) e = cudaMalloc(&lv.T, tb);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return lso_set_error(ctx, LSO_ERR_ALLOC, "QR reflector workspace: %s", cudaGetErrorString(e));
+        for (int b = 0; b < 2; ++b) {
+            e = cudaMalloc(&lv.V[b], vb);
+            if (e == cudaSuccess) e = cudaMalloc(&lv.T[b], tb);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return lso_set_error(ctx, LSO_ERR_ALLOC, "QR reflector workspace: %s", cudaGetErrorString(e));
+            }
+            LSO_CHECK_CUDA(ctx, cudaMemsetAsync(lv.V[b], 0, vb, ctx->stream));
+            LSO_CHECK_CUDA(ctx, cudaMemsetAsync(lv.T[b], 0, tb, ctx->stream));
         }
-        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(lv.V, 0, vb, ctx->stream));
-        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(lv.T, 0, tb, ctx->stream));
         ++L;
         if (nb <= 1) break;
         if (L > 1) stride *= QG;   // heads of level L-1 blocks are QH*QG^(L-1) rows apart
         nb = cdiv64(nb, QG);
     }
     plan->nlevels = L;
+    LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&plan->panel_stream, cudaStreamNonBlocking));
+    LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_start, cudaEventDisableTiming));
+    const int64_t npanels = plan->Npad / QB;
+    plan->ev_leaf.resize(npanels);
+    plan->ev_rest.resize(npanels);
+    for (int64_t k = 0; k < npanels; ++k) {
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_leaf[k], cudaEventDisableTiming));
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_rest[k], cudaEventDisableTiming));
+    }
     static bool attr_done = false;
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES));
@@ -645,66 +656,115 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
 
 void qr_plan_destroy(QRPlan* plan) {
     if (!plan) return;
+    if (plan->panel_stream) { cudaStreamSynchronize(plan->panel_stream); cudaStreamDestroy(plan->panel_stream); }
+    if (plan->ev_start) cudaEventDestroy(plan->ev_start);
+    for (cudaEvent_t ev : plan->ev_leaf) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : plan->ev_rest) cudaEventDestroy(ev);
     cudaFree(plan->A);
-    for (int l = 0; l < plan->nlevels; ++l) {
-        cudaFree(plan->lev[l].V);
-        cudaFree(plan->lev[l].T);
-    }
+    for (int l = 0; l < plan->nlevels; ++l)
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(plan->lev[l].V[b]);
+            cudaFree(plan->lev[l].T[b]);
+        }
     *plan = QRPlan();
 }
 
+struct PanelLevels {
+    int L = 0;
+    int64_t nblk[QR_MAX_LEVELS];
+    TileMap tm[QR_MAX_LEVELS];
+};
+
+static void panel_levels(const QRPlan* plan, int64_t c0, PanelLevels& pl) {
+    const int64_t r0 = c0;
+    int L = 0;
+    int64_t nb = cdiv64(plan->M - r0, QH);
+    int64_t stride = QH;
+    for (;;) {
+        pl.nblk[L] = nb;
+        TileMap& tm = pl.tm[L];
+        tm.r0 = r0;
+        if (L == 0) {
+            tm.seg_stride = QH; tm.n_items = nb; tm.seg_shift = 8; tm.nseg = 1;
+        } else {
+            tm.seg_stride = stride; tm.n_items = pl.nblk[L - 1]; tm.seg_shift = 5; tm.nseg = QG;
+        }
+        ++L;
+        if (nb <= 1) break;
+        if (L > 1) stride *= QG;
+        nb = cdiv64(nb, QG);
+    }
+    pl.L = L;
+}
+
+static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st) {
+    for (int l = 0; l < pl.L; ++l) {
+        qr_leaf_kernel<<<(unsigned)pl.nblk[l], 256, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf],
+                                                             plan->lev[l].T[buf]);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    return LSO_OK;
+}
+
+// apply the panel's block reflectors (all tree levels) to columns [cfirst, cfirst + ntiles*QCT)
+static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int buf, int64_t cfirst, int ntiles,
+                        cudaStream_t st, bool mark) {
+    if (ntiles <= 0) return LSO_OK;
+    for (int l = 0; l < pl.L; ++l) {
+        if (ctx->opt_qr_apply == 0) {
+            int64_t chunks = cdiv64((int64_t)ctx->num_sms * 2, pl.nblk[l]);
+            if (chunks > ntiles) chunks = ntiles;
+            if (chunks < 1) chunks = 1;
+            int tiles_per = (int)cdiv64(ntiles, chunks);
+            dim3 grid((unsigned)pl.nblk[l], (unsigned)cdiv64(ntiles, tiles_per));
+            qr_apply_fma_kernel<<<grid, 256, AF_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, tiles_per, pl.tm[l],
+                                                                 plan->lev[l].V[buf], plan->lev[l].T[buf]);
+        } else {
+            int64_t jtot = pl.nblk[l] * ntiles;
+            int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
+            if (mark) lso_prof_mark(ctx);
+            qr_apply_mma_kernel<<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
+                                                                 plan->lev[l].V[buf], plan->lev[l].T[buf]);
+            if (mark) lso_prof_mark(ctx);
+        }
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    return LSO_OK;
+}
+
+// Look-ahead schedule.  Main stream U carries the bulk trailing updates; the panel stream P carries, for each
+// panel k, the update of just the next panel's columns followed by that panel's factorisation tree, so the
+// latency-bound leaf kernels of panel k+1 run underneath the tensor-pipe-bound update of panel k (they fit on the
+// same SMs: 188 KB + 15 KB of shared memory).  V/T workspaces alternate between two buffers.
 int qr_factor(lso_ctx* ctx, QRPlan* plan) {
     const int64_t M = plan->M;
-    for (int64_t c0 = 0; c0 < plan->Npad; c0 += QB) {
-        const int64_t r0 = c0;
-        if (r0 >= M) break;    // no rows left: remaining columns have no R rows
-        // level sizes for this panel
-        int64_t nblk[QR_MAX_LEVELS];
-        TileMap tms[QR_MAX_LEVELS];
-        int L = 0;
-        int64_t nb = cdiv64(M - r0, QH);
-        int64_t stride = QH;
-        for (;;) {
-            nblk[L] = nb;
-            TileMap& tm = tms[L];
-            tm.r0 = r0;
-            if (L == 0) {
-                tm.seg_stride = QH; tm.n_items = nb; tm.seg_shift = 8; tm.nseg = 1;
-            } else {
-                tm.seg_stride = stride; tm.n_items = nblk[L - 1]; tm.seg_shift = 5; tm.nseg = QG;
-            }
-            ++L;
-            if (nb <= 1) break;
-            if (L > 1) stride *= QG;
-            nb = cdiv64(nb, QG);
-        }
-        for (int l = 0; l < L; ++l) {
-            qr_leaf_kernel<<<(unsigned)nblk[l], 256, 0, ctx->stream>>>(plan->A, plan->ld, c0, tms[l],
-                                                                                    plan->lev[l].V, plan->lev[l].T);
-            LSO_CHECK_LAUNCH(ctx);
-        }
-        const int64_t ctrail = c0 + QB;
+    const int64_t npanels = std::min<int64_t>(plan->Npad / QB, cdiv64(M, QB));   // no rows left beyond that
+    if (npanels <= 0) return LSO_OK;
+    cudaStream_t U = ctx->stream, P = plan->panel_stream;
+    const int LA = 2 * (QB / QCT) / 2;      // tiles that make up the next panel's columns (QB / QCT)
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_start, U));
+    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(P, plan->ev_start, 0));
+    PanelLevels cur, nxt;
+    panel_levels(plan, 0, cur);
+    LSO_TRY(launch_leaf_chain(ctx, plan, 0, cur, 0, P));
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_leaf[0], P));
+    for (int64_t k = 0; k < npanels; ++k) {
+        const int64_t c0 = k * QB, ctrail = c0 + QB;
+        const int buf = (int)(k & 1);
         const int ntiles = (int)((plan->Nc - ctrail) / QCT);
-        if (ntiles <= 0) continue;
-        for (int l = 0; l < L; ++l) {
-            if (ctx->opt_qr_apply == 0) {
-                int64_t chunks = cdiv64((int64_t)ctx->num_sms * 2, nblk[l]);
-                if (chunks > ntiles) chunks = ntiles;
-                if (chunks < 1) chunks = 1;
-                int tiles_per = (int)cdiv64(ntiles, chunks);
-                dim3 grid((unsigned)nblk[l], (unsigned)cdiv64(ntiles, tiles_per));
-                qr_apply_fma_kernel<<<grid, 256, AF_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, ctrail, ntiles, tiles_per,
-                                                                              tms[l], plan->lev[l].V, plan->lev[l].T);
-            } else {
-                int64_t jtot = nblk[l] * ntiles;
-                int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
-                lso_prof_mark(ctx);
-                qr_apply_mma_kernel<<<grid, 288, AM_SMEM_BYTES, ctx->stream>>>(plan->A, plan->ld, ctrail, ntiles, nblk[l],
-                                                                              tms[l], plan->lev[l].V, plan->lev[l].T);
-                lso_prof_mark(ctx);
-            }
-            LSO_CHECK_LAUNCH(ctx);
+        const bool has_next = (k + 1 < npanels);
+        if (has_next) {
+            if (k > 0) LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(P, plan->ev_rest[k - 1], 0));
+            LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail, LA, P, false));
+            panel_levels(plan, ctrail, nxt);
+            LSO_TRY(launch_leaf_chain(ctx, plan, ctrail, nxt, buf ^ 1, P));
+            LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_leaf[k + 1], P));
         }
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, plan->ev_leaf[k], 0));
+        if (has_next) LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail + LA * QCT, ntiles - LA, U, true));
+        else LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail, ntiles, U, true));
+        LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_rest[k], U));
+        if (has_next) cur = nxt;
     }
     return LSO_OK;
 }

@@ -22,8 +22,8 @@
 struct QRLevel {
     int64_t nblocks;     // blocks at this level (for the widest panel, r0 = 0)
     int64_t seg_stride;  // matrix rows between consecutive items (heads) gathered by this level
-    double* V;           // nblocks * QB*QS doubles
-    double* T;           // nblocks * QB*QB doubles
+    double* V[2];        // nblocks * QB*QS doubles, double-buffered over panels (look-ahead)
+    double* T[2];        // nblocks * QB*QB doubles
 };
 
 struct QRPlan {
@@ -35,6 +35,10 @@ struct QRPlan {
     double* A = nullptr; // ld x Nc, column-major
     int nlevels = 0;
     QRLevel lev[QR_MAX_LEVELS];
+    // look-ahead: panel factorisations run on a second stream, overlapped with the previous trailing update
+    cudaStream_t panel_stream = nullptr;
+    cudaEvent_t ev_start = nullptr;
+    std::vector<cudaEvent_t> ev_leaf, ev_rest;   // per panel
 };
 
 int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan);

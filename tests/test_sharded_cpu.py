@@ -1,0 +1,77 @@
+"""N > 1 host logic on CPU: world_size-2 gloo process group.  Checks the row partition, that the TSQR stack layout
+used by lso_qr_solve_sharded reproduces the single-process solve (R_k from each rank's rows, all-gathered, stacked with
+the sqrt(damp) rows), and that the packed [J'J | J'y] all-reduce reproduces the Cholesky solve."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import lsob200  # noqa: F401
+    from lsob200.sharding import row_partition, stack_layout
+    from oracle import reference_port as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(42)          # same data on every rank, each takes its rows
+    m, n = 1003, 17
+    J = rng.standard_normal((m, n)) * np.exp2(rng.integers(-4, 5, n))
+    y = rng.standard_normal(m)
+    damp = np.einsum("ij,ij->j", J, J) / 10
+    row0, rows = row_partition(m, world)[rank]
+    Jk, yk = J[row0:row0 + rows], y[row0:row0 + rows]
+    # ---- TSQR: local [R_k | c_k], all-gather, stack, QR ----
+    Q, R = np.linalg.qr(np.hstack([Jk, yk[:, None]]), mode="reduced")
+    Rk = np.triu(R[:n, :])                                   # n x (n+1): [R_k | Q_k' y_k]
+    gathered = [torch.zeros(n, n + 1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(Rk.copy()))
+    lay = stack_layout(n, world)
+    S = np.zeros((lay["rows"], lay["cols"]))
+    for k, (a, b) in enumerate(lay["R_rows"]):
+        S[a:b] = gathered[k].numpy()
+    a, b = lay["damp_rows"]
+    S[a:b, :n] = np.diag(np.sqrt(damp))
+    x_tsqr = np.linalg.lstsq(S[:, :n], S[:, n], rcond=None)[0]
+    x_ref, _ = O.qr_ldiv(J, y, damp.copy())
+    # ---- Cholesky: one all-reduce of the packed [J'J | J'y] ----
+    packed = torch.from_numpy(np.concatenate([(Jk.T @ Jk).ravel(), Jk.T @ yk]))
+    dist.all_reduce(packed)
+    C = packed.numpy()[:n * n].reshape(n, n) + np.diag(damp)
+    x_chol = np.linalg.solve(C, packed.numpy()[n * n:])
+    out[rank] = (float(np.linalg.norm(x_tsqr - x_ref) / np.linalg.norm(x_ref)),
+                 float(np.linalg.norm(x_chol - x_ref) / np.linalg.norm(x_ref)), rows)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_partition():
+    sys.path.insert(0, ROOT)
+    from lsob200.sharding import row_partition
+    for m, w in [(100000, 8), (1003, 2), (7, 7), (2_000_000, 8)]:
+        parts = row_partition(m, w)
+        assert parts[0][0] == 0 and sum(r for _, r in parts) == m
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        assert max(r for _, r in parts) - min(r for _, r in parts) <= 1
+    with pytest.raises(ValueError):
+        row_partition(3, 4)
+
+
+def test_world2_gloo_tsqr_and_allreduce():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        e_tsqr, e_chol, rows = out[rank]
+        assert e_tsqr <= 1e-12 and e_chol <= 1e-11
+    assert sum(out[r][2] for r in range(world)) == 1003
