@@ -201,6 +201,8 @@ int lso_synth_csc_jacobian(lso_csc* A, const double* d_Aval, const double* d_t, 
 /* ---- micro-benchmarks that give the roofline denominators this library reports against ---- */
 int lso_bench_fp64_mma_peak(lso_ctx* ctx, int iters, double* tflops_out);   /* DMMA m8n8k4 issue-bound loop */
 int lso_bench_fp64_fma_peak(lso_ctx* ctx, int iters, double* tflops_out);   /* DFMA issue-bound loop */
+/* DMMA with the trailing-update kernel's register pattern (operands change every k-step) at 8/16/32 warps per SM */
+int lso_bench_fp64_mma_pattern(lso_ctx* ctx, int iters, int mode, double* tflops_out);
 int lso_bench_hbm_copy(lso_ctx* ctx, size_t nbytes, int iters, double* gbs_out);
 
 #ifdef __cplusplus

@@ -24,6 +24,7 @@ struct lso_ctx {
     // options
     int64_t opt_qr_apply = 1;          // 0 = plain-FMA apply kernel, 1 = DMMA apply kernel
     int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
+    int64_t opt_qr_lookahead = 1;      // 0 = in-order QR schedule on one stream
     int64_t opt_profile = 0;           // 1 = bracket every launch of the dominant kernel with CUDA events
     std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
     size_t prof_used = 0;

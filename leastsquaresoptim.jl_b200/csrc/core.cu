@@ -91,6 +91,7 @@ int lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value) {
     LSO_REQUIRE(ctx, ctx && key, "ctx/key is NULL");
     if (!strcmp(key, "qr_apply")) ctx->opt_qr_apply = value;
     else if (!strcmp(key, "syrk")) ctx->opt_syrk = value;
+    else if (!strcmp(key, "qr_lookahead")) ctx->opt_qr_lookahead = value;
     else if (!strcmp(key, "profile")) { ctx->opt_profile = value; ctx->prof_used = 0; }
     else return lso_set_error(ctx, LSO_ERR_ARG, "unknown option '%s'", key);
     return LSO_OK;

@@ -17,6 +17,7 @@
 // ring with a dedicated producer warp.  tcgen05.mma has no f64 kind, see DESIGN.md.
 #include "qr.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 struct TileMap {
     long long r0;          // first active matrix row of this panel
@@ -636,19 +637,29 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         nb = cdiv64(nb, QG);
     }
     plan->nlevels = L;
-    LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&plan->panel_stream, cudaStreamNonBlocking));
+    {   // the panel stream gets the highest priority: its (small, latency-bound) kernels must be placed as soon as
+        // they are ready, underneath / ahead of the bulk trailing update
+        int prio_lo = 0, prio_hi = 0;
+        LSO_CHECK_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        LSO_CHECK_CUDA(ctx, cudaStreamCreateWithPriority(&plan->panel_stream, cudaStreamNonBlocking, prio_hi));
+    }
     LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_start, cudaEventDisableTiming));
     const int64_t npanels = plan->Npad / QB;
     plan->ev_leaf.resize(npanels);
     plan->ev_rest.resize(npanels);
+    plan->ev_next.resize(npanels);
     for (int64_t k = 0; k < npanels; ++k) {
         LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_leaf[k], cudaEventDisableTiming));
         LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_rest[k], cudaEventDisableTiming));
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_next[k], cudaEventDisableTiming));
     }
     static bool attr_done = false;
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
+        // same (maximum) shared-memory carveout for both kernels so a leaf CTA can join an SM that runs an update CTA
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     return LSO_OK;
@@ -660,6 +671,7 @@ void qr_plan_destroy(QRPlan* plan) {
     if (plan->ev_start) cudaEventDestroy(plan->ev_start);
     for (cudaEvent_t ev : plan->ev_leaf) cudaEventDestroy(ev);
     for (cudaEvent_t ev : plan->ev_rest) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : plan->ev_next) cudaEventDestroy(ev);
     cudaFree(plan->A);
     for (int l = 0; l < plan->nlevels; ++l)
         for (int b = 0; b < 2; ++b) {
@@ -735,16 +747,53 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
 // Look-ahead schedule.  Main stream U carries the bulk trailing updates; the panel stream P carries, for each
 // panel k, the update of just the next panel's columns followed by that panel's factorisation tree, so the
 // latency-bound leaf kernels of panel k+1 run underneath the tensor-pipe-bound update of panel k (they fit on the
-// same SMs: 188 KB + 15 KB of shared memory).  V/T workspaces alternate between two buffers.
+// same SMs: 188 KB + 15 KB of shared memory).  The bulk update of panel k is held back until the narrow update of
+// the next panel's columns has been placed (two update kernels cannot share an SM).  V/T workspaces alternate
+// between two buffers.  ctx option "qr_lookahead" = 0 runs everything in order on the main stream.
+struct TLMark { cudaEvent_t ev; const char* what; int64_t k; int stream; };
+static std::vector<TLMark> g_tl;
+static bool g_tl_on = false;
+static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id) {
+    if (!g_tl_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_tl.push_back({e, what, k, stream_id});
+}
+static void tl_dump(cudaStream_t U, cudaStream_t P) {
+    if (!g_tl_on || g_tl.empty()) return;
+    cudaStreamSynchronize(U);
+    cudaStreamSynchronize(P);
+    for (size_t i = 1; i < g_tl.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_tl[0].ev, g_tl[i].ev);
+        fprintf(stderr, "TL %8.3f ms  %c  panel %3lld  %s\n", ms, g_tl[i].stream ? 'P' : 'U', (long long)g_tl[i].k, g_tl[i].what);
+    }
+    for (auto& m : g_tl) cudaEventDestroy(m.ev);
+    g_tl.clear();
+    g_tl_on = false;
+}
+
 int qr_factor(lso_ctx* ctx, QRPlan* plan) {
     const int64_t M = plan->M;
+    g_tl_on = (getenv("LSO_QR_TIMELINE") != nullptr) && plan->M > 50000;
     const int64_t npanels = std::min<int64_t>(plan->Npad / QB, cdiv64(M, QB));   // no rows left beyond that
     if (npanels <= 0) return LSO_OK;
     cudaStream_t U = ctx->stream, P = plan->panel_stream;
-    const int LA = 2 * (QB / QCT) / 2;      // tiles that make up the next panel's columns (QB / QCT)
+    const int LA = QB / QCT;      // tiles that make up the next panel's columns
+    PanelLevels cur, nxt;
+    if (!ctx->opt_qr_lookahead) {
+        for (int64_t k = 0; k < npanels; ++k) {
+            const int64_t c0 = k * QB, ctrail = c0 + QB;
+            panel_levels(plan, c0, cur);
+            LSO_TRY(launch_leaf_chain(ctx, plan, c0, cur, 0, U));
+            LSO_TRY(launch_apply(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U, true));
+        }
+        return LSO_OK;
+    }
     LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_start, U));
     LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(P, plan->ev_start, 0));
-    PanelLevels cur, nxt;
+    tl_mark(U, "start", 0, 0);
     panel_levels(plan, 0, cur);
     LSO_TRY(launch_leaf_chain(ctx, plan, 0, cur, 0, P));
     LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_leaf[0], P));
@@ -755,16 +804,25 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
         const bool has_next = (k + 1 < npanels);
         if (has_next) {
             if (k > 0) LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(P, plan->ev_rest[k - 1], 0));
+            tl_mark(P, "applyNext begin", k, 1);
             LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail, LA, P, false));
+            LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_next[k], P));
+            tl_mark(P, "applyNext end / leaf(k+1) begin", k, 1);
             panel_levels(plan, ctrail, nxt);
             LSO_TRY(launch_leaf_chain(ctx, plan, ctrail, nxt, buf ^ 1, P));
             LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_leaf[k + 1], P));
+            tl_mark(P, "leaf(k+1) end", k, 1);
+            LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, plan->ev_next[k], 0));
+            tl_mark(U, "applyRest begin", k, 0);
+            LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail + LA * QCT, ntiles - LA, U, true));
+            tl_mark(U, "applyRest end", k, 0);
+        } else {
+            LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, plan->ev_leaf[k], 0));
+            LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail, ntiles, U, true));
         }
-        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, plan->ev_leaf[k], 0));
-        if (has_next) LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail + LA * QCT, ntiles - LA, U, true));
-        else LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail, ntiles, U, true));
         LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_rest[k], U));
         if (has_next) cur = nxt;
     }
+    tl_dump(U, P);
     return LSO_OK;
 }

@@ -38,7 +38,7 @@ struct QRPlan {
     // look-ahead: panel factorisations run on a second stream, overlapped with the previous trailing update
     cudaStream_t panel_stream = nullptr;
     cudaEvent_t ev_start = nullptr;
-    std::vector<cudaEvent_t> ev_leaf, ev_rest;   // per panel
+    std::vector<cudaEvent_t> ev_leaf, ev_rest, ev_next;   // per panel
 };
 
 int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan);

@@ -78,6 +78,36 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* __res
     for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
     if (s == 12345.678) out[0] = s;
 }
+// same accumulator pattern as the QR trailing update (2 x 4 accumulators, 2 + 4 distinct operand registers per k-step)
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) dmma_pattern_kernel(int iters, double* __restrict__ out) {
+    double c[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[i][j][0] = threadIdx.x * 1e-9; c[i][j][1] = i + j; }
+    double a[2], b[4];
+    a[0] = 1.0 + threadIdx.x * 1e-12; a[1] = 1.0 - threadIdx.x * 2e-12;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = 1.0 + (threadIdx.x + j) * 3e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+        a[0] += 1e-13; a[1] -= 1e-13;          // operands change every k-step, as when they come from shared memory
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] += 1e-13;
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += c[i][j][0] + c[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* __restrict__ out) {
     double c[16];
 #pragma unroll
@@ -171,6 +201,26 @@ int lso_bench_fp64_mma_peak(lso_ctx* ctx, int iters, double* tflops_out) {
     float ms = 0;
     LSO_TRY(time_ms(ctx, e0, e1, &ms));
     const double flops = (double)grid * 8.0 /*warps*/ * (double)iters * 8.0 * 512.0;
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return LSO_OK;
+}
+// mode 1: 8 warps / SM (the trailing-update kernel's occupancy), mode 2: 16 warps / SM, mode 3: 32 warps / SM
+int lso_bench_fp64_mma_pattern(lso_ctx* ctx, int iters, int mode, double* tflops_out) {
+    LSO_REQUIRE(ctx, ctx && tflops_out && iters > 0, "bad arguments");
+    cudaEvent_t e0, e1;
+    LSO_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+    LSO_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+    const int ctas_per_sm = (mode == 1) ? 1 : (mode == 2 ? 2 : 4);
+    const int grid = ctx->num_sms * ctas_per_sm;
+    dmma_pattern_kernel<8><<<grid, 256, 0, ctx->stream>>>(iters / 8 + 1, ctx->d_partials);
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    dmma_pattern_kernel<8><<<grid, 256, 0, ctx->stream>>>(iters, ctx->d_partials);
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    ctx->launches += 2;
+    float ms = 0;
+    LSO_TRY(time_ms(ctx, e0, e1, &ms));
+    const double flops = (double)grid * 8.0 * (double)iters * 8.0 * 512.0;
     *tflops_out = flops / (ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return LSO_OK;

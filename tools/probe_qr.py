@@ -15,7 +15,10 @@ out = C.c_double()
 check(lib().lso_bench_fp64_mma_peak(ctx.handle, 20000, C.byref(out)), ctx.handle); dmma = out.value
 check(lib().lso_bench_fp64_fma_peak(ctx.handle, 20000, C.byref(out)), ctx.handle); dfma = out.value
 check(lib().lso_bench_hbm_copy(ctx.handle, 2 << 30, 5, C.byref(out)), ctx.handle); hbm = out.value
-print(json.dumps({"dmma_tflops": dmma, "dfma_tflops": dfma, "hbm_copy_gbs": hbm}), flush=True)
+pat = {}
+for mode in (1, 2, 3):
+    check(lib().lso_bench_fp64_mma_pattern(ctx.handle, 20000, mode, C.byref(out)), ctx.handle); pat[f"dmma_pattern_{8 * 2 ** (mode - 1)}warps"] = out.value
+print(json.dumps({"dmma_tflops": dmma, "dfma_tflops": dfma, "hbm_copy_gbs": hbm, **pat}), flush=True)
 
 import torch
 def timeit(fn, reps=5):
@@ -41,6 +44,11 @@ for (m, n) in shapes:
         res[kind + "_ms"] = [1e3 * t for t in timeit(lambda: ws.ldiv(x, A, y, dtd))]
         res[kind + "_x_norm"] = float(np.linalg.norm(x.download()))
         del ws
+    ws = L.DenseQRAllocatedSolver(ctx, m, n, True)
+    for la in (0, 1):
+        ctx.set_option("qr_lookahead", la)
+        res[f"qr_lookahead{la}_ms"] = [1e3 * t for t in timeit(lambda: ws.ldiv(x, A, y, dtd))]
+    del ws
     flops_qr = 2 * (m + n) * n * n - 2 * n ** 3 / 3
     res["qr_tflops"] = flops_qr / (res["qr_ms"][0] * 1e-3) / 1e12
     res["syrk_tflops_equiv"] = m * n * (n + 1) / (res["chol_ms"][0] * 1e-3) / 1e12
