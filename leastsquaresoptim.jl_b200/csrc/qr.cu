@@ -54,14 +54,16 @@ __device__ __forceinline__ double* leaf_row_ptr(double* __restrict__ colbase, co
     return colbase + mrow;
 }
 
+template <bool TIMING>
 __global__ void __launch_bounds__(256, 2)
-qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
-               double* __restrict__ Tout) {
-    __shared__ __align__(16) double colbuf[2][QH];    // published pivot column, thread-major: [grp*32 + i]
-    __shared__ double rowbuf[2][QB];                  // pivot-row entry of every column
-    __shared__ double red[8][QB];
+qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
+               double* __restrict__ Tout, long long* __restrict__ tbuf) {
+#define LEAF_T(slot) do { if (TIMING && tid == 32) tbuf[(slot)] = clock64(); } while (0)
+    __shared__ __align__(16) double colbuf[8][32];    // pivot column, exchanged WITHIN each warp (same row group)
+    __shared__ double rowbuf[2][QB];                  // pivot-row entry of every column (parity double buffer)
+    __shared__ double red[2][8][QB];                  // per-row-group partial dot products
     __shared__ double Zs[QB][QB + 1];                 // Zs[j][k] = v_k' v_j  (k < j)
-    __shared__ double taus[QB];
+    __shared__ double taus[QB], rdiag[QB];
 
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const long long blk = blockIdx.x;
@@ -83,106 +85,108 @@ qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, d
         if (ok) v = *reinterpret_cast<const double2*>(p);
         x[4 + i] = v.x; x[5 + i] = v.y;
     }
+    double* cb = colbuf[grp];
+    LEAF_T(0);
 
+    // Reflectors are kept UNNORMALISED: v = a_j + sign(alpha) ||a_j|| e_j, H = I - t v v', t = -1 / (beta v_j).
+    // No column is rescaled and the only long-latency scalar work per step is one rsqrt and one reciprocal.
     for (int j = 0; j < QB; ++j) {
-        double* cb = colbuf[j & 1];
-        double* rb = rowbuf[j & 1];
+        const int par = j & 1;
         const int jg = j & 7, ji = j >> 3;            // pivot row j lives in warp jg at head index ji
         // head index i holds row grp + 8 i: below the diagonal  <=>  i > ji  or  (i == ji and grp > jg)
-        const int ilow = (grp > jg) ? ji : ji + 1;    // first head index strictly below the diagonal
+        const int ilow = (grp > jg) ? ji : ji + 1;
+        __syncwarp();
+        LEAF_T(1 + 6 * j);
         if (lane == j) {
 #pragma unroll
             for (int i = 0; i < 4; i += 2)
-                *reinterpret_cast<double2*>(cb + grp * 32 + i) =
-                    make_double2(i >= ilow ? x[i] : 0.0, i + 1 >= ilow ? x[i + 1] : 0.0);
+                *reinterpret_cast<double2*>(cb + i) = make_double2(i >= ilow ? x[i] : 0.0, i + 1 >= ilow ? x[i + 1] : 0.0);
 #pragma unroll
-            for (int i = 4; i < 32; i += 2)
-                *reinterpret_cast<double2*>(cb + grp * 32 + i) = make_double2(x[i], x[i + 1]);
+            for (int i = 4; i < 32; i += 2) *reinterpret_cast<double2*>(cb + i) = make_double2(x[i], x[i + 1]);
         }
-        if (grp == jg) {
-            const double xj = (ji == 0) ? x[0] : (ji == 1) ? x[1] : (ji == 2) ? x[2] : x[3];
-            rb[lane] = xj;                            // pivot-row entry of column `lane`
-        }
-        __syncthreads();   // S1
+        if (grp == jg) rowbuf[par][lane] = (ji == 0) ? x[0] : (ji == 1) ? x[1] : (ji == 2) ? x[2] : x[3];
+        __syncwarp();
+        LEAF_T(2 + 6 * j);
         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-            const double2 v0 = *reinterpret_cast<const double2*>(cb + grp * 32 + i);
-            const double2 v1 = *reinterpret_cast<const double2*>(cb + grp * 32 + i + 2);
-            const double2 v2 = *reinterpret_cast<const double2*>(cb + grp * 32 + i + 4);
-            const double2 v3 = *reinterpret_cast<const double2*>(cb + grp * 32 + i + 6);
+            const double2 v0 = *reinterpret_cast<const double2*>(cb + i);
+            const double2 v1 = *reinterpret_cast<const double2*>(cb + i + 2);
+            const double2 v2 = *reinterpret_cast<const double2*>(cb + i + 4);
+            const double2 v3 = *reinterpret_cast<const double2*>(cb + i + 6);
             d0 = fma(v0.x, x[i], d0);     d0 = fma(v0.y, x[i + 1], d0);
             d1 = fma(v1.x, x[i + 2], d1); d1 = fma(v1.y, x[i + 3], d1);
             d2 = fma(v2.x, x[i + 4], d2); d2 = fma(v2.y, x[i + 5], d2);
             d3 = fma(v3.x, x[i + 6], d3); d3 = fma(v3.y, x[i + 7], d3);
         }
-        red[grp][lane] = (d0 + d1) + (d2 + d3);
-        __syncthreads();   // S2
-        const double s_k = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
-                           ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
-        const double s_j = ((red[0][j] + red[1][j]) + (red[2][j] + red[3][j])) +
-                           ((red[4][j] + red[5][j]) + (red[6][j] + red[7][j]));
-        const double alpha = rb[j];
-        const double rowk = rb[lane];
-        double beta, tau, scale;
+        red[par][grp][lane] = (d0 + d1) + (d2 + d3);
+        LEAF_T(3 + 6 * j);
+        __syncthreads();                               // the only block-wide barrier of the step
+        LEAF_T(4 + 6 * j);
+        const double s_k = ((red[par][0][lane] + red[par][1][lane]) + (red[par][2][lane] + red[par][3][lane])) +
+                           ((red[par][4][lane] + red[par][5][lane]) + (red[par][6][lane] + red[par][7][lane]));
+        const double s_j = __shfl_sync(0xffffffffu, s_k, j);          // sum over rows > j of a_j^2
+        const double alpha = rowbuf[par][j];
+        const double rowk = rowbuf[par][lane];
+        double beta, tj, vjj;
         if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
-            beta = alpha; tau = 0.0; scale = 0.0;
+            beta = alpha; tj = 0.0; vjj = 1.0;
         } else {
-            beta = -copysign(sqrt(fma(alpha, alpha, s_j)), alpha);
-            const double amb = alpha - beta;
-            const double r = 1.0 / (beta * amb);      // one division: scale = 1/(alpha-beta), tau = (beta-alpha)/beta
-            scale = beta * r;
-            tau = -(amb * amb) * r;
+            const double q = fma(alpha, alpha, s_j);
+            const double nrm = q * rsqrt(q);
+            beta = -copysign(nrm, alpha);
+            vjj = alpha - beta;
+            tj = -1.0 / (beta * vjj);
         }
-        const double wz = fma(scale, s_k, rowk);    // v_j' a_k  (k > j)   or   v_k' v_j  (k < j)
+        const double wz = fma(vjj, rowk, s_k);      // v_j' a_k  (k > j)   or   v_k' v_j  (k < j)
+        if (TIMING && tid == 32) { if (wz == 1.2345e-300) tbuf[0] = 0; tbuf[5 + 6 * j] = clock64(); }
         if (lane > j) {
-            const double coef = tau * wz;
-            const double cs = -coef * scale;
+            const double coef = tj * wz;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(cb + grp * 32 + i);
-                x[i] = fma(cs, v.x, x[i]);
-                x[i + 1] = fma(cs, v.y, x[i + 1]);
+                const double2 v = *reinterpret_cast<const double2*>(cb + i);
+                x[i] = fma(-coef, v.x, x[i]);
+                x[i + 1] = fma(-coef, v.y, x[i + 1]);
             }
-            if (grp == jg) {       // pivot row: v_j = 1
-                x[0] = (ji == 0) ? x[0] - coef : x[0];
-                x[1] = (ji == 1) ? x[1] - coef : x[1];
-                x[2] = (ji == 2) ? x[2] - coef : x[2];
-                x[3] = (ji == 3) ? x[3] - coef : x[3];
-            }
-        } else if (lane == j) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = (i >= ilow) ? x[i] * scale : x[i];
-#pragma unroll
-            for (int i = 4; i < 32; ++i) x[i] *= scale;
-            if (grp == jg) {
-                x[0] = (ji == 0) ? beta : x[0];
-                x[1] = (ji == 1) ? beta : x[1];
-                x[2] = (ji == 2) ? beta : x[2];
-                x[3] = (ji == 3) ? beta : x[3];
-                taus[j] = tau;
+            if (grp == jg) {       // pivot row
+                const double pv = coef * vjj;
+                x[0] = (ji == 0) ? x[0] - pv : x[0];
+                x[1] = (ji == 1) ? x[1] - pv : x[1];
+                x[2] = (ji == 2) ? x[2] - pv : x[2];
+                x[3] = (ji == 3) ? x[3] - pv : x[3];
             }
         } else if (grp == jg) {
-            Zs[j][lane] = wz;
+            if (lane == j) {
+                x[0] = (ji == 0) ? vjj : x[0];
+                x[1] = (ji == 1) ? vjj : x[1];
+                x[2] = (ji == 2) ? vjj : x[2];
+                x[3] = (ji == 3) ? vjj : x[3];
+                taus[j] = tj;
+                rdiag[j] = beta;
+            } else {
+                Zs[j][lane] = wz;
+            }
         }
+        if (TIMING && tid == 32) { if (x[5] == 1.2345e-300) tbuf[0] = 0; tbuf[6 + 6 * j] = clock64(); }
     }
+    __syncthreads();
+    LEAF_T(200);
 
-    // ---- V (explicit unit diagonal, zeros above) to the workspace; R head back into the matrix ----
+    // ---- V (explicit diagonal entry, zeros above) to the workspace; R head back into the matrix ----
     double* __restrict__ Vb = Vout + blk * (long long)(QB * QS) + lane * QS;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = grp + 8 * i;                                // head row
-        Vb[r] = (r > lane) ? x[i] : ((r == lane) ? 1.0 : 0.0);
+        Vb[r] = (r >= lane) ? x[i] : 0.0;
         bool ok;
         double* p = leaf_row_ptr(colbase, tm, blk, r, ok);
-        if (ok) *p = (r <= lane) ? x[i] : 0.0;
+        if (ok) *p = (r < lane) ? x[i] : ((r == lane) ? rdiag[lane] : 0.0);
     }
 #pragma unroll
     for (int i = 0; i < 28; i += 2)
         *reinterpret_cast<double2*>(Vb + body0 + i) = make_double2(x[4 + i], x[5 + i]);
-    __syncthreads();
 
-    // ---- T = (diag(1/tau) + striu(V'V))^{-1}, one column per lane of warp 0 (division-free back substitution) ----
+    // ---- T = (diag(1/t) + striu(V'V))^{-1}, one column per lane of warp 0 (division-free back substitution) ----
     if (grp == 0) {
         double t[32];
         const double tau_c = taus[lane];
@@ -198,6 +202,8 @@ qr_leaf_kernel(double* __restrict__ A, long long ld, long long c0, TileMap tm, d
 #pragma unroll
         for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(Tb + k) = make_double2(t[k], t[k + 1]);
     }
+    if (TIMING && tid == 0) tbuf[201] = clock64();
+#undef LEAF_T
 }
 
 // =================================================================================================
@@ -659,7 +665,7 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
         // same (maximum) shared-memory carveout for both kernels so a leaf CTA can join an SM that runs an update CTA
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     return LSO_OK;
@@ -679,6 +685,18 @@ void qr_plan_destroy(QRPlan* plan) {
             cudaFree(plan->lev[l].T[b]);
         }
     *plan = QRPlan();
+}
+
+static long long* g_leaf_tbuf = nullptr;     // debug: per-phase clock64 stamps of the single-block leaf (LSO_LEAF_TIMING)
+extern "C" int lso_debug_leaf_timing(lso_ctx* ctx, long long* h_out /* 256 */) {
+    if (!g_leaf_tbuf) {
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&g_leaf_tbuf, 256 * sizeof(long long)));
+        LSO_CHECK_CUDA(ctx, cudaMemset(g_leaf_tbuf, 0, 256 * sizeof(long long)));
+        return LSO_OK;
+    }
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaMemcpy(h_out, g_leaf_tbuf, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return LSO_OK;
 }
 
 struct PanelLevels {
@@ -711,8 +729,11 @@ static void panel_levels(const QRPlan* plan, int64_t c0, PanelLevels& pl) {
 
 static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st) {
     for (int l = 0; l < pl.L; ++l) {
-        qr_leaf_kernel<<<(unsigned)pl.nblk[l], 256, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf],
-                                                             plan->lev[l].T[buf]);
+        if (g_leaf_tbuf && pl.nblk[l] == 1)
+            qr_leaf_kernel_t<true><<<1, 256, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf], plan->lev[l].T[buf], g_leaf_tbuf);
+        else
+            qr_leaf_kernel_t<false><<<(unsigned)pl.nblk[l], 256, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf],
+                                                                          plan->lev[l].T[buf], nullptr);
         LSO_CHECK_LAUNCH(ctx);
     }
     return LSO_OK;
