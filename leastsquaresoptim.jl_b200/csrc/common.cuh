@@ -24,13 +24,15 @@ struct lso_ctx {
     // options
     int64_t opt_qr_apply = 1;          // 0 = plain-FMA apply kernel, 1 = DMMA apply kernel
     int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
-    int64_t opt_qr_lookahead = 1;      // 0 = in-order QR schedule on one stream
+    int64_t opt_qr_lookahead = 0;      // 1 = panel trees on a second stream under the previous update (+2% at C2)
     int64_t opt_profile = 0;           // 1 = bracket every launch of the dominant kernel with CUDA events
     std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
     size_t prof_used = 0;
     // scratch of the rank-revealing small-R finish (qr_finish.cu), grown on demand
     double* d_finish = nullptr;
     size_t finish_cap = 0;
+    double* d_gemv = nullptr;          // column-split gemv partial row sums
+    size_t gemv_cap = 0;
     // NCCL (lazily loaded)
     void* nccl_comm = nullptr;
     int nranks = 1;

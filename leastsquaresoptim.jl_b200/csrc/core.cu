@@ -70,6 +70,7 @@ int lso_ctx_destroy(lso_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_finish);
+    cudaFree(ctx->d_gemv);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     cudaFreeHost(ctx->h_scalars);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -15,15 +15,27 @@ csc_mul_t_kernel(long long n, const int* __restrict__ colptr, const int* __restr
     const long long j = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (j >= n) return;
     const int k0 = colptr[j], k1 = colptr[j + 1];
-    double a0 = 0.0, a1 = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int k = k0 + lane;
-    for (; k + 32 < k1; k += 64) {
-        const double v0 = val[k], v1 = val[k + 32];
-        const int r0 = rowidx[k], r1 = rowidx[k + 32];
+    // 4 independent (value, index, gather) chains in flight per lane
+    for (; k + 96 < k1; k += 128) {
+        const double v0 = val[k], v1 = val[k + 32], v2 = val[k + 64], v3 = val[k + 96];
+        const int r0 = rowidx[k], r1 = rowidx[k + 32], r2 = rowidx[k + 64], r3 = rowidx[k + 96];
         a0 = fma(v0, y[r0], a0);
         a1 = fma(v1, y[r1], a1);
+        a2 = fma(v2, y[r2], a2);
+        a3 = fma(v3, y[r3], a3);
     }
-    if (k < k1) a0 = fma(val[k], y[rowidx[k]], a0);
+    {   // tail: up to 3 more entries, still issued together
+        const bool p0 = k < k1, p1 = k + 32 < k1, p2 = k + 64 < k1;
+        const double v0 = p0 ? val[k] : 0.0, v1 = p1 ? val[k + 32] : 0.0, v2 = p2 ? val[k + 64] : 0.0;
+        const int r0 = p0 ? rowidx[k] : 0, r1 = p1 ? rowidx[k + 32] : 0, r2 = p2 ? rowidx[k + 64] : 0;
+        if (p0) a0 = fma(v0, y[r0], a0);
+        if (p1) a1 = fma(v1, y[r1], a1);
+        if (p2) a2 = fma(v2, y[r2], a2);
+    }
+    a0 = (a0 + a1) + (a2 + a3);
+    a1 = 0.0;
     double acc = warp_sum(a0 + a1);
     if (lane == 0) {
         acc *= alpha;
@@ -63,7 +75,18 @@ csr_mul_n_kernel(long long m, const int* __restrict__ rowptr, const int* __restr
     double acc = 0.0;
     if (i < m) {
         const int k0 = rowptr[i], k1 = rowptr[i + 1];
-        for (int k = k0 + sub; k < k1; k += G) acc = fma(val[k], x[colidx[k]], acc);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int k = k0 + sub; k < k1; k += 4 * G) {      // 4 predicated chains in flight per lane
+            const bool p1 = k + G < k1, p2 = k + 2 * G < k1, p3 = k + 3 * G < k1;
+            const double v0 = val[k], v1 = p1 ? val[k + G] : 0.0, v2 = p2 ? val[k + 2 * G] : 0.0, v3 = p3 ? val[k + 3 * G] : 0.0;
+            const int c0 = colidx[k], c1 = p1 ? colidx[k + G] : 0, c2 = p2 ? colidx[k + 2 * G] : 0, c3 = p3 ? colidx[k + 3 * G] : 0;
+            const double x0 = x[c0], x1 = p1 ? x[c1] : 0.0, x2 = p2 ? x[c2] : 0.0, x3 = p3 ? x[c3] : 0.0;
+            a0 = fma(v0, x0, a0);
+            a1 = fma(v1, x1, a1);
+            a2 = fma(v2, x2, a2);
+            a3 = fma(v3, x3, a3);
+        }
+        acc = (a0 + a1) + (a2 + a3);
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

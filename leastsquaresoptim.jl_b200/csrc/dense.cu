@@ -164,6 +164,93 @@ gemv_n_kernel(int64_t m, int64_t n, double alpha, const double* __restrict__ J, 
     }
 }
 
+// column-split variant for tall-but-not-huge J: grid.y chunks of columns give enough CTAs (bytes in flight) to
+// saturate HBM; partial row sums go to a small scratch and a combine kernel finishes (deterministic order).
+__global__ void __launch_bounds__(256)
+gemv_n_part_kernel(int64_t m, int64_t n, const double* __restrict__ J, int64_t ld, const double* __restrict__ x,
+                   int64_t cols_per_chunk, double* __restrict__ part) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t j0 = (int64_t)blockIdx.y * cols_per_chunk;
+    int64_t j1 = j0 + cols_per_chunk;
+    if (j1 > n) j1 = n;
+    const double* __restrict__ row = J + i;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int64_t j = j0;
+    for (; j + 7 < j1; j += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = row[(j + u) * ld];
+        a0 = fma(v[0], x[j + 0], a0); a1 = fma(v[1], x[j + 1], a1);
+        a2 = fma(v[2], x[j + 2], a2); a3 = fma(v[3], x[j + 3], a3);
+        a0 = fma(v[4], x[j + 4], a0); a1 = fma(v[5], x[j + 5], a1);
+        a2 = fma(v[6], x[j + 6], a2); a3 = fma(v[7], x[j + 7], a3);
+    }
+    for (; j < j1; ++j) a0 = fma(row[j * ld], x[j], a0);
+    part[(int64_t)blockIdx.y * m + i] = (a0 + a1) + (a2 + a3);
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(256)
+gemv_n_combine_kernel(int64_t m, int nchunk, const double* __restrict__ part, double alpha, double beta,
+                      double* __restrict__ y, const double* __restrict__ f, double* __restrict__ partials,
+                      unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double sm[32];
+    __shared__ bool is_last;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if (i < m)
+        for (int c = 0; c < nchunk; ++c) acc += part[(int64_t)c * m + i];
+    if (!FUSE) {
+        if (i < m) {
+            const double r = alpha * acc;
+            y[i] = (beta == 0.0) ? r : fma(beta, y[i], r);
+        }
+        return;
+    }
+    double r = 0.0;
+    if (i < m) {
+        r = acc - f[i];
+        if (y) y[i] = r;
+    }
+    double s = block_sum(r * r, sm);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double a = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) a += ((volatile double*)partials)[k];
+        a = block_sum(a, sm);
+        if (threadIdx.x == 0) { *out = a; *counter = 0; }
+    }
+}
+
+static int gemv_n_chunks(lso_ctx* ctx, int64_t m, int64_t n) {
+    const int64_t rows_ctas = cdiv64(m, 256);
+    int64_t cs = cdiv64((int64_t)ctx->num_sms * 8, rows_ctas);
+    if (cs > 16) cs = 16;
+    if (cs > n / 64) cs = n / 64;
+    return (int)(cs < 1 ? 1 : cs);
+}
+
+static int gemv_scratch(lso_ctx* ctx, size_t doubles, double** out) {
+    if (ctx->gemv_cap < doubles) {
+        LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_gemv);
+        ctx->d_gemv = nullptr;
+        ctx->gemv_cap = 0;
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_gemv, doubles * sizeof(double)));
+        ctx->gemv_cap = doubles;
+    }
+    *out = ctx->d_gemv;
+    return LSO_OK;
+}
+
 int lso_fetch_scalar(lso_ctx* ctx, int slot, double* out);
 
 extern "C" {
@@ -191,6 +278,19 @@ int lso_dense_gemv_n(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const dou
     LSO_REQUIRE(ctx, m >= 0 && n >= 0 && ld >= m, "bad dimensions");
     if (m == 0) return LSO_OK;
     LSO_REQUIRE(ctx, d_y && (n == 0 || (d_J && d_x)), "NULL pointer");
+    const int cs = gemv_n_chunks(ctx, m, n);
+    if (cs > 1) {
+        double* part = nullptr;
+        LSO_TRY(gemv_scratch(ctx, (size_t)cs * m, &part));
+        const int64_t cpc = roundup64(cdiv64(n, cs), 8);
+        dim3 grid((unsigned)cdiv64(m, 256), (unsigned)cdiv64(n, cpc));
+        gemv_n_part_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, d_J, ld, d_x, cpc, part);
+        LSO_CHECK_LAUNCH(ctx);
+        gemv_n_combine_kernel<false><<<(unsigned)cdiv64(m, 256), 256, 0, ctx->stream>>>(m, (int)grid.y, part, alpha, beta, d_y,
+                                                                                    nullptr, nullptr, nullptr, nullptr);
+        LSO_CHECK_LAUNCH(ctx);
+        return LSO_OK;
+    }
     gemv_n_kernel<false><<<(unsigned)cdiv64(m, 256), 256, 0, ctx->stream>>>(m, n, alpha, d_J, ld, d_x, beta, d_y, nullptr,
                                                                           nullptr, nullptr, nullptr);
     LSO_CHECK_LAUNCH(ctx);
@@ -205,6 +305,19 @@ int lso_dense_predicted_ssr(lso_ctx* ctx, int64_t m, int64_t n, const double* d_
     LSO_REQUIRE(ctx, d_f && (n == 0 || (d_J && d_delta)), "NULL pointer");
     int64_t g = cdiv64(m, 256);
     LSO_REQUIRE(ctx, g <= LSO_PARTIALS, "m too large");
+    const int cs = gemv_n_chunks(ctx, m, n);
+    if (cs > 1) {
+        double* part = nullptr;
+        LSO_TRY(gemv_scratch(ctx, (size_t)cs * m, &part));
+        const int64_t cpc = roundup64(cdiv64(n, cs), 8);
+        dim3 grid((unsigned)g, (unsigned)cdiv64(n, cpc));
+        gemv_n_part_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, d_J, ld, d_delta, cpc, part);
+        LSO_CHECK_LAUNCH(ctx);
+        gemv_n_combine_kernel<true><<<(unsigned)g, 256, 0, ctx->stream>>>(m, (int)grid.y, part, 1.0, 0.0, d_fpredict, d_f,
+                                                                         ctx->d_partials, ctx->d_counters + 1, ctx->d_scalars + 3);
+        LSO_CHECK_LAUNCH(ctx);
+        return lso_fetch_scalar(ctx, 3, ssr_out);
+    }
     gemv_n_kernel<true><<<(unsigned)g, 256, 0, ctx->stream>>>(m, n, 1.0, d_J, ld, d_delta, 0.0, d_fpredict, d_f,
                                                              ctx->d_partials, ctx->d_counters + 1, ctx->d_scalars + 3);
     LSO_CHECK_LAUNCH(ctx);

@@ -459,31 +459,32 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
                         make_double2(c1[mi][ni][0], c1[mi][ni][1]);
         }
         consumer_sync();
-        // ---- reduce the 8 partials: Wsum[c][k] = (V'X)[k][c] ----
+        // ---- reduce the 8 partials: Wsum[c][k] = (V'X)[k][c]  (tree order: fp64 adds have ~23-cycle latency) ----
         {
             const int c = tid >> 4, k = tid & 15;
-            double s0 = 0.0, s1 = 0.0;
+            const double* w0 = Wp + c * QWP + k;
+            double p[8], r[8];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                s0 += Wp[w * QCT * QWP + c * QWP + k];
-                s1 += Wp[w * QCT * QWP + c * QWP + k + 16];
-            }
-            Wsum[c * QWS + k] = s0;
-            Wsum[c * QWS + k + 16] = s1;
+            for (int w = 0; w < 8; ++w) { p[w] = w0[w * QCT * QWP]; r[w] = w0[w * QCT * QWP + 16]; }
+            Wsum[c * QWS + k] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            Wsum[c * QWS + k + 16] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
         }
         consumer_sync();
-        // ---- Wfin = -T' Wsum   (negated so GEMM2 is a plain accumulate) ----
+        // ---- Wfin = -T' Wsum   (negated so GEMM2 is a plain accumulate); 4 independent chains per output ----
         {
             const int c = tid >> 4, i0 = tid & 15;
-            double s0 = 0.0, s1 = 0.0;
+            double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int k = 0; k < QB; ++k) {
-                const double wv = Wsum[c * QWS + k];
-                s0 = fma(Ts[i0 * 33 + k], wv, s0);
-                s1 = fma(Ts[(i0 + 16) * 33 + k], wv, s1);
+            for (int k = 0; k < QB; k += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double wv = Wsum[c * QWS + k + u];
+                    s0[u] = fma(Ts[i0 * 33 + k + u], wv, s0[u]);
+                    s1[u] = fma(Ts[(i0 + 16) * 33 + k + u], wv, s1[u]);
+                }
             }
-            Wfin[c * QWS + i0] = -s0;
-            Wfin[c * QWS + i0 + 16] = -s1;
+            Wfin[c * QWS + i0] = -((s0[0] + s0[1]) + (s0[2] + s0[3]));
+            Wfin[c * QWS + i0 + 16] = -((s1[0] + s1[1]) + (s1[2] + s1[3]));
         }
         consumer_sync();
         // ---- GEMM2 (transposed): X[32w:32w+32, :]' += Wfin' V[32w:32w+32, :]' ; results go straight to HBM ----
