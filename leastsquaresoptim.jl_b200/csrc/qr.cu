@@ -279,7 +279,7 @@ qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
 #define AM_VS_BYTES (QB * QS * 8)
 #define AM_XS_BYTES (QCT * QS * 8)
 #define QWP (QB + 8)    /* stride of the per-warp partial buffers: 16-byte stores of 8 lanes hit 32 distinct banks */
-#define AM_SMEM_BYTES (AM_VS_BYTES + AM_NST * AM_XS_BYTES + 8 * QCT * QWP * 8 + 2 * QCT * QWS * 8 + QB * 33 * 8 + 64)
+#define AM_SMEM_BYTES (AM_VS_BYTES + AM_NST * AM_XS_BYTES + 8 * QCT * QWP * 8 + 2 * QCT * QWS * 8 + QB * QWS * 8 + 64)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -322,17 +322,21 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
+template <bool ATIMING>
 __global__ void __launch_bounds__(288, 1)
-qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int ntiles, long long nblocks,
-                    TileMap tm, const double* __restrict__ V, const double* __restrict__ T) {
+qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int ntiles, long long nblocks,
+                    TileMap tm, const double* __restrict__ V, const double* __restrict__ T, long long* __restrict__ tbuf) {
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0;
+#define AP_T(slot) do { if (ATIMING && blockIdx.x == 0 && tid == 0) { const long long now = clock64(); tacc[slot] += now - tprev; tprev = now; } } while (0)
     extern __shared__ __align__(128) unsigned char amsm[];
     double* Vs = (double*)amsm;                                           // [QB][QS]
     double* Xs = (double*)(amsm + AM_VS_BYTES);                           // [AM_NST][QCT][QS]
     double* Wp = (double*)(amsm + AM_VS_BYTES + AM_NST * AM_XS_BYTES);    // [8][QCT][QWP] partial (V'X)' per warp
     double* Wsum = Wp + 8 * QCT * QWP;                                    // [QCT][QWS]
     double* Wfin = Wsum + QCT * QWS;                                      // [QCT][QWS]   -(T' V'X)
-    double* Ts = Wfin + QCT * QWS;                                        // Ts[i*33 + k] = T[k][i]
-    uint64_t* bars = (uint64_t*)(Ts + QB * 33);                           // full[3], done[3], vfull, vfree
+    double* Ts = Wfin + QCT * QWS;                                        // Ts[i*QWS + k] = T[k][i]
+    uint64_t* bars = (uint64_t*)(Ts + QB * QWS);                          // full[], done[], vfull, vfree
     const uint32_t bar_full = smem_u32(bars), bar_done = smem_u32(bars + AM_NST), bar_v = smem_u32(bars + 2 * AM_NST),
                    bar_vfree = smem_u32(bars + 2 * AM_NST + 1);
 
@@ -422,12 +426,14 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
             cur_blk = blk;
             ++seg_i;
             const double* __restrict__ Tb = T + blk * (long long)(QB * QB);
-            for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * 33 + k] = Tb[e]; }
+            for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * QWS + k] = Tb[e]; }
             wvalid = tm_row(tm, blk, 32 * wrp, wrow0);
             mbar_wait(bar_v, (uint32_t)(seg_i & 1));
         }
         const bool last_of_seg = (u + 1 == njobs) || ((q + 1) / ntiles != blk);
+        if (ATIMING && blockIdx.x == 0 && tid == 0) tprev = clock64();
         mbar_wait(bar_full + 8 * s, (uint32_t)((u / AM_NST) & 1));
+        AP_T(0);
         const double* Xst = Xs + s * QCT * QS;
 
         // ---- GEMM1 (transposed): partial (V'X)'_w = X[32w:32w+32, :]' V[32w:32w+32, :]   (QCT x QB) ----
@@ -458,7 +464,23 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
                     *reinterpret_cast<double2*>(wp + (8 * mi + g) * QWP + 8 * ni + 2 * t) =
                         make_double2(c1[mi][ni][0], c1[mi][ni][1]);
         }
+        // accumulator init for GEMM2 (this warp's rows of the staged tile), issued now so the loads are in flight
+        // during the reduction phases; afterwards this thread no longer reads the staged tile
+        double c2[2][4][2];
+        {
+            const int rbase = 32 * wrp + 2 * t;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
+                    c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
+                }
+        }
+        AP_T(1);
         consumer_sync();
+        mbar_arrive(bar_done + 8 * s);          // every warp has finished GEMM1: the staged tile is free
+        AP_T(2);
         // ---- reduce the 8 partials: Wsum[c][k] = (V'X)[k][c]  (tree order: fp64 adds have ~23-cycle latency) ----
         {
             const int c = tid >> 4, k = tid & 15;
@@ -469,36 +491,28 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
             Wsum[c * QWS + k] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
             Wsum[c * QWS + k + 16] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
         }
+        AP_T(3);
         consumer_sync();
-        // ---- Wfin = -T' Wsum   (negated so GEMM2 is a plain accumulate); 4 independent chains per output ----
+        AP_T(4);
+        // ---- Wfin' = -Wsum' T  on the tensor pipe: 2 x 4 fragments of 8 x 8, one per warp, K = 32 ----
         {
-            const int c = tid >> 4, i0 = tid & 15;
-            double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+            const int mi = wrp & 1, ni = wrp >> 1;
+            double ct[2][2] = {{0.0, 0.0}, {0.0, 0.0}};      // two accumulators (even / odd k-steps) to shorten the chain
 #pragma unroll
-            for (int k = 0; k < QB; k += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double wv = Wsum[c * QWS + k + u];
-                    s0[u] = fma(Ts[i0 * 33 + k + u], wv, s0[u]);
-                    s1[u] = fma(Ts[(i0 + 16) * 33 + k + u], wv, s1[u]);
-                }
+            for (int ks = 0; ks < 8; ++ks) {
+                const double a = Wsum[(8 * mi + g) * QWS + 4 * ks + t];
+                const double b = Ts[(8 * ni + g) * QWS + 4 * ks + t];
+                dmma(ct[ks & 1], a, b);
             }
-            Wfin[c * QWS + i0] = -((s0[0] + s0[1]) + (s0[2] + s0[3]));
-            Wfin[c * QWS + i0 + 16] = -((s1[0] + s1[1]) + (s1[2] + s1[3]));
+            *reinterpret_cast<double2*>(Wfin + (8 * mi + g) * QWS + 8 * ni + 2 * t) =
+                make_double2(-(ct[0][0] + ct[1][0]), -(ct[0][1] + ct[1][1]));
         }
+        AP_T(5);
         consumer_sync();
+        AP_T(6);
+        AP_T(7);
         // ---- GEMM2 (transposed): X[32w:32w+32, :]' += Wfin' V[32w:32w+32, :]' ; results go straight to HBM ----
         {
-            double c2[2][4][2];
-            const int rbase = 32 * wrp + 2 * t;
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
-                    c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
-                }
-            mbar_arrive(bar_done + 8 * s);          // this thread no longer reads the staged tile
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int k0 = 4 * ks + t;
@@ -512,6 +526,8 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
             }
+            if (ATIMING && blockIdx.x == 0 && tid == 0) { if (c2[0][0][0] == 1.2345e-300) tacc[9] = 1; }
+            AP_T(8);
             if (last_of_seg) mbar_arrive(bar_vfree);     // V of this block is dead for this thread
             if (wvalid) {
                 double* __restrict__ dst = A + (ctrail + (long long)tile * QCT + g) * ld + wrow0 + 2 * t;
@@ -524,6 +540,8 @@ qr_apply_mma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
             }
         }
     }
+    if (ATIMING && blockIdx.x == 0 && tid == 0) { for (int i = 0; i < 10; ++i) tbuf[i] = tacc[i]; tbuf[10] = njobs; }
+#undef AP_T
 }
 
 // =================================================================================================
@@ -663,9 +681,10 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
     static bool attr_done = false;
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES));
-        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
         // same (maximum) shared-memory carveout for both kernels so a leaf CTA can join an SM that runs an update CTA
-        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
@@ -688,6 +707,17 @@ void qr_plan_destroy(QRPlan* plan) {
     *plan = QRPlan();
 }
 
+static long long* g_apply_tbuf = nullptr;    // debug: per-phase clock64 sums of CTA 0 / warp 0 of the first level-0 update
+extern "C" int lso_debug_apply_timing(lso_ctx* ctx, long long* h_out /* 16 */) {
+    if (!g_apply_tbuf) {
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&g_apply_tbuf, 16 * sizeof(long long)));
+        LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf, 0, 16 * sizeof(long long)));
+        return LSO_OK;
+    }
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaMemcpy(h_out, g_apply_tbuf, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return LSO_OK;
+}
 static long long* g_leaf_tbuf = nullptr;     // debug: per-phase clock64 stamps of the single-block leaf (LSO_LEAF_TIMING)
 extern "C" int lso_debug_leaf_timing(lso_ctx* ctx, long long* h_out /* 256 */) {
     if (!g_leaf_tbuf) {
@@ -757,8 +787,12 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
             int64_t jtot = pl.nblk[l] * ntiles;
             int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
             if (mark) lso_prof_mark(ctx);
-            qr_apply_mma_kernel<<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
-                                                                 plan->lev[l].V[buf], plan->lev[l].T[buf]);
+            if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
+                qr_apply_mma_kernel_t<true><<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
+                                                                           plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
+            else
+                qr_apply_mma_kernel_t<false><<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
+                                                                            plan->lev[l].V[buf], plan->lev[l].T[buf], nullptr);
             if (mark) lso_prof_mark(ctx);
         }
         LSO_CHECK_LAUNCH(ctx);

@@ -108,6 +108,27 @@ __global__ void __launch_bounds__(NWARPS * 32) dmma_pattern_kernel(int iters, do
         for (int j = 0; j < 4; ++j) s += c[i][j][0] + c[i][j][1];
     if (s == 12345.678) out[0] = s;
 }
+// dependency-distance probe: NACC independent accumulators per warp, 8 warps per SM (the update kernel's occupancy)
+template <int NACC>
+__global__ void __launch_bounds__(256) dmma_dist_kernel(int iters, double* __restrict__ out) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i; }
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8 / NACC; ++r)
+#pragma unroll
+            for (int i = 0; i < NACC; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        a += 1e-13; b -= 1e-13;
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* __restrict__ out) {
     double c[16];
 #pragma unroll
@@ -211,11 +232,17 @@ int lso_bench_fp64_mma_pattern(lso_ctx* ctx, int iters, int mode, double* tflops
     cudaEvent_t e0, e1;
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e0));
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e1));
-    const int ctas_per_sm = (mode == 1) ? 1 : (mode == 2 ? 2 : 4);
+    const int ctas_per_sm = (mode == 1) ? 1 : (mode == 2 ? 2 : (mode == 3 ? 4 : 1));
     const int grid = ctx->num_sms * ctas_per_sm;
-    dmma_pattern_kernel<8><<<grid, 256, 0, ctx->stream>>>(iters / 8 + 1, ctx->d_partials);
+    auto launch = [&](int it) {
+        if (mode <= 3) dmma_pattern_kernel<8><<<grid, 256, 0, ctx->stream>>>(it, ctx->d_partials);
+        else if (mode == 12) dmma_dist_kernel<2><<<grid, 256, 0, ctx->stream>>>(it, ctx->d_partials);   // 8 warps/SM, distance 2
+        else if (mode == 14) dmma_dist_kernel<4><<<grid, 256, 0, ctx->stream>>>(it, ctx->d_partials);
+        else dmma_dist_kernel<8><<<grid, 256, 0, ctx->stream>>>(it, ctx->d_partials);
+    };
+    launch(iters / 8 + 1);
     LSO_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    dmma_pattern_kernel<8><<<grid, 256, 0, ctx->stream>>>(iters, ctx->d_partials);
+    launch(iters);
     LSO_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     ctx->launches += 2;
     float ms = 0;

@@ -1,0 +1,26 @@
+import ctypes as C, sys
+import numpy as np
+sys.path.insert(0, ".")
+import lsob200 as L
+from lsob200._lib import check, lib
+ctx = L.Context.default(0)
+fn = lib().lso_debug_apply_timing
+fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_void_p]
+buf = np.zeros(16, dtype=np.int64)
+fn(ctx.handle, buf.ctypes.data)           # arm
+m, n = 100000, 1000
+A = L.DenseMatrix(ctx, m, n)
+check(lib().lso_synth_dense_matrix(ctx.handle, m, n, 0, 20240608, A.ptr, A.ld), ctx.handle)
+y = L.DeviceVector(ctx, m); check(lib().lso_synth_vector(ctx.handle, m, 0, 77, 1.0, y.ptr), ctx.handle)
+dtd, x = L.DeviceVector(ctx, n), L.DeviceVector(ctx, n)
+A.colsumabs2(dtd); L.api._lm_damping(ctx, dtd, 0.1)
+ws = L.DenseQRAllocatedSolver(ctx, m, n, True)
+for _ in range(2):
+    ws.ldiv(x, A, y, dtd)
+fn(ctx.handle, buf.ctypes.data)
+names = ["wait full", "GEMM1+store partial", "sync1", "reduce", "sync2", "T-mult", "sync3", "C-init loads", "GEMM2", "-"]
+nj = max(int(buf[10]), 1)
+tot = sum(buf[:9])
+print("tiles", nj, "cycles/tile", tot / nj)
+for i in range(9):
+    print(f"  {names[i]:22s} {buf[i] / nj:8.0f} cycles  {100 * buf[i] / tot:5.1f}%")

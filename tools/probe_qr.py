@@ -18,6 +18,8 @@ check(lib().lso_bench_hbm_copy(ctx.handle, 2 << 30, 5, C.byref(out)), ctx.handle
 pat = {}
 for mode in (1, 2, 3):
     check(lib().lso_bench_fp64_mma_pattern(ctx.handle, 20000, mode, C.byref(out)), ctx.handle); pat[f"dmma_pattern_{8 * 2 ** (mode - 1)}warps"] = out.value
+for mode in (12, 14, 18):
+    check(lib().lso_bench_fp64_mma_pattern(ctx.handle, 20000, mode, C.byref(out)), ctx.handle); pat[f"dmma_8warps_depdist{mode - 10}"] = out.value
 print(json.dumps({"dmma_tflops": dmma, "dfma_tflops": dfma, "hbm_copy_gbs": hbm, **pat}), flush=True)
 
 import torch
