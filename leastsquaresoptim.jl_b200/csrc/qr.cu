@@ -19,20 +19,30 @@
 #include <math.h>
 #include <stdlib.h>
 
+// Row layout of one tree level ("head first").  The level covers matrix rows [r0, r0 + rows), rows a multiple of
+// QB.  It is cut into nb = ceil(rows / QH) blocks; block b owns
+//     its HEAD : the QB rows  r0 + QB*b ...                       (receives the block's R factor)
+//     its BODY : the QH-QB rows  r0 + QB*nb + (QH-QB)*b ...       (clipped to the level's row range)
+// so the heads of all blocks form the contiguous range [r0, r0 + QB*nb), which is exactly the next level's row
+// range: every level reads and writes two contiguous runs per column, and the final R lands in rows r0..r0+QB.
 struct TileMap {
-    long long r0;          // first active matrix row of this panel
-    long long seg_stride;  // matrix rows between consecutive items
-    long long n_items;     // items available at this level
-    int seg_shift;         // log2(rows per segment): 8 (level 0: one 256-row segment) or 5 (heads)
-    int nseg;              // segments per block: 1 or QG
+    long long r0;     // first active matrix row of this panel
+    long long nb;     // blocks at this level
+    long long rows;   // rows covered by this level (multiple of QB)
 };
+#define QBODY (QH - QB)
 
+// matrix row of tile row p of block blk; false if the row lies beyond the level's range (reads as zero)
 __device__ __forceinline__ bool tm_row(const TileMap& tm, long long blk, int p, long long& mrow) {
-    const int q = p >> tm.seg_shift;
-    const int t = p - (q << tm.seg_shift);
-    const long long item = blk * tm.nseg + q;
-    mrow = tm.r0 + item * tm.seg_stride + t;
-    return item < tm.n_items;
+    if (p < QB) { mrow = tm.r0 + QB * blk + p; return true; }
+    const long long off = QB * tm.nb + QBODY * blk + (p - QB);
+    mrow = tm.r0 + off;
+    return off < tm.rows;
+}
+// number of valid body rows of block blk (0 .. QBODY, multiple of QB)
+__device__ __forceinline__ int tm_body_rows(const TileMap& tm, long long blk) {
+    long long nv = tm.rows - QB * tm.nb - QBODY * blk;
+    return (int)(nv < 0 ? 0 : (nv > QBODY ? QBODY : nv));
 }
 
 // =================================================================================================
@@ -198,7 +208,7 @@ qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm,
             const double tk = -acc * taus[k];
             t[k] = (k == lane) ? tau_c : ((k < lane) ? tk : 0.0);
         }
-        double* __restrict__ Tb = Tout + blk * (long long)(QB * QB) + lane * QB;   // column `lane`, column-major
+        double* __restrict__ Tb = Tout + blk * (long long)(QB * QWS) + lane * QWS;   // column `lane`, column stride QWS (smem image)
 #pragma unroll
         for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(Tb + k) = make_double2(t[k], t[k + 1]);
     }
@@ -222,9 +232,9 @@ qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const long long blk = blockIdx.x;
     const double* __restrict__ Vb = V + blk * (long long)(QB * QS);
-    const double* __restrict__ Tb = T + blk * (long long)(QB * QB);
+    const double* __restrict__ Tb = T + blk * (long long)(QB * QWS);
     for (int e = tid; e < QB * QS; e += 256) Vs[e] = Vb[e];
-    for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * 33 + k] = Tb[e]; }
+    for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * 33 + k] = Tb[i * QWS + k]; }
     const int t0 = blockIdx.y * tiles_per_cta;
     int t1 = t0 + tiles_per_cta;
     if (t1 > ntiles) t1 = ntiles;
@@ -316,6 +326,7 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ long long gtimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1])
@@ -326,8 +337,10 @@ template <bool ATIMING>
 __global__ void __launch_bounds__(288, 1)
 qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int ntiles, long long nblocks,
                     TileMap tm, const double* __restrict__ V, const double* __restrict__ T, long long* __restrict__ tbuf) {
-    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = 0;
+    const long long tstart = ATIMING ? clock64() : 0;
+    const long long tstart_ns = ATIMING ? gtimer_ns() : 0;
 #define AP_T(slot) do { if (ATIMING && blockIdx.x == 0 && tid == 0) { const long long now = clock64(); tacc[slot] += now - tprev; tprev = now; } } while (0)
     extern __shared__ __align__(128) unsigned char amsm[];
     double* Vs = (double*)amsm;                                           // [QB][QS]
@@ -359,9 +372,6 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
     __syncthreads();
     if (njobs <= 0) return;
 
-    const int seg_rows = 1 << tm.seg_shift;
-    const uint32_t seg_bytes = (uint32_t)seg_rows * 8u;
-
     if (wrp == 8) {
         // =========================== producer warp: TMA-unit bulk loads only ===========================
         long long cur_blk = -1;
@@ -382,27 +392,22 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
             }
             if (u >= AM_NST) mbar_wait(bar_done + 8 * s, (uint32_t)(((u / AM_NST) - 1) & 1));   // stage drained
             double* xst = Xs + s * QCT * QS;
-            long long nvalid = tm.n_items - blk * tm.nseg;
-            if (nvalid > tm.nseg) nvalid = tm.nseg;
-            if (nvalid < tm.nseg) {
-                for (int e = lane; e < QCT * tm.nseg; e += 32) {
-                    const int col = e / tm.nseg, qq = e - col * tm.nseg;
-                    if (qq >= nvalid)
-                        for (int r = 0; r < seg_rows; ++r) xst[col * QS + qq * seg_rows + r] = 0.0;
-                }
+            const int nv = tm_body_rows(tm, blk);
+            if (nv < QBODY) {
+                for (int e = lane; e < QCT; e += 32)
+                    for (int r = QB + nv; r < QH; ++r) xst[e * QS + r] = 0.0;
             }
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)(QCT * nvalid) * seg_bytes);
+            if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)(QCT * (QB + nv)) * 8u);
             __syncwarp();
             const long long cbase = ctrail + (long long)tile * QCT;
             const uint32_t xs = smem_u32(xst);
-            for (int e = lane; e < QCT * tm.nseg; e += 32) {
-                const int col = e / tm.nseg, qq = e - col * tm.nseg;
-                const long long item = blk * tm.nseg + qq;
-                if (item < tm.n_items) {
-                    const double* src = A + (cbase + col) * ld + tm.r0 + item * tm.seg_stride;
-                    bulk_g2s(xs + (uint32_t)(col * QS + qq * seg_rows) * 8u, src, seg_bytes, bar_full + 8 * s);
-                }
+            {
+                const int col = lane & (QCT - 1), seg = lane >> 4;      // 2 copies per column: head, body
+                const double* colp = A + (cbase + col) * ld + tm.r0;
+                if (seg == 0) bulk_g2s(xs + (uint32_t)(col * QS) * 8u, colp + QB * blk, QB * 8u, bar_full + 8 * s);
+                else if (nv > 0)
+                    bulk_g2s(xs + (uint32_t)(col * QS + QB) * 8u, colp + QB * tm.nb + QBODY * blk, (uint32_t)nv * 8u, bar_full + 8 * s);
             }
         }
         return;
@@ -425,13 +430,13 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
         if (blk != cur_blk) {
             cur_blk = blk;
             ++seg_i;
-            const double* __restrict__ Tb = T + blk * (long long)(QB * QB);
-            for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * QWS + k] = Tb[e]; }
+            const double* __restrict__ Tb = T + blk * (long long)(QB * QWS);
+            for (int e = tid; e < QB * QB; e += 256) { const int k = e & 31, i = e >> 5; Ts[i * QWS + k] = Tb[i * QWS + k]; }
             wvalid = tm_row(tm, blk, 32 * wrp, wrow0);
             mbar_wait(bar_v, (uint32_t)(seg_i & 1));
         }
         const bool last_of_seg = (u + 1 == njobs) || ((q + 1) / ntiles != blk);
-        if (ATIMING && blockIdx.x == 0 && tid == 0) tprev = clock64();
+        if (ATIMING && blockIdx.x == 0 && tid == 0) { if (u == 0) tprev = clock64(); else AP_T(9); }
         mbar_wait(bar_full + 8 * s, (uint32_t)((u / AM_NST) & 1));
         AP_T(0);
         const double* Xst = Xs + s * QCT * QS;
@@ -526,7 +531,7 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
             }
-            if (ATIMING && blockIdx.x == 0 && tid == 0) { if (c2[0][0][0] == 1.2345e-300) tacc[9] = 1; }
+            if (ATIMING && blockIdx.x == 0 && tid == 0) { if (c2[0][0][0] == 1.2345e-300) tacc[11] = 1; }
             AP_T(8);
             if (last_of_seg) mbar_arrive(bar_vfree);     // V of this block is dead for this thread
             if (wvalid) {
@@ -540,8 +545,273 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
             }
         }
     }
-    if (ATIMING && blockIdx.x == 0 && tid == 0) { for (int i = 0; i < 10; ++i) tbuf[i] = tacc[i]; tbuf[10] = njobs; }
+    if (ATIMING && blockIdx.x == 0 && tid == 0) { AP_T(9); for (int i = 0; i < 10; ++i) tbuf[i] = tacc[i]; tbuf[10] = njobs; tbuf[11] = clock64() - tstart; tbuf[12] = gtimer_ns() - tstart_ns; }
 #undef AP_T
+}
+
+// =================================================================================================
+// trailing update, ping-pong version (ctx option qr_apply = 2, the default).
+// Two independent consumer groups of 4 warps work on alternate tiles, so that one group's reduction / T-multiply /
+// barrier phases run underneath the other group's DMMA phases, and NO consumer thread touches global memory:
+//   producer warp : cp.async.bulk loads of V|T (per block) and of X tiles into a 3-stage ring, and cp.async.bulk
+//                   STORES of the finished tiles straight from the ring (results are written back in place)
+//   consumer warp w of a group owns tile rows [64w, 64w+64): its K-slice of W' = X'V (GEMM1) and its output rows of
+//                   X' += Wfin' V' (GEMM2).  A warp only ever touches its own row slice of the staged tile.
+// =================================================================================================
+#define PP_NST 3
+#define PP_GW 4                                     /* warps per consumer group */
+#define PP_T_BYTES (QB * QWS * 8)
+#define PP_WP_BYTES (PP_GW * QCT * QWP * 8)         /* per group; Wfin aliases its head */
+#define PP_WS_BYTES (QCT * QWS * 8)
+#define PP_SMEM_BYTES (AM_VS_BYTES + PP_T_BYTES + PP_NST * AM_XS_BYTES + 2 * PP_WP_BYTES + 2 * PP_WS_BYTES + 128)
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+template <bool ATIMING>
+__global__ void __launch_bounds__(288, 1)
+qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int ntiles, long long nblocks,
+                     TileMap tm, const double* __restrict__ V, const double* __restrict__ T, long long* __restrict__ tbuf) {
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0;
+    const long long tstart = ATIMING ? clock64() : 0;
+    const long long tstart_ns = ATIMING ? gtimer_ns() : 0;
+#define PP_TM(slot) do { if (ATIMING && blockIdx.x == 0 && tid == 0) { const long long now = clock64(); tacc[slot] += now - tprev; tprev = now; } } while (0)
+    extern __shared__ __align__(128) unsigned char ppsm[];
+    double* Vs = (double*)ppsm;                                            // [QB][QS]
+    double* Ts = (double*)(ppsm + AM_VS_BYTES);                            // Ts[i*QWS + k] = T[k][i]  (contiguous after Vs)
+    double* Xs = (double*)(ppsm + AM_VS_BYTES + PP_T_BYTES);               // [PP_NST][QCT][QS]
+    unsigned char* wbase = ppsm + AM_VS_BYTES + PP_T_BYTES + PP_NST * AM_XS_BYTES;
+    uint64_t* bars = (uint64_t*)(wbase + 2 * PP_WP_BYTES + 2 * PP_WS_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_out = smem_u32(bars + PP_NST), bar_v = smem_u32(bars + 2 * PP_NST),
+                   bar_vfree = smem_u32(bars + 2 * PP_NST + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const long long jtot = nblocks * ntiles;
+    const long long q_begin = (jtot * blockIdx.x) / gridDim.x;
+    const long long q_end = (jtot * (blockIdx.x + 1)) / gridDim.x;
+    const int njobs = (int)(q_end - q_begin);
+
+    if (tid == 0) {
+        for (int s = 0; s < PP_NST; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_out + 8 * s, 128);
+        }
+        mbar_init(bar_v, 1);
+        mbar_init(bar_vfree, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    __syncthreads();
+    if (njobs <= 0) return;
+
+    const long long blk0 = q_begin / ntiles;
+    const int tile0 = (int)(q_begin - blk0 * ntiles);
+
+    if (wrp == 8) {
+        // =========================== producer warp: all global traffic, via the TMA unit ===========================
+        long long blk = blk0;
+        int tile = tile0;
+        int seg_i = -1;
+        long long cur_blk = -1;
+        long long hist_blk[PP_NST];
+        int hist_tile[PP_NST];
+        const int pcol = lane & (QCT - 1), pseg = lane >> 4;      // 2 copies per column: head, body
+        for (int u = 0; u < njobs + PP_NST; ++u) {
+            const int s = u % PP_NST;
+            if (u >= PP_NST) {
+                // stage s holds the finished tile of job u - PP_NST: store it, and wait until the copy engine has read it
+                mbar_wait(bar_out + 8 * s, (uint32_t)(((u / PP_NST) - 1) & 1));
+                const long long sb = hist_blk[s];
+                const long long cbase = ctrail + (long long)hist_tile[s] * QCT;
+                const uint32_t xs = smem_u32(Xs + s * QCT * QS);
+                const int snv = tm_body_rows(tm, sb);
+                double* colp = A + (cbase + pcol) * ld + tm.r0;
+                if (pseg == 0) bulk_s2g(colp + QB * sb, xs + (uint32_t)(pcol * QS) * 8u, QB * 8u);
+                else if (snv > 0) bulk_s2g(colp + QB * tm.nb + QBODY * sb, xs + (uint32_t)(pcol * QS + QB) * 8u, (uint32_t)snv * 8u);
+                bulk_commit();
+                if (u < njobs) bulk_wait_read0();
+            }
+            if (u >= njobs) continue;
+            if (blk != cur_blk) {
+                if (seg_i >= 0) mbar_wait(bar_vfree, (uint32_t)(seg_i & 1));   // both groups are done with the old V
+                cur_blk = blk;
+                ++seg_i;
+                if (lane == 0) {
+                    mbar_expect_tx(bar_v, AM_VS_BYTES + PP_T_BYTES);
+                    bulk_g2s(smem_u32(Vs), V + blk * (long long)(QB * QS), AM_VS_BYTES, bar_v);
+                    bulk_g2s(smem_u32(Ts), T + blk * (long long)(QB * QWS), PP_T_BYTES, bar_v);
+                }
+            }
+            double* xst = Xs + s * QCT * QS;
+            const int nv = tm_body_rows(tm, blk);
+            if (nv < QBODY) {
+                for (int e = lane; e < QCT; e += 32)
+                    for (int r = QB + nv; r < QH; ++r) xst[e * QS + r] = 0.0;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)(QCT * (QB + nv)) * 8u);
+            __syncwarp();
+            {
+                const long long cbase = ctrail + (long long)tile * QCT;
+                const uint32_t xs = smem_u32(xst);
+                const double* colp = A + (cbase + pcol) * ld + tm.r0;
+                if (pseg == 0) bulk_g2s(xs + (uint32_t)(pcol * QS) * 8u, colp + QB * blk, QB * 8u, bar_full + 8 * s);
+                else if (nv > 0)
+                    bulk_g2s(xs + (uint32_t)(pcol * QS + QB) * 8u, colp + QB * tm.nb + QBODY * blk, (uint32_t)nv * 8u, bar_full + 8 * s);
+            }
+            hist_blk[s] = blk;
+            hist_tile[s] = tile;
+            if (++tile == ntiles) { tile = 0; ++blk; }
+        }
+        bulk_wait0();      // all stores have completed (not just been read) before the CTA retires
+        return;
+    }
+
+    // =============================== consumer groups ===============================
+    const int grp = wrp >> 2, w4 = wrp & 3;
+    const int gtid = tid & 127;
+    const int g = lane >> 2, t = lane & 3;
+    double* Wp = (double*)(wbase + grp * PP_WP_BYTES);          // [PP_GW][QCT][QWP] partial (V'X)' per warp
+    double* Wfin = Wp;                                          // [QCT][QWS]  -(T'V'X)', aliases the partials
+    double* Wsum = (double*)(wbase + 2 * PP_WP_BYTES + grp * PP_WS_BYTES);   // [QCT][QWS]
+    long long blk = blk0;
+    int tile = tile0;
+    long long cur_blk = -1;
+    int seg_i = -1;
+    bool need_v = false;
+    for (int u = 0; u < njobs; ++u) {
+        if (blk != cur_blk) { cur_blk = blk; ++seg_i; need_v = true; }
+        const bool last_of_seg = (u + 1 == njobs) || (tile + 1 == ntiles);
+        if (++tile == ntiles) { tile = 0; ++blk; }
+        if ((u & 1) != grp) {
+            if (last_of_seg) mbar_arrive(bar_vfree);     // this thread's jobs of the segment are all behind it
+            continue;
+        }
+        const int s = u % PP_NST;
+        if (ATIMING && blockIdx.x == 0 && tid == 0) { if (u == 0) tprev = clock64(); else PP_TM(9); }
+        if (need_v) { mbar_wait(bar_v, (uint32_t)(seg_i & 1)); need_v = false; }
+        mbar_wait(bar_full + 8 * s, (uint32_t)((u / PP_NST) & 1));
+        PP_TM(0);
+        double* Xst = Xs + s * QCT * QS;
+
+        // ---- GEMM1 (transposed): partial (V'X)'_w = X[64w:64w+64, :]' V[64w:64w+64, :]   (QCT x QB) ----
+        {
+            double c1[2][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) c1[mi][ni][0] = c1[mi][ni][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                const int k0 = 64 * w4 + 4 * ks + t;
+                double a[2], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) a[mi] = Xst[(8 * mi + g) * QS + k0];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = Vs[(8 * ni + g) * QS + k0];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma(c1[mi][ni], a[mi], b[ni]);
+            }
+            double* wp = Wp + w4 * QCT * QWP;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(wp + (8 * mi + g) * QWP + 8 * ni + 2 * t) =
+                        make_double2(c1[mi][ni][0], c1[mi][ni][1]);
+        }
+        PP_TM(1);
+        group_sync(grp);
+        PP_TM(2);
+        // ---- reduce the 4 partials: Wsum[c][k] = (V'X)[k][c] ----
+        {
+            const int c = gtid >> 3, k4 = (gtid & 7) * 4;
+            const double* w0 = Wp + c * QWP + k4;
+            double2 p[PP_GW][2];
+#pragma unroll
+            for (int w = 0; w < PP_GW; ++w) {
+                p[w][0] = *reinterpret_cast<const double2*>(w0 + w * QCT * QWP);
+                p[w][1] = *reinterpret_cast<const double2*>(w0 + w * QCT * QWP + 2);
+            }
+            double2 r0, r1;
+            r0.x = (p[0][0].x + p[1][0].x) + (p[2][0].x + p[3][0].x);
+            r0.y = (p[0][0].y + p[1][0].y) + (p[2][0].y + p[3][0].y);
+            r1.x = (p[0][1].x + p[1][1].x) + (p[2][1].x + p[3][1].x);
+            r1.y = (p[0][1].y + p[1][1].y) + (p[2][1].y + p[3][1].y);
+            *reinterpret_cast<double2*>(Wsum + c * QWS + k4) = r0;
+            *reinterpret_cast<double2*>(Wsum + c * QWS + k4 + 2) = r1;
+        }
+        PP_TM(3);
+        group_sync(grp);
+        PP_TM(4);
+        // ---- Wfin' = -Wsum' T  on the tensor pipe: warp w4 forms columns [8 w4, 8 w4 + 8) for both row fragments ----
+        {
+            double ct[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double b = Ts[(8 * w4 + g) * QWS + 4 * ks + t];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) {
+                    const double a = Wsum[(8 * mi + g) * QWS + 4 * ks + t];
+                    dmma(ct[mi][ks & 1], a, b);
+                }
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+                *reinterpret_cast<double2*>(Wfin + (8 * mi + g) * QWS + 8 * w4 + 2 * t) =
+                    make_double2(-(ct[mi][0][0] + ct[mi][1][0]), -(ct[mi][0][1] + ct[mi][1][1]));
+        }
+        PP_TM(5);
+        group_sync(grp);
+        PP_TM(6);
+        // ---- GEMM2 (transposed): X[64w:64w+64, :]' += Wfin' V[64w:64w+64, :]' ; written back into the stage ----
+        {
+            double c2[2][8][2];
+            const int rbase = 64 * w4 + 2 * t;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) {
+                    const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
+                    c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
+                }
+            PP_TM(7);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int k0 = 4 * ks + t;
+                double a[2], b[8];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) a[mi] = Wfin[(8 * mi + g) * QWS + k0];
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) b[ni] = Vs[k0 * QS + 64 * w4 + 8 * ni + g];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
+            }
+            if (ATIMING && blockIdx.x == 0 && tid == 0) { if (c2[0][0][0] == 1.2345e-300) tacc[11] = 1; }
+            PP_TM(8);
+            if (last_of_seg) mbar_arrive(bar_vfree);     // V of this block is dead for this thread
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+                    *reinterpret_cast<double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni) =
+                        make_double2(c2[mi][ni][0], c2[mi][ni][1]);
+        }
+        fence_async_smem();                  // generic-proxy writes -> visible to the bulk-copy engine
+        mbar_arrive(bar_out + 8 * s);
+    }
+    if (ATIMING && blockIdx.x == 0 && tid == 0) {
+        PP_TM(9);
+        for (int i = 0; i < 10; ++i) tbuf[i] = tacc[i];
+        tbuf[10] = (njobs + 1) / 2;
+        tbuf[11] = clock64() - tstart;
+        tbuf[12] = gtimer_ns() - tstart_ns;
+    }
+#undef PP_TM
 }
 
 // =================================================================================================
@@ -638,14 +908,12 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
     }
     LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->A, 0, bytes, ctx->stream));
     int64_t nb = cdiv64(M > 0 ? M : 1, QH);
-    int64_t stride = QH;
     int L = 0;
     for (;;) {
         LSO_REQUIRE(ctx, L < QR_MAX_LEVELS, "too many TSQR levels");
         QRLevel& lv = plan->lev[L];
         lv.nblocks = nb;
-        lv.seg_stride = (L == 0) ? QH : stride;
-        size_t vb = (size_t)nb * QB * QS * sizeof(double), tb = (size_t)nb * QB * QB * sizeof(double);
+        size_t vb = (size_t)nb * QB * QS * sizeof(double), tb = (size_t)nb * QB * QWS * sizeof(double);
         for (int b = 0; b < 2; ++b) {
             e = cudaMalloc(&lv.V[b], vb);
             if (e == cudaSuccess) e = cudaMalloc(&lv.T[b], tb);
@@ -658,8 +926,7 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         }
         ++L;
         if (nb <= 1) break;
-        if (L > 1) stride *= QG;   // heads of level L-1 blocks are QH*QG^(L-1) rows apart
-        nb = cdiv64(nb, QG);
+        nb = cdiv64(nb * QB, QH);
     }
     plan->nlevels = L;
     {   // the panel stream gets the highest priority: its (small, latency-bound) kernels must be placed as soon as
@@ -685,6 +952,8 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         // same (maximum) shared-memory carveout for both kernels so a leaf CTA can join an SM that runs an update CTA
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
@@ -737,27 +1006,31 @@ struct PanelLevels {
 };
 
 static void panel_levels(const QRPlan* plan, int64_t c0, PanelLevels& pl) {
-    const int64_t r0 = c0;
     int L = 0;
-    int64_t nb = cdiv64(plan->M - r0, QH);
-    int64_t stride = QH;
+    int64_t rows = roundup64(plan->M, QB) - c0;
     for (;;) {
+        const int64_t nb = cdiv64(rows, QH);
         pl.nblk[L] = nb;
-        TileMap& tm = pl.tm[L];
-        tm.r0 = r0;
-        if (L == 0) {
-            tm.seg_stride = QH; tm.n_items = nb; tm.seg_shift = 8; tm.nseg = 1;
-        } else {
-            tm.seg_stride = stride; tm.n_items = pl.nblk[L - 1]; tm.seg_shift = 5; tm.nseg = QG;
-        }
+        pl.tm[L].r0 = c0;
+        pl.tm[L].nb = nb;
+        pl.tm[L].rows = rows;
         ++L;
         if (nb <= 1) break;
-        if (L > 1) stride *= QG;
-        nb = cdiv64(nb, QG);
+        rows = nb * QB;
     }
     pl.L = L;
 }
 
+struct TLMark { cudaEvent_t ev; const char* what; int64_t k; int stream; };
+static std::vector<TLMark> g_tl;
+static bool g_tl_on = false;
+static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id) {
+    if (!g_tl_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_tl.push_back({e, what, k, stream_id});
+}
 static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st) {
     for (int l = 0; l < pl.L; ++l) {
         if (g_leaf_tbuf && pl.nblk[l] == 1)
@@ -787,7 +1060,16 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
             int64_t jtot = pl.nblk[l] * ntiles;
             int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
             if (mark) lso_prof_mark(ctx);
-            if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
+            if (ctx->opt_qr_apply == 2) {
+                // two jobs per CTA keep both consumer groups busy when there are fewer jobs than 2 x SMs
+                if (jtot < 2 * (int64_t)ctx->num_sms) grid = (int)((jtot + 1) / 2);
+                if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
+                    qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
+                                                                              plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
+                else
+                    qr_apply_pp_kernel_t<false><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
+                                                                               plan->lev[l].V[buf], plan->lev[l].T[buf], nullptr);
+            } else if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
                 qr_apply_mma_kernel_t<true><<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
                                                                            plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
             else
@@ -796,6 +1078,9 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
             if (mark) lso_prof_mark(ctx);
         }
         LSO_CHECK_LAUNCH(ctx);
+        static const char* lvl_names[QR_MAX_LEVELS] = {"apply L0 end", "apply L1 end", "apply L2 end", "apply L3 end", "apply L4 end",
+                                                       "apply L5 end", "apply L6 end", "apply L7 end", "apply L8 end", "apply L9 end"};
+        tl_mark(st, lvl_names[l], cfirst / QB - 1, st == ctx->stream ? 0 : 1);
     }
     return LSO_OK;
 }
@@ -806,16 +1091,6 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
 // same SMs: 188 KB + 15 KB of shared memory).  The bulk update of panel k is held back until the narrow update of
 // the next panel's columns has been placed (two update kernels cannot share an SM).  V/T workspaces alternate
 // between two buffers.  ctx option "qr_lookahead" = 0 runs everything in order on the main stream.
-struct TLMark { cudaEvent_t ev; const char* what; int64_t k; int stream; };
-static std::vector<TLMark> g_tl;
-static bool g_tl_on = false;
-static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id) {
-    if (!g_tl_on) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, st);
-    g_tl.push_back({e, what, k, stream_id});
-}
 static void tl_dump(cudaStream_t U, cudaStream_t P) {
     if (!g_tl_on || g_tl.empty()) return;
     cudaStreamSynchronize(U);
@@ -839,12 +1114,15 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
     const int LA = QB / QCT;      // tiles that make up the next panel's columns
     PanelLevels cur, nxt;
     if (!ctx->opt_qr_lookahead) {
+        tl_mark(U, "start", 0, 0);
         for (int64_t k = 0; k < npanels; ++k) {
             const int64_t c0 = k * QB, ctrail = c0 + QB;
             panel_levels(plan, c0, cur);
             LSO_TRY(launch_leaf_chain(ctx, plan, c0, cur, 0, U));
+            tl_mark(U, "leaf chain end", k, 0);
             LSO_TRY(launch_apply(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U, true));
         }
+        tl_dump(U, plan->panel_stream);
         return LSO_OK;
     }
     LSO_CHECK_CUDA(ctx, cudaEventRecord(plan->ev_start, U));

@@ -6,7 +6,8 @@
 // Tiling constants of the CAQR:
 //   QB  panel width (columns factorised together; reflectors per block reflector)
 //   QH  rows of one leaf block (one CTA factorises a QH x QB block out of shared memory/registers)
-//   QG  fan-in of the reduction tree (QH / QB heads are stacked into the next level's block)
+//   QG  fan-in of the reduction tree (QH / QB heads are stacked into the next level's block; the rows of a
+//       level are ordered "heads first", see TileMap in qr.cu)
 //   QS  padded column stride (doubles) of V blocks in the workspace and in shared memory:
 //       QS = QH + 4 makes every DMMA fragment load (4 rows x 8 cols, or 8 rows x 4 cols) hit 16
 //       distinct 8-byte banks per half-warp.
@@ -21,7 +22,6 @@
 
 struct QRLevel {
     int64_t nblocks;     // blocks at this level (for the widest panel, r0 = 0)
-    int64_t seg_stride;  // matrix rows between consecutive items (heads) gathered by this level
     double* V[2];        // nblocks * QB*QS doubles, double-buffered over panels (look-ahead)
     double* T[2];        // nblocks * QB*QB doubles
 };

@@ -4,6 +4,7 @@ sys.path.insert(0, ".")
 import lsob200 as L
 from lsob200._lib import check, lib
 ctx = L.Context.default(0)
+if len(sys.argv) > 1: ctx.set_option('qr_apply', int(sys.argv[1]))
 fn = lib().lso_debug_apply_timing
 fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_void_p]
 buf = np.zeros(16, dtype=np.int64)
@@ -18,9 +19,11 @@ ws = L.DenseQRAllocatedSolver(ctx, m, n, True)
 for _ in range(2):
     ws.ldiv(x, A, y, dtd)
 fn(ctx.handle, buf.ctypes.data)
-names = ["wait full", "GEMM1+store partial", "sync1", "reduce", "sync2", "T-mult", "sync3", "C-init loads", "GEMM2", "-"]
+names = ["wait full", "GEMM1+store partial", "sync1", "reduce", "sync2", "T-mult", "sync3", "C-init loads", "GEMM2", "stores + loop top (V switch)"]
 nj = max(int(buf[10]), 1)
-tot = sum(buf[:9])
+tot = sum(buf[:10])
 print("tiles", nj, "cycles/tile", tot / nj)
-for i in range(9):
+for i in range(10):
     print(f"  {names[i]:22s} {buf[i] / nj:8.0f} cycles  {100 * buf[i] / tot:5.1f}%")
+print("CTA 0 total cycles in kernel", int(buf[11]), "=> per tile", buf[11] / nj)
+print("CTA 0 wall ns", int(buf[12]), "=> effective SM clock %.0f MHz" % (buf[11] / max(buf[12], 1) * 1e3))
