@@ -57,160 +57,263 @@ __device__ __forceinline__ int tm_body_rows(const TileMap& tm, long long blk) {
 // reduced through shared memory, and the rank-1 update is applied from the published column.  The T factor of
 // the compact WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V).
 // =================================================================================================
-__device__ __forceinline__ double* leaf_row_ptr(double* __restrict__ colbase, const TileMap& tm, long long blk, int p,
-                                                bool& ok) {
-    long long mrow;
-    ok = tm_row(tm, blk, p, mrow);
-    return colbase + mrow;
+// sqrt(q) and 1/d for the reflector scalars.  Fast path: MUFU seed + two Goldschmidt / Newton steps (no IEEE
+// slow-path branches on the critical chain of every Householder step); operands outside a safe range take the
+// library routines.  Results are within a couple of ulp, which perturbs H = I - t v v' by O(eps) like dlarfg.
+__device__ __forceinline__ double leaf_sqrt(double q) {
+    if (!(q > 1e-280 && q < 1e280)) return sqrt(q);
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(q));
+    double g = q * y0, h = 0.5 * y0;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    return fma(h, fma(-g, g, q), g);         // one correction step: g + (q - g^2) / (2 g)
+}
+__device__ __forceinline__ double leaf_rcp(double d) {
+    if (!(d > 1e-280 && d < 1e280)) return 1.0 / d;
+    double z;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(d));
+    double e = fma(-d, z, 1.0);
+    z = fma(z, e, z);
+    e = fma(-d, z, 1.0);
+    z = fma(z, e, z);
+    e = fma(-d, z, 1.0);
+    return fma(z, e, z);
 }
 
-template <bool TIMING>
-__global__ void __launch_bounds__(256, 2)
+// 256 threads.  The step time of a Householder factorisation held in registers is set by the shared-memory pipe:
+// every value of the pivot column that a thread needs costs 8 bytes of LDS return bandwidth (128 B/clk per SM), so
+// the layout minimises "pivot-column values per thread" and reads them ONCE per step:
+//     lane = (column pair cp = lane & 15, half hh = lane >> 4); warp w, half hh  ->  row group rg = 2 w + hh (16 groups)
+//     a thread holds 16 rows of TWO adjacent columns (xa: column 2 cp, xb: column 2 cp + 1), rows
+//         i = 0, 1   head rows  rg, rg + 16            (the 32 head rows end up holding R)
+//         i = 2..15  body rows  32 + 14 rg ... + 13    (one contiguous run; always below the diagonal)
+//     and loads the 16 pivot-column values of its row group into registers once per step (dot product AND update).
+#define LEAF_THREADS 256
+#define LEAF_NG 16          /* row groups */
+#define LEAF_NX 16          /* rows per thread */
+#define LEAF_BR 14          /* body rows per thread */
+
+struct LeafSmem {
+    double colbuf[2][LEAF_NG][LEAF_NX];   // pivot column (parity double buffer), exchanged WITHIN each half-warp
+    double rowbuf[2][QB];                 // pivot-row entry of every column (parity double buffer)
+    double red[2][8][QB];                 // per-warp partial dot products
+    double Zs[QB][QB + 1];                // Zs[j][k] = v_k' v_j  (k < j)  =  U[k][j],  U = T^{-1}
+    double Tm[QB][QB + 1];                // T
+    double Wm[QB][QB + 1];                // scratch of the blocked inversion
+    double taus[QB], rdiag[QB];
+};
+
+// one Householder step; COMP = j & 1 selects which of the thread's two columns can be the pivot column
+template <int COMP, int VAR>
+__device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], double (&xb)[LEAF_NX], LeafSmem& sm,
+                                          const int lane, const int wrp, const int cp, const int hh, const int rg) {
+    const int par = j & 1;
+    const int rgj = j & (LEAF_NG - 1), ji = j >> 4;       // pivot row j: row group rgj, head index ji
+    double v[LEAF_NX];
+    {
+        const double* cb = sm.colbuf[par][rg];
+#pragma unroll
+        for (int i = 0; i < LEAF_NX; i += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(cb + i);
+            v[i] = t.x; v[i + 1] = t.y;
+        }
+    }
+    double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;
+    if (VAR & 8) { da0 = v[0] + v[15]; db0 = v[1] + v[14]; }
+    else
+#pragma unroll
+    for (int i = 0; i < LEAF_NX; i += 2) {
+        da0 = fma(v[i], xa[i], da0); da1 = fma(v[i + 1], xa[i + 1], da1);
+        db0 = fma(v[i], xb[i], db0); db1 = fma(v[i + 1], xb[i + 1], db1);
+    }
+    double da = da0 + da1, db = db0 + db1;
+    da += __shfl_xor_sync(0xffffffffu, da, 16);
+    db += __shfl_xor_sync(0xffffffffu, db, 16);
+    if (hh == 0) *reinterpret_cast<double2*>(&sm.red[par][wrp][2 * cp]) = make_double2(da, db);
+    if (!(VAR & 16)) __syncthreads();                  // the only block-wide barrier of the step
+    double sa, sb;
+    if (VAR & 32) { sa = da; sb = db; }
+    else {
+        const double* rp = &sm.red[par][4 * hh][2 * cp];
+        const double2 p0 = *reinterpret_cast<const double2*>(rp);
+        const double2 p1 = *reinterpret_cast<const double2*>(rp + QB);
+        const double2 p2 = *reinterpret_cast<const double2*>(rp + 2 * QB);
+        const double2 p3 = *reinterpret_cast<const double2*>(rp + 3 * QB);
+        sa = (p0.x + p1.x) + (p2.x + p3.x);
+        sb = (p0.y + p1.y) + (p2.y + p3.y);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+        sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+    }
+    const double s_j = __shfl_sync(0xffffffffu, COMP ? sb : sa, j >> 1);      // sum over rows > j of a_j^2
+    const double alpha = sm.rowbuf[par][j];
+    const double2 rk = *reinterpret_cast<const double2*>(&sm.rowbuf[par][2 * cp]);
+    double beta, tj, vjj;
+    if (VAR & 1) { beta = alpha; tj = 1e-3 * s_j; vjj = 1.0; }
+    else if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
+        beta = alpha; tj = 0.0; vjj = 1.0;
+    } else {
+        const double q = fma(alpha, alpha, s_j);
+        const double nrm = leaf_sqrt(q);
+        beta = -copysign(nrm, alpha);
+        vjj = alpha - beta;                                       // = sign(alpha) (|alpha| + nrm)
+        tj = leaf_rcp(fma(fabs(alpha), nrm, q));                  // 1 / (nrm (nrm + |alpha|)) = -1 / (beta vjj)
+    }
+    const double wza = fma(vjj, rk.x, sa), wzb = fma(vjj, rk.y, sb);   // v_j' a_k (k > j)  or  v_k' v_j (k < j)
+    if ((VAR & 2) && lane == 77) xa[3] = wza + wzb + tj;
+    if (!(VAR & 2) && 2 * cp + 1 > j) {
+        const double cb_ = tj * wzb;
+#pragma unroll
+        for (int i = 0; i < LEAF_NX; ++i) xb[i] = fma(-cb_, v[i], xb[i]);
+        if (rg == rgj) { if (ji == 0) xb[0] = fma(-cb_, vjj, xb[0]); else xb[1] = fma(-cb_, vjj, xb[1]); }
+        if (2 * cp > j) {
+            const double ca_ = tj * wza;
+#pragma unroll
+            for (int i = 0; i < LEAF_NX; ++i) xa[i] = fma(-ca_, v[i], xa[i]);
+            if (rg == rgj) { if (ji == 0) xa[0] = fma(-ca_, vjj, xa[0]); else xa[1] = fma(-ca_, vjj, xa[1]); }
+        }
+    }
+    if (cp == (j >> 1) && rg == rgj) {                  // explicit diagonal entry of V
+        if (COMP == 0) { if (ji == 0) xa[0] = vjj; else xa[1] = vjj; }
+        else           { if (ji == 0) xb[0] = vjj; else xb[1] = vjj; }
+    }
+    if (wrp == 0 && hh == 0) {
+        if (2 * cp < j) sm.Zs[j][2 * cp] = wza;
+        if (2 * cp + 1 < j) sm.Zs[j][2 * cp + 1] = wzb;
+        if (lane == 0) { sm.taus[j] = tj; sm.rdiag[j] = beta; }
+    }
+    const int j1 = j + 1;
+    if (j1 < QB) {
+        const int rg1 = j1 & (LEAF_NG - 1), ji1 = j1 >> 4;
+        if (!(VAR & 4) && cp == (j1 >> 1)) {    // publish the next pivot column: zeros at and above row j+1
+            double* cn = sm.colbuf[par ^ 1][rg];
+            const bool k0 = (0 > ji1) || (0 == ji1 && rg > rg1), k1 = (1 > ji1) || (1 == ji1 && rg > rg1);
+            if (COMP == 0) {      // next pivot column is this thread's column b
+                *reinterpret_cast<double2*>(cn) = make_double2(k0 ? xb[0] : 0.0, k1 ? xb[1] : 0.0);
+#pragma unroll
+                for (int i = 2; i < LEAF_NX; i += 2) *reinterpret_cast<double2*>(cn + i) = make_double2(xb[i], xb[i + 1]);
+            } else {
+                *reinterpret_cast<double2*>(cn) = make_double2(k0 ? xa[0] : 0.0, k1 ? xa[1] : 0.0);
+#pragma unroll
+                for (int i = 2; i < LEAF_NX; i += 2) *reinterpret_cast<double2*>(cn + i) = make_double2(xa[i], xa[i + 1]);
+            }
+        }
+        if (rg == rg1)            // next pivot row (read after the next step's barrier)
+            *reinterpret_cast<double2*>(&sm.rowbuf[par ^ 1][2 * cp]) = ji1 ? make_double2(xa[1], xb[1]) : make_double2(xa[0], xb[0]);
+    }
+    __syncwarp();
+}
+
+template <bool TIMING, int VAR>
+__global__ void __launch_bounds__(LEAF_THREADS, 2)
 qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
                double* __restrict__ Tout, long long* __restrict__ tbuf) {
 #define LEAF_T(slot) do { if (TIMING && tid == 32) tbuf[(slot)] = clock64(); } while (0)
-    __shared__ __align__(16) double colbuf[8][32];    // pivot column, exchanged WITHIN each warp (same row group)
-    __shared__ double rowbuf[2][QB];                  // pivot-row entry of every column (parity double buffer)
-    __shared__ double red[2][8][QB];                  // per-row-group partial dot products
-    __shared__ double Zs[QB][QB + 1];                 // Zs[j][k] = v_k' v_j  (k < j)
-    __shared__ double taus[QB], rdiag[QB];
+    __shared__ __align__(16) LeafSmem sm;
 
-    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int cp = lane & 15, hh = lane >> 4, rg = 2 * wrp + hh;
     const long long blk = blockIdx.x;
-    double* __restrict__ colbase = A + (c0 + lane) * ld;
-    const int body0 = 32 + 28 * grp;                  // first body row (tile coordinates)
+    double* __restrict__ cola = A + (c0 + 2 * cp) * ld;
+    double* __restrict__ colb = cola + ld;
+    const int body0 = QB + LEAF_BR * rg;              // first body row (tile coordinates)
 
-    double x[32];
+    double xa[LEAF_NX], xb[LEAF_NX];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        bool ok;
-        const double* p = leaf_row_ptr(colbase, tm, blk, grp + 8 * i, ok);
-        x[i] = ok ? *p : 0.0;
+    for (int i = 0; i < 2; ++i) {
+        long long mrow;
+        const bool ok = tm_row(tm, blk, rg + LEAF_NG * i, mrow);
+        xa[i] = ok ? cola[mrow] : 0.0;
+        xb[i] = ok ? colb[mrow] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 28; i += 2) {
-        bool ok;
-        const double* p = leaf_row_ptr(colbase, tm, blk, body0 + i, ok);
-        double2 v = make_double2(0.0, 0.0);
-        if (ok) v = *reinterpret_cast<const double2*>(p);
-        x[4 + i] = v.x; x[5 + i] = v.y;
+    for (int i = 0; i < LEAF_BR; i += 2) {
+        long long mrow;
+        const bool ok = tm_row(tm, blk, body0 + i, mrow);
+        double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+        if (ok) { va = *reinterpret_cast<const double2*>(cola + mrow); vb = *reinterpret_cast<const double2*>(colb + mrow); }
+        xa[2 + i] = va.x; xa[3 + i] = va.y;
+        xb[2 + i] = vb.x; xb[3 + i] = vb.y;
     }
-    double* cb = colbuf[grp];
+    // publish pivot column 0 (zeros at and above the diagonal) and pivot row 0
+    if (cp == 0) {
+        double* cb = sm.colbuf[0][rg];
+        *reinterpret_cast<double2*>(cb) = make_double2(rg > 0 ? xa[0] : 0.0, xa[1]);
+#pragma unroll
+        for (int i = 2; i < LEAF_NX; i += 2) *reinterpret_cast<double2*>(cb + i) = make_double2(xa[i], xa[i + 1]);
+    }
+    if (rg == 0) *reinterpret_cast<double2*>(&sm.rowbuf[0][2 * cp]) = make_double2(xa[0], xb[0]);
+    __syncwarp();
     LEAF_T(0);
 
-    // Reflectors are kept UNNORMALISED: v = a_j + sign(alpha) ||a_j|| e_j, H = I - t v v', t = -1 / (beta v_j).
-    // No column is rescaled and the only long-latency scalar work per step is one rsqrt and one reciprocal.
-    for (int j = 0; j < QB; ++j) {
-        const int par = j & 1;
-        const int jg = j & 7, ji = j >> 3;            // pivot row j lives in warp jg at head index ji
-        // head index i holds row grp + 8 i: below the diagonal  <=>  i > ji  or  (i == ji and grp > jg)
-        const int ilow = (grp > jg) ? ji : ji + 1;
-        __syncwarp();
-        LEAF_T(1 + 6 * j);
-        if (lane == j) {
-#pragma unroll
-            for (int i = 0; i < 4; i += 2)
-                *reinterpret_cast<double2*>(cb + i) = make_double2(i >= ilow ? x[i] : 0.0, i + 1 >= ilow ? x[i + 1] : 0.0);
-#pragma unroll
-            for (int i = 4; i < 32; i += 2) *reinterpret_cast<double2*>(cb + i) = make_double2(x[i], x[i + 1]);
-        }
-        if (grp == jg) rowbuf[par][lane] = (ji == 0) ? x[0] : (ji == 1) ? x[1] : (ji == 2) ? x[2] : x[3];
-        __syncwarp();
-        LEAF_T(2 + 6 * j);
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            const double2 v0 = *reinterpret_cast<const double2*>(cb + i);
-            const double2 v1 = *reinterpret_cast<const double2*>(cb + i + 2);
-            const double2 v2 = *reinterpret_cast<const double2*>(cb + i + 4);
-            const double2 v3 = *reinterpret_cast<const double2*>(cb + i + 6);
-            d0 = fma(v0.x, x[i], d0);     d0 = fma(v0.y, x[i + 1], d0);
-            d1 = fma(v1.x, x[i + 2], d1); d1 = fma(v1.y, x[i + 3], d1);
-            d2 = fma(v2.x, x[i + 4], d2); d2 = fma(v2.y, x[i + 5], d2);
-            d3 = fma(v3.x, x[i + 6], d3); d3 = fma(v3.y, x[i + 7], d3);
-        }
-        red[par][grp][lane] = (d0 + d1) + (d2 + d3);
-        LEAF_T(3 + 6 * j);
-        __syncthreads();                               // the only block-wide barrier of the step
-        LEAF_T(4 + 6 * j);
-        const double s_k = ((red[par][0][lane] + red[par][1][lane]) + (red[par][2][lane] + red[par][3][lane])) +
-                           ((red[par][4][lane] + red[par][5][lane]) + (red[par][6][lane] + red[par][7][lane]));
-        const double s_j = __shfl_sync(0xffffffffu, s_k, j);          // sum over rows > j of a_j^2
-        const double alpha = rowbuf[par][j];
-        const double rowk = rowbuf[par][lane];
-        double beta, tj, vjj;
-        if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
-            beta = alpha; tj = 0.0; vjj = 1.0;
-        } else {
-            const double q = fma(alpha, alpha, s_j);
-            const double nrm = q * rsqrt(q);
-            beta = -copysign(nrm, alpha);
-            vjj = alpha - beta;
-            tj = -1.0 / (beta * vjj);
-        }
-        const double wz = fma(vjj, rowk, s_k);      // v_j' a_k  (k > j)   or   v_k' v_j  (k < j)
-        if (TIMING && tid == 32) { if (wz == 1.2345e-300) tbuf[0] = 0; tbuf[5 + 6 * j] = clock64(); }
-        if (lane > j) {
-            const double coef = tj * wz;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(cb + i);
-                x[i] = fma(-coef, v.x, x[i]);
-                x[i + 1] = fma(-coef, v.y, x[i + 1]);
-            }
-            if (grp == jg) {       // pivot row
-                const double pv = coef * vjj;
-                x[0] = (ji == 0) ? x[0] - pv : x[0];
-                x[1] = (ji == 1) ? x[1] - pv : x[1];
-                x[2] = (ji == 2) ? x[2] - pv : x[2];
-                x[3] = (ji == 3) ? x[3] - pv : x[3];
-            }
-        } else if (grp == jg) {
-            if (lane == j) {
-                x[0] = (ji == 0) ? vjj : x[0];
-                x[1] = (ji == 1) ? vjj : x[1];
-                x[2] = (ji == 2) ? vjj : x[2];
-                x[3] = (ji == 3) ? vjj : x[3];
-                taus[j] = tj;
-                rdiag[j] = beta;
-            } else {
-                Zs[j][lane] = wz;
-            }
-        }
-        if (TIMING && tid == 32) { if (x[5] == 1.2345e-300) tbuf[0] = 0; tbuf[6 + 6 * j] = clock64(); }
+    // Reflectors are kept UNNORMALISED: v = a_j + sign(alpha) ||a_j|| e_j, H = I - t v v', t = 1 / (||a_j|| (||a_j|| + |alpha|)).
+    // One block-wide barrier per step; the owners of column j+1 publish it from inside step j.
+#pragma unroll 1
+    for (int jj = 0; jj < QB / 2; ++jj) {
+        LEAF_T(1 + 2 * jj);
+        leaf_step<0, VAR>(2 * jj, xa, xb, sm, lane, wrp, cp, hh, rg);
+        LEAF_T(2 + 2 * jj);
+        leaf_step<1, VAR>(2 * jj + 1, xa, xb, sm, lane, wrp, cp, hh, rg);
     }
     __syncthreads();
     LEAF_T(200);
 
     // ---- V (explicit diagonal entry, zeros above) to the workspace; R head back into the matrix ----
-    double* __restrict__ Vb = Vout + blk * (long long)(QB * QS) + lane * QS;
+    {
+        double* __restrict__ Va = Vout + blk * (long long)(QB * QS) + (2 * cp) * QS;
+        double* __restrict__ Vbp = Va + QS;
+        const int ca = 2 * cp, cbn = 2 * cp + 1;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = grp + 8 * i;                                // head row
-        Vb[r] = (r >= lane) ? x[i] : 0.0;
-        bool ok;
-        double* p = leaf_row_ptr(colbase, tm, blk, r, ok);
-        if (ok) *p = (r < lane) ? x[i] : ((r == lane) ? rdiag[lane] : 0.0);
-    }
-#pragma unroll
-    for (int i = 0; i < 28; i += 2)
-        *reinterpret_cast<double2*>(Vb + body0 + i) = make_double2(x[4 + i], x[5 + i]);
-
-    // ---- T = (diag(1/t) + striu(V'V))^{-1}, one column per lane of warp 0 (division-free back substitution) ----
-    if (grp == 0) {
-        double t[32];
-        const double tau_c = taus[lane];
-#pragma unroll
-        for (int k = 31; k >= 0; --k) {
-            double acc = 0.0;
-#pragma unroll
-            for (int i = k + 1; i < 32; ++i) acc = fma(Zs[i][k], t[i], acc);
-            const double tk = -acc * taus[k];
-            t[k] = (k == lane) ? tau_c : ((k < lane) ? tk : 0.0);
+        for (int i = 0; i < 2; ++i) {
+            const int r = rg + LEAF_NG * i;                       // head row
+            Va[r] = (r >= ca) ? xa[i] : 0.0;
+            Vbp[r] = (r >= cbn) ? xb[i] : 0.0;
+            long long mrow;
+            if (tm_row(tm, blk, r, mrow)) {
+                cola[mrow] = (r < ca) ? xa[i] : ((r == ca) ? sm.rdiag[ca] : 0.0);
+                colb[mrow] = (r < cbn) ? xb[i] : ((r == cbn) ? sm.rdiag[cbn] : 0.0);
+            }
         }
-        double* __restrict__ Tb = Tout + blk * (long long)(QB * QWS) + lane * QWS;   // column `lane`, column stride QWS (smem image)
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(Tb + k) = make_double2(t[k], t[k + 1]);
+        for (int i = 0; i < LEAF_BR; i += 2) {
+            *reinterpret_cast<double2*>(Va + body0 + i) = make_double2(xa[2 + i], xa[3 + i]);
+            *reinterpret_cast<double2*>(Vbp + body0 + i) = make_double2(xb[2 + i], xb[3 + i]);
+        }
+    }
+
+    // ---- T = U^{-1},  U = diag(1/t) + striu(V'V)  (U[k][i] = Zs[i][k], k < i).  Recursive blocked inversion of the upper
+    //      triangular U:  [U11 U12; 0 U22]^{-1} = [T11, -T11 U12 T22; 0, T22], block size 1, 2, 4, 8, 16. ----
+    {
+        for (int e = tid; e < QB * QB; e += LEAF_THREADS) {
+            const int r = e >> 5, c = e & 31;
+            sm.Tm[r][c] = (r == c) ? sm.taus[r] : 0.0;
+        }
+        __syncthreads();
+        for (int b = 1; b < QB; b <<= 1) {
+            // element (i, jn) of every pair's off-diagonal block: 16 b elements in all
+            const int ne = (QB / 2) * b;
+            const int pr = tid / (b * b), rem = tid - pr * b * b, i = rem / b, jn = rem - i * b;
+            const int r0 = 2 * b * pr;
+            if (tid < ne) {      // W = U12 T22
+                double acc = 0.0;
+                for (int k = 0; k <= jn; ++k) acc = fma(sm.Zs[r0 + b + k][r0 + i], sm.Tm[r0 + b + k][r0 + b + jn], acc);
+                sm.Wm[r0 + i][r0 + b + jn] = acc;
+            }
+            __syncthreads();
+            if (tid < ne) {      // T12 = -T11 W
+                double acc = 0.0;
+                for (int k = i; k < b; ++k) acc = fma(sm.Tm[r0 + i][r0 + k], sm.Wm[r0 + k][r0 + b + jn], acc);
+                sm.Tm[r0 + i][r0 + b + jn] = -acc;
+            }
+            __syncthreads();
+        }
+        double* __restrict__ Tb = Tout + blk * (long long)(QB * QWS);     // Tb[c * QWS + k] = T[k][c]  (smem image of the update kernels)
+        for (int e = tid; e < QB * QB; e += LEAF_THREADS) {
+            const int c = e >> 5, k = e & 31;
+            Tb[c * QWS + k] = sm.Tm[k][c];
+        }
     }
     if (TIMING && tid == 0) tbuf[201] = clock64();
 #undef LEAF_T
@@ -954,7 +1057,7 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
-        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel_t<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     return LSO_OK;
@@ -1033,10 +1136,18 @@ static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id)
 }
 static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st) {
     for (int l = 0; l < pl.L; ++l) {
-        if (g_leaf_tbuf && pl.nblk[l] == 1)
-            qr_leaf_kernel_t<true><<<1, 256, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf], plan->lev[l].T[buf], g_leaf_tbuf);
+        if (g_leaf_tbuf && pl.nblk[l] == 1) {
+            static int var = getenv("LSO_LEAF_VARIANT") ? atoi(getenv("LSO_LEAF_VARIANT")) : 0;
+#define LEAF_VAR_CASE(VV) case VV: qr_leaf_kernel_t<true, VV><<<1, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf], plan->lev[l].T[buf], g_leaf_tbuf); break;
+            switch (var) {
+                LEAF_VAR_CASE(1) LEAF_VAR_CASE(2) LEAF_VAR_CASE(3) LEAF_VAR_CASE(7) LEAF_VAR_CASE(15) LEAF_VAR_CASE(31) LEAF_VAR_CASE(63)
+                LEAF_VAR_CASE(4) LEAF_VAR_CASE(8) LEAF_VAR_CASE(16) LEAF_VAR_CASE(32)
+                default: qr_leaf_kernel_t<true, 0><<<1, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf], plan->lev[l].T[buf], g_leaf_tbuf);
+            }
+#undef LEAF_VAR_CASE
+        }
         else
-            qr_leaf_kernel_t<false><<<(unsigned)pl.nblk[l], 256, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf],
+            qr_leaf_kernel_t<false, 0><<<(unsigned)pl.nblk[l], LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf],
                                                                           plan->lev[l].T[buf], nullptr);
         LSO_CHECK_LAUNCH(ctx);
     }

@@ -17,10 +17,5 @@ for _ in range(3):
     ws.ldiv(x, J, y, d)
 fn(ctx.handle, buf.ctypes.data)
 t = buf
-print("prologue (loads)->loop start: n/a ; total loop", t[200] - t[0], "epilogue", t[201] - t[200])
-ph = np.zeros(6)
-for j in range(32):
-    b = 6 * j
-    nxt = t[1 + 6 * (j + 1)] if j < 31 else t[200]
-    ph += [t[2 + b] - t[1 + b], t[3 + b] - t[2 + b], t[4 + b] - t[3 + b], t[5 + b] - t[4 + b], t[6 + b] - t[5 + b], nxt - t[6 + b]]
-print("avg cycles/step: publish %.0f | dot %.0f | barrier %.0f | reduce+scalars %.0f | update %.0f | loop overhead %.0f | sum %.0f" % (*(ph / 32), ph.sum() / 32))
+print("loop cycles", t[200] - t[0], "=> per step", (t[200] - t[0]) / 32, "| epilogue", t[201] - t[200])
+print("per-step:", [int(t[2 + k] - t[1 + k]) for k in range(31)])
