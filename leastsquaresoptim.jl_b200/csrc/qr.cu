@@ -83,35 +83,103 @@ __device__ __forceinline__ double leaf_rcp(double d) {
     return fma(z, e, z);
 }
 
-// 256 threads.  The step time of a Householder factorisation held in registers is set by the shared-memory pipe:
-// every value of the pivot column that a thread needs costs 8 bytes of LDS return bandwidth (128 B/clk per SM), so
-// the layout minimises "pivot-column values per thread" and reads them ONCE per step:
+// ---- panel factorisation: the whole TSQR tree of a panel in ONE launch, levels pipelined step by step ----
+// 256 threads per block.  The step time of a Householder factorisation held in registers is set by the length of
+// one warp's dependent instruction stream and by the shared-memory pipe (every pivot-column value a thread needs
+// costs 8 bytes of LDS return bandwidth), so the layout minimises "pivot-column values per thread" and reads them
+// ONCE per step:
 //     lane = (column pair cp = lane & 15, half hh = lane >> 4); warp w, half hh  ->  row group rg = 2 w + hh (16 groups)
-//     a thread holds 16 rows of TWO adjacent columns (xa: column 2 cp, xb: column 2 cp + 1), rows
-//         i = 0, 1   head rows  rg, rg + 16            (the 32 head rows end up holding R)
-//         i = 2..15  body rows  32 + 14 rg ... + 13    (one contiguous run; always below the diagonal)
+//     a thread holds 16 rows ("slots") of TWO adjacent columns (xa: column 2 cp, xb: column 2 cp + 1)
+//         slots 0, 1    head rows  rg, rg + 16          (the 32 head rows end up holding R)
+//         slots 2..15   level 0 : body rows 32 + 14 rg ... + 13  (one contiguous run; always below the diagonal)
+//                       level>0 : slot 2 s + h = row rg + 16 h of segment s = 1..7 (child s's R factor)
 //     and loads the 16 pivot-column values of its row group into registers once per step (dot product AND update).
+//
+// Tree levels run CONCURRENTLY.  The block of level l > 0 stacks the R factors of 8 children; row i of a child's R is
+// final after the child's step i, and the parent's step j only touches rows <= j of every child triangle (the rest
+// of column j is zero).  So a child publishes row j of its R right after its step j, and the parent pulls row j + 3
+// of its 8 children at its own step j: the levels of the tree are skewed by a few steps instead of running one
+// after the other (QB + 3 (L-1) steps instead of QB L).  Rows travel through an L2-resident mailbox in 16-byte
+// units {lo32, tag, hi32, tag} (the NCCL "LL" idea: the data carries its own flag; every 8-byte half is single-copy
+// atomic, the tag is unique per launch and row), so neither side executes a fence: the child fires and forgets,
+// the parent polls the data itself.  Blocks are numbered children first, so a waiting parent never occupies a slot
+// that one of its children still needs.
 #define LEAF_THREADS 256
 #define LEAF_NG 16          /* row groups */
-#define LEAF_NX 16          /* rows per thread */
-#define LEAF_BR 14          /* body rows per thread */
+#define LEAF_NX 16          /* rows (slots) per thread */
+#define LEAF_BR 14          /* body rows per thread at level 0 */
+#define LEAF_D 3            /* a parent requests row j + LEAF_D of its children at step j */
+#define LEAF_NSTG 4         /* staging buffers for pulled rows */
+
+struct TreeParams {
+    int nlev;
+    int start[QR_MAX_LEVELS + 1];     // first blockIdx of each level
+    TileMap tm[QR_MAX_LEVELS];
+    double* V[QR_MAX_LEVELS];
+    double* T[QR_MAX_LEVELS];
+    uint4* mail;                      // mailbox: [block][row][column] {lo32, tag, hi32, tag}
+    unsigned base;                    // tag of row r in this launch = base + r + 1
+};
 
 struct LeafSmem {
     double colbuf[2][LEAF_NG][LEAF_NX];   // pivot column (parity double buffer), exchanged WITHIN each half-warp
     double rowbuf[2][QB];                 // pivot-row entry of every column (parity double buffer)
     double red[2][8][QB];                 // per-warp partial dot products
+    double stage[LEAF_NSTG][8][QB];       // rows pulled from the children (level > 0): [row % NSTG][segment][column]
     double Zs[QB][QB + 1];                // Zs[j][k] = v_k' v_j  (k < j)  =  U[k][j],  U = T^{-1}
     double Tm[QB][QB + 1];                // T
     double Wm[QB][QB + 1];                // scratch of the blocked inversion
     double taus[QB], rdiag[QB];
 };
 
+struct LeafCtx {
+    int lane, wrp, cp, hh, rg;
+    bool lazy, publish;
+    uint4* mymail;            // this block's mailbox rows, already offset to column 2 cp  (publish)
+    unsigned base;
+    // puller state (level > 0): thread t pulls column (t & 31) of segment (t >> 5)
+    const uint4* src;         // the child's mailbox, offset to that column (nullptr: no such child => zeros)
+    uint4 pend;               // row requested during the previous step
+    int pseg, pcol;
+};
+
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 leaf_pack(double x, unsigned tag) {
+    return make_uint4((unsigned)__double2loint(x), tag, (unsigned)__double2hiint(x), tag);
+}
+// request row `row` of the child (non-blocking)
+__device__ __forceinline__ void leaf_request(LeafCtx& c, int row) {
+    if (c.src != nullptr) c.pend = ld_volatile_u4(c.src + row * QB);
+}
+// complete the request for row `row`: poll until both halves carry this launch's tag for that row
+__device__ __forceinline__ double leaf_complete(LeafCtx& c, int row) {
+    if (c.src == nullptr) return 0.0;
+    const unsigned tag = c.base + (unsigned)row + 1u;
+    while (c.pend.y != tag || c.pend.w != tag) {
+        __nanosleep(20);
+        c.pend = ld_volatile_u4(c.src + row * QB);
+    }
+    return __hiloint2double((int)c.pend.z, (int)c.pend.x);
+}
+
 // one Householder step; COMP = j & 1 selects which of the thread's two columns can be the pivot column
-template <int COMP, int VAR>
-__device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], double (&xb)[LEAF_NX], LeafSmem& sm,
-                                          const int lane, const int wrp, const int cp, const int hh, const int rg) {
+template <int COMP>
+__device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], double (&xb)[LEAF_NX], LeafSmem& sm, LeafCtx& c) {
+    const int lane = c.lane, wrp = c.wrp, cp = c.cp, hh = c.hh, rg = c.rg;
     const int par = j & 1;
-    const int rgj = j & (LEAF_NG - 1), ji = j >> 4;       // pivot row j: row group rgj, head index ji
+    const int rgj = j & (LEAF_NG - 1), ji = j >> 4;       // pivot row j: row group rgj, head slot ji
+    if (c.lazy) {
+        // row j+2 (requested during the previous step) goes to the staging buffer; row j+3 is requested now
+        if (j + LEAF_D - 1 < QB) sm.stage[(j + LEAF_D - 1) & (LEAF_NSTG - 1)][c.pseg][c.pcol] = leaf_complete(c, j + LEAF_D - 1);
+        if (j + LEAF_D < QB) leaf_request(c, j + LEAF_D);
+    }
     double v[LEAF_NX];
     {
         const double* cb = sm.colbuf[par][rg];
@@ -122,8 +190,6 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
         }
     }
     double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;
-    if (VAR & 8) { da0 = v[0] + v[15]; db0 = v[1] + v[14]; }
-    else
 #pragma unroll
     for (int i = 0; i < LEAF_NX; i += 2) {
         da0 = fma(v[i], xa[i], da0); da1 = fma(v[i + 1], xa[i + 1], da1);
@@ -133,10 +199,21 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
     da += __shfl_xor_sync(0xffffffffu, da, 16);
     db += __shfl_xor_sync(0xffffffffu, db, 16);
     if (hh == 0) *reinterpret_cast<double2*>(&sm.red[par][wrp][2 * cp]) = make_double2(da, db);
-    if (!(VAR & 16)) __syncthreads();                  // the only block-wide barrier of the step
+    __syncthreads();                                   // the only block-wide barrier of the step
+    if (c.lazy && j + 1 < QB && rg == ((j + 1) & (LEAF_NG - 1))) {
+        // row j+1 of the 8 children moves from the staging buffer into this row group's slots (it is all zero left of
+        // column j+1, so the rest of this step leaves it alone, and the publication of column j+1 below includes it)
+        const double* st = &sm.stage[(j + 1) & (LEAF_NSTG - 1)][0][2 * cp];
+        if ((j + 1) >> 4) {
+#pragma unroll
+            for (int sg = 0; sg < 8; ++sg) { const double2 t = *reinterpret_cast<const double2*>(st + sg * QB); xa[2 * sg + 1] = t.x; xb[2 * sg + 1] = t.y; }
+        } else {
+#pragma unroll
+            for (int sg = 0; sg < 8; ++sg) { const double2 t = *reinterpret_cast<const double2*>(st + sg * QB); xa[2 * sg] = t.x; xb[2 * sg] = t.y; }
+        }
+    }
     double sa, sb;
-    if (VAR & 32) { sa = da; sb = db; }
-    else {
+    {
         const double* rp = &sm.red[par][4 * hh][2 * cp];
         const double2 p0 = *reinterpret_cast<const double2*>(rp);
         const double2 p1 = *reinterpret_cast<const double2*>(rp + QB);
@@ -151,8 +228,7 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
     const double alpha = sm.rowbuf[par][j];
     const double2 rk = *reinterpret_cast<const double2*>(&sm.rowbuf[par][2 * cp]);
     double beta, tj, vjj;
-    if (VAR & 1) { beta = alpha; tj = 1e-3 * s_j; vjj = 1.0; }
-    else if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
+    if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
         beta = alpha; tj = 0.0; vjj = 1.0;
     } else {
         const double q = fma(alpha, alpha, s_j);
@@ -162,8 +238,7 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
         tj = leaf_rcp(fma(fabs(alpha), nrm, q));                  // 1 / (nrm (nrm + |alpha|)) = -1 / (beta vjj)
     }
     const double wza = fma(vjj, rk.x, sa), wzb = fma(vjj, rk.y, sb);   // v_j' a_k (k > j)  or  v_k' v_j (k < j)
-    if ((VAR & 2) && lane == 77) xa[3] = wza + wzb + tj;
-    if (!(VAR & 2) && 2 * cp + 1 > j) {
+    if (2 * cp + 1 > j) {
         const double cb_ = tj * wzb;
 #pragma unroll
         for (int i = 0; i < LEAF_NX; ++i) xb[i] = fma(-cb_, v[i], xb[i]);
@@ -175,9 +250,18 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
             if (rg == rgj) { if (ji == 0) xa[0] = fma(-ca_, vjj, xa[0]); else xa[1] = fma(-ca_, vjj, xa[1]); }
         }
     }
-    if (cp == (j >> 1) && rg == rgj) {                  // explicit diagonal entry of V
-        if (COMP == 0) { if (ji == 0) xa[0] = vjj; else xa[1] = vjj; }
-        else           { if (ji == 0) xb[0] = vjj; else xb[1] = vjj; }
+    if (rg == rgj) {
+        if (c.publish) {        // row j of R is final: hand it to the parent (fire and forget)
+            const double ra = ji ? xa[1] : xa[0], rb = ji ? xb[1] : xb[0];
+            const unsigned tag = c.base + (unsigned)j + 1u;
+            uint4* dst = c.mymail + j * QB;
+            st_volatile_u4(dst, leaf_pack((2 * cp > j) ? ra : ((2 * cp == j) ? beta : 0.0), tag));
+            st_volatile_u4(dst + 1, leaf_pack((2 * cp + 1 > j) ? rb : ((2 * cp + 1 == j) ? beta : 0.0), tag));
+        }
+        if (cp == (j >> 1)) {                           // explicit diagonal entry of V
+            if (COMP == 0) { if (ji == 0) xa[0] = vjj; else xa[1] = vjj; }
+            else           { if (ji == 0) xb[0] = vjj; else xb[1] = vjj; }
+        }
     }
     if (wrp == 0 && hh == 0) {
         if (2 * cp < j) sm.Zs[j][2 * cp] = wza;
@@ -187,7 +271,7 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
     const int j1 = j + 1;
     if (j1 < QB) {
         const int rg1 = j1 & (LEAF_NG - 1), ji1 = j1 >> 4;
-        if (!(VAR & 4) && cp == (j1 >> 1)) {    // publish the next pivot column: zeros at and above row j+1
+        if (cp == (j1 >> 1)) {    // publish the next pivot column: zeros at and above row j+1
             double* cn = sm.colbuf[par ^ 1][rg];
             const bool k0 = (0 > ji1) || (0 == ji1 && rg > rg1), k1 = (1 > ji1) || (1 == ji1 && rg > rg1);
             if (COMP == 0) {      // next pivot column is this thread's column b
@@ -206,36 +290,68 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
     __syncwarp();
 }
 
-template <bool TIMING, int VAR>
+template <bool TIMING>
 __global__ void __launch_bounds__(LEAF_THREADS, 2)
-qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm, double* __restrict__ Vout,
-               double* __restrict__ Tout, long long* __restrict__ tbuf) {
-#define LEAF_T(slot) do { if (TIMING && tid == 32) tbuf[(slot)] = clock64(); } while (0)
+qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams tp, long long* __restrict__ tbuf) {
     __shared__ __align__(16) LeafSmem sm;
 
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int cp = lane & 15, hh = lane >> 4, rg = 2 * wrp + hh;
-    const long long blk = blockIdx.x;
+    const int tid = threadIdx.x;
+    int lev = 0;
+    while (lev + 1 < tp.nlev && (int)blockIdx.x >= tp.start[lev + 1]) ++lev;
+    const long long blk = (int)blockIdx.x - tp.start[lev];
+    const TileMap tm = tp.tm[lev];
+    const bool timed = TIMING && blockIdx.x == gridDim.x - 1;
+#define LEAF_T(slot) do { if (timed && tid == 32) tbuf[(slot)] = clock64(); } while (0)
+
+    LeafCtx c;
+    c.lane = tid & 31; c.wrp = tid >> 5; c.cp = c.lane & 15; c.hh = c.lane >> 4; c.rg = 2 * c.wrp + c.hh;
+    c.lazy = lev > 0;
+    c.publish = lev + 1 < tp.nlev;
+    c.base = tp.base;
+    c.src = nullptr; c.pend = make_uint4(0u, 0u, 0u, 0u); c.pseg = tid >> 5; c.pcol = tid & 31;
+    const int cp = c.cp, rg = c.rg;
     double* __restrict__ cola = A + (c0 + 2 * cp) * ld;
     double* __restrict__ colb = cola + ld;
-    const int body0 = QB + LEAF_BR * rg;              // first body row (tile coordinates)
+    c.mymail = tp.mail + (long long)blockIdx.x * (QB * QB) + 2 * cp;
+    double* __restrict__ heada = cola + tm.r0 + QB * blk;     // head row 0 of this block, column a
+    const int body0 = QB + LEAF_BR * rg;              // level 0: first body row (tile coordinates)
 
     double xa[LEAF_NX], xb[LEAF_NX];
+    if (!c.lazy) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        long long mrow;
-        const bool ok = tm_row(tm, blk, rg + LEAF_NG * i, mrow);
-        xa[i] = ok ? cola[mrow] : 0.0;
-        xb[i] = ok ? colb[mrow] : 0.0;
-    }
+        for (int i = 0; i < 2; ++i) {
+            long long mrow;
+            const bool ok = tm_row(tm, blk, rg + LEAF_NG * i, mrow);
+            xa[i] = ok ? cola[mrow] : 0.0;
+            xb[i] = ok ? colb[mrow] : 0.0;
+        }
 #pragma unroll
-    for (int i = 0; i < LEAF_BR; i += 2) {
-        long long mrow;
-        const bool ok = tm_row(tm, blk, body0 + i, mrow);
-        double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-        if (ok) { va = *reinterpret_cast<const double2*>(cola + mrow); vb = *reinterpret_cast<const double2*>(colb + mrow); }
-        xa[2 + i] = va.x; xa[3 + i] = va.y;
-        xb[2 + i] = vb.x; xb[3 + i] = vb.y;
+        for (int i = 0; i < LEAF_BR; i += 2) {
+            long long mrow;
+            const bool ok = tm_row(tm, blk, body0 + i, mrow);
+            double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+            if (ok) { va = *reinterpret_cast<const double2*>(cola + mrow); vb = *reinterpret_cast<const double2*>(colb + mrow); }
+            xa[2 + i] = va.x; xa[3 + i] = va.y;
+            xb[2 + i] = vb.x; xb[3 + i] = vb.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < LEAF_NX; ++i) { xa[i] = 0.0; xb[i] = 0.0; }
+        // puller: segment 0 is child `blk` of the level below (its head is this block's head), segment s >= 1 is child
+        // nb + 7 blk + s - 1 (this block's body rows 32 s ... 32 s + 31)
+        const long long child = (c.pseg == 0) ? blk : tm.nb + (QG - 1) * blk + (c.pseg - 1);
+        if (child < tp.tm[lev - 1].nb) c.src = tp.mail + (long long)(tp.start[lev - 1] + child) * (QB * QB) + c.pcol;
+        leaf_request(c, 0);
+        sm.stage[0][c.pseg][c.pcol] = leaf_complete(c, 0);
+        leaf_request(c, 1);
+        sm.stage[1][c.pseg][c.pcol] = leaf_complete(c, 1);
+        leaf_request(c, 2);
+        __syncthreads();
+        if (rg == 0) {
+            const double* st = &sm.stage[0][0][2 * cp];
+#pragma unroll
+            for (int sg = 0; sg < 8; ++sg) { const double2 t = *reinterpret_cast<const double2*>(st + sg * QB); xa[2 * sg] = t.x; xb[2 * sg] = t.y; }
+        }
     }
     // publish pivot column 0 (zeros at and above the diagonal) and pivot row 0
     if (cp == 0) {
@@ -253,16 +369,16 @@ qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm,
 #pragma unroll 1
     for (int jj = 0; jj < QB / 2; ++jj) {
         LEAF_T(1 + 2 * jj);
-        leaf_step<0, VAR>(2 * jj, xa, xb, sm, lane, wrp, cp, hh, rg);
+        leaf_step<0>(2 * jj, xa, xb, sm, c);
         LEAF_T(2 + 2 * jj);
-        leaf_step<1, VAR>(2 * jj + 1, xa, xb, sm, lane, wrp, cp, hh, rg);
+        leaf_step<1>(2 * jj + 1, xa, xb, sm, c);
     }
     __syncthreads();
     LEAF_T(200);
 
     // ---- V (explicit diagonal entry, zeros above) to the workspace; R head back into the matrix ----
     {
-        double* __restrict__ Va = Vout + blk * (long long)(QB * QS) + (2 * cp) * QS;
+        double* __restrict__ Va = tp.V[lev] + blk * (long long)(QB * QS) + (2 * cp) * QS;
         double* __restrict__ Vbp = Va + QS;
         const int ca = 2 * cp, cbn = 2 * cp + 1;
 #pragma unroll
@@ -270,16 +386,22 @@ qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm,
             const int r = rg + LEAF_NG * i;                       // head row
             Va[r] = (r >= ca) ? xa[i] : 0.0;
             Vbp[r] = (r >= cbn) ? xb[i] : 0.0;
-            long long mrow;
-            if (tm_row(tm, blk, r, mrow)) {
-                cola[mrow] = (r < ca) ? xa[i] : ((r == ca) ? sm.rdiag[ca] : 0.0);
-                colb[mrow] = (r < cbn) ? xb[i] : ((r == cbn) ? sm.rdiag[cbn] : 0.0);
-            }
+            heada[r] = (r < ca) ? xa[i] : ((r == ca) ? sm.rdiag[ca] : 0.0);
+            heada[ld + r] = (r < cbn) ? xb[i] : ((r == cbn) ? sm.rdiag[cbn] : 0.0);
         }
+        if (!c.lazy) {
 #pragma unroll
-        for (int i = 0; i < LEAF_BR; i += 2) {
-            *reinterpret_cast<double2*>(Va + body0 + i) = make_double2(xa[2 + i], xa[3 + i]);
-            *reinterpret_cast<double2*>(Vbp + body0 + i) = make_double2(xb[2 + i], xb[3 + i]);
+            for (int i = 0; i < LEAF_BR; i += 2) {
+                *reinterpret_cast<double2*>(Va + body0 + i) = make_double2(xa[2 + i], xa[3 + i]);
+                *reinterpret_cast<double2*>(Vbp + body0 + i) = make_double2(xb[2 + i], xb[3 + i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 2; i < LEAF_NX; ++i) {
+                const int r = QB * (i >> 1) + rg + LEAF_NG * (i & 1);
+                Va[r] = xa[i];
+                Vbp[r] = xb[i];
+            }
         }
     }
 
@@ -287,8 +409,8 @@ qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm,
     //      triangular U:  [U11 U12; 0 U22]^{-1} = [T11, -T11 U12 T22; 0, T22], block size 1, 2, 4, 8, 16. ----
     {
         for (int e = tid; e < QB * QB; e += LEAF_THREADS) {
-            const int r = e >> 5, c = e & 31;
-            sm.Tm[r][c] = (r == c) ? sm.taus[r] : 0.0;
+            const int r = e >> 5, cc = e & 31;
+            sm.Tm[r][cc] = (r == cc) ? sm.taus[r] : 0.0;
         }
         __syncthreads();
         for (int b = 1; b < QB; b <<= 1) {
@@ -309,13 +431,13 @@ qr_leaf_kernel_t(double* __restrict__ A, long long ld, long long c0, TileMap tm,
             }
             __syncthreads();
         }
-        double* __restrict__ Tb = Tout + blk * (long long)(QB * QWS);     // Tb[c * QWS + k] = T[k][c]  (smem image of the update kernels)
+        double* __restrict__ Tb = tp.T[lev] + blk * (long long)(QB * QWS);     // Tb[c * QWS + k] = T[k][c]  (smem image of the update kernels)
         for (int e = tid; e < QB * QB; e += LEAF_THREADS) {
-            const int c = e >> 5, k = e & 31;
-            Tb[c * QWS + k] = sm.Tm[k][c];
+            const int cc = e >> 5, k = e & 31;
+            Tb[cc * QWS + k] = sm.Tm[k][cc];
         }
     }
-    if (TIMING && tid == 0) tbuf[201] = clock64();
+    if (timed && tid == 0) tbuf[201] = clock64();
 #undef LEAF_T
 }
 
@@ -1032,6 +1154,13 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         nb = cdiv64(nb * QB, QH);
     }
     plan->nlevels = L;
+    {
+        int64_t tot = 0;
+        for (int l = 0; l < L; ++l) tot += plan->lev[l].nblocks;
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&plan->mail, (size_t)tot * QB * QB * sizeof(uint4)));
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->mail, 0, (size_t)tot * QB * QB * sizeof(uint4), ctx->stream));
+        plan->prog_base = 0;
+    }
     {   // the panel stream gets the highest priority: its (small, latency-bound) kernels must be placed as soon as
         // they are ready, underneath / ahead of the bulk trailing update
         int prio_lo = 0, prio_hi = 0;
@@ -1057,7 +1186,7 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
-        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_leaf_kernel_t<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_tree_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     return LSO_OK;
@@ -1071,6 +1200,7 @@ void qr_plan_destroy(QRPlan* plan) {
     for (cudaEvent_t ev : plan->ev_rest) cudaEventDestroy(ev);
     for (cudaEvent_t ev : plan->ev_next) cudaEventDestroy(ev);
     cudaFree(plan->A);
+    cudaFree(plan->mail);
     for (int l = 0; l < plan->nlevels; ++l)
         for (int b = 0; b < 2; ++b) {
             cudaFree(plan->lev[l].V[b]);
@@ -1135,22 +1265,31 @@ static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id)
     g_tl.push_back({e, what, k, stream_id});
 }
 static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st) {
+    TreeParams tp;
+    tp.nlev = pl.L;
+    int total = 0;
     for (int l = 0; l < pl.L; ++l) {
-        if (g_leaf_tbuf && pl.nblk[l] == 1) {
-            static int var = getenv("LSO_LEAF_VARIANT") ? atoi(getenv("LSO_LEAF_VARIANT")) : 0;
-#define LEAF_VAR_CASE(VV) case VV: qr_leaf_kernel_t<true, VV><<<1, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf], plan->lev[l].T[buf], g_leaf_tbuf); break;
-            switch (var) {
-                LEAF_VAR_CASE(1) LEAF_VAR_CASE(2) LEAF_VAR_CASE(3) LEAF_VAR_CASE(7) LEAF_VAR_CASE(15) LEAF_VAR_CASE(31) LEAF_VAR_CASE(63)
-                LEAF_VAR_CASE(4) LEAF_VAR_CASE(8) LEAF_VAR_CASE(16) LEAF_VAR_CASE(32)
-                default: qr_leaf_kernel_t<true, 0><<<1, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf], plan->lev[l].T[buf], g_leaf_tbuf);
-            }
-#undef LEAF_VAR_CASE
-        }
-        else
-            qr_leaf_kernel_t<false, 0><<<(unsigned)pl.nblk[l], LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, pl.tm[l], plan->lev[l].V[buf],
-                                                                          plan->lev[l].T[buf], nullptr);
-        LSO_CHECK_LAUNCH(ctx);
+        tp.start[l] = total;
+        tp.tm[l] = pl.tm[l];
+        tp.V[l] = plan->lev[l].V[buf];
+        tp.T[l] = plan->lev[l].T[buf];
+        total += (int)pl.nblk[l];
     }
+    tp.start[pl.L] = total;
+    tp.mail = plan->mail;
+    if (plan->prog_base > 0xfffff000u) {      // counter wrap: start over (stream-ordered after every earlier launch)
+        int64_t tot = 0;
+        for (int l = 0; l < plan->nlevels; ++l) tot += plan->lev[l].nblocks;
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->mail, 0, (size_t)tot * QB * QB * sizeof(uint4), st));
+        plan->prog_base = 0;
+    }
+    plan->prog_base += 64;            // counters of earlier launches are all below the new base
+    tp.base = plan->prog_base;
+    if (g_leaf_tbuf && pl.nblk[0] <= 64)
+        qr_tree_kernel_t<true><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);
+    else
+        qr_tree_kernel_t<false><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, nullptr);
+    LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
 }
 

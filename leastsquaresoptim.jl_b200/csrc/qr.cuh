@@ -34,6 +34,8 @@ struct QRPlan {
     int64_t ld = 0;      // leading dimension: roundup(M, QB) + QH zero rows of padding
     double* A = nullptr; // ld x Nc, column-major
     int nlevels = 0;
+    uint4* mail = nullptr;      // mailbox of the fused panel-tree kernel: [block][row][column] {lo32, tag, hi32, tag}
+    unsigned prog_base = 0;     // tag base of the current launch (row r carries tag base + r + 1)
     QRLevel lev[QR_MAX_LEVELS];
     // look-ahead: panel factorisations run on a second stream, overlapped with the previous trailing update
     cudaStream_t panel_stream = nullptr;
