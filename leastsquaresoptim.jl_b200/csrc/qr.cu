@@ -57,22 +57,23 @@ __device__ __forceinline__ int tm_body_rows(const TileMap& tm, long long blk) {
 // reduced through shared memory, and the rank-1 update is applied from the published column.  The T factor of
 // the compact WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V).
 // =================================================================================================
-// sqrt(q) and 1/d for the reflector scalars.  Fast path: MUFU seed + two Goldschmidt / Newton steps (no IEEE
-// slow-path branches on the critical chain of every Householder step); operands outside a safe range take the
-// library routines.  Results are within a couple of ulp, which perturbs H = I - t v v' by O(eps) like dlarfg.
-__device__ __forceinline__ double leaf_sqrt(double q) {
-    if (!(q > 1e-280 && q < 1e280)) return sqrt(q);
+// Reflector scalars of one Householder step (dlarfg with an unnormalised v):
+//     nrm = sqrt(alpha^2 + s),  beta = -sign(alpha) nrm,  vjj = alpha - beta,  t = 1 / (nrm (nrm + |alpha|)).
+// Fast path: MUFU seeds + two Goldschmidt / Newton steps, no branches on the chain; results are within a couple of
+// ulp, which perturbs H = I - t v v' by O(eps) like dlarfg's own rounding.  Arguments outside the safe range (zero
+// column, subnormal or huge norm) take the library routines behind one rarely taken branch.
+__device__ __forceinline__ void leaf_scalars(double alpha, double s, double& beta, double& tj, double& vjj) {
+    const double q = fma(alpha, alpha, s);
+    const bool safe = (s > 0.0) && (q > 1e-280) && (q < 1e280);
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(q));
     double g = q * y0, h = 0.5 * y0;
     double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
     r = fma(-g, h, 0.5);
-    g = fma(g, r, g); h = fma(h, r, h);
-    return fma(h, fma(-g, g, q), g);         // one correction step: g + (q - g^2) / (2 g)
-}
-__device__ __forceinline__ double leaf_rcp(double d) {
-    if (!(d > 1e-280 && d < 1e280)) return 1.0 / d;
+    g = fma(g, r, g);                                   // g = sqrt(q)
+    double nrm = g;
+    const double d = fma(fabs(alpha), nrm, q);          // nrm (nrm + |alpha|)
     double z;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(d));
     double e = fma(-d, z, 1.0);
@@ -80,7 +81,15 @@ __device__ __forceinline__ double leaf_rcp(double d) {
     e = fma(-d, z, 1.0);
     z = fma(z, e, z);
     e = fma(-d, z, 1.0);
-    return fma(z, e, z);
+    z = fma(z, e, z);
+    tj = z;
+    if (!safe) {
+        if (s == 0.0) { beta = alpha; tj = 0.0; vjj = 1.0; return; }     // dlarfg: xnorm == 0 -> H = I
+        nrm = sqrt(q);
+        tj = 1.0 / fma(fabs(alpha), nrm, q);
+    }
+    beta = -copysign(nrm, alpha);
+    vjj = alpha - beta;                                 // = sign(alpha) (|alpha| + nrm)
 }
 
 // ---- panel factorisation: the whole TSQR tree of a panel in ONE launch, levels pipelined step by step ----
@@ -170,12 +179,12 @@ __device__ __forceinline__ double leaf_complete(LeafCtx& c, int row) {
 }
 
 // one Householder step; COMP = j & 1 selects which of the thread's two columns can be the pivot column
-template <int COMP>
+template <int COMP, bool LAZY, bool PUB>
 __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], double (&xb)[LEAF_NX], LeafSmem& sm, LeafCtx& c) {
     const int lane = c.lane, wrp = c.wrp, cp = c.cp, hh = c.hh, rg = c.rg;
     const int par = j & 1;
     const int rgj = j & (LEAF_NG - 1), ji = j >> 4;       // pivot row j: row group rgj, head slot ji
-    if (c.lazy) {
+    if (LAZY) {
         // row j+2 (requested during the previous step) goes to the staging buffer; row j+3 is requested now
         if (j + LEAF_D - 1 < QB) sm.stage[(j + LEAF_D - 1) & (LEAF_NSTG - 1)][c.pseg][c.pcol] = leaf_complete(c, j + LEAF_D - 1);
         if (j + LEAF_D < QB) leaf_request(c, j + LEAF_D);
@@ -200,7 +209,7 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
     db += __shfl_xor_sync(0xffffffffu, db, 16);
     if (hh == 0) *reinterpret_cast<double2*>(&sm.red[par][wrp][2 * cp]) = make_double2(da, db);
     __syncthreads();                                   // the only block-wide barrier of the step
-    if (c.lazy && j + 1 < QB && rg == ((j + 1) & (LEAF_NG - 1))) {
+    if (LAZY && j + 1 < QB && rg == ((j + 1) & (LEAF_NG - 1))) {
         // row j+1 of the 8 children moves from the staging buffer into this row group's slots (it is all zero left of
         // column j+1, so the rest of this step leaves it alone, and the publication of column j+1 below includes it)
         const double* st = &sm.stage[(j + 1) & (LEAF_NSTG - 1)][0][2 * cp];
@@ -228,15 +237,7 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
     const double alpha = sm.rowbuf[par][j];
     const double2 rk = *reinterpret_cast<const double2*>(&sm.rowbuf[par][2 * cp]);
     double beta, tj, vjj;
-    if (s_j == 0.0) {          // dlarfg: xnorm == 0 -> H = I
-        beta = alpha; tj = 0.0; vjj = 1.0;
-    } else {
-        const double q = fma(alpha, alpha, s_j);
-        const double nrm = leaf_sqrt(q);
-        beta = -copysign(nrm, alpha);
-        vjj = alpha - beta;                                       // = sign(alpha) (|alpha| + nrm)
-        tj = leaf_rcp(fma(fabs(alpha), nrm, q));                  // 1 / (nrm (nrm + |alpha|)) = -1 / (beta vjj)
-    }
+    leaf_scalars(alpha, s_j, beta, tj, vjj);
     const double wza = fma(vjj, rk.x, sa), wzb = fma(vjj, rk.y, sb);   // v_j' a_k (k > j)  or  v_k' v_j (k < j)
     if (2 * cp + 1 > j) {
         const double cb_ = tj * wzb;
@@ -251,7 +252,7 @@ __device__ __forceinline__ void leaf_step(const int j, double (&xa)[LEAF_NX], do
         }
     }
     if (rg == rgj) {
-        if (c.publish) {        // row j of R is final: hand it to the parent (fire and forget)
+        if (PUB) {        // row j of R is final: hand it to the parent (fire and forget)
             const double ra = ji ? xa[1] : xa[0], rb = ji ? xb[1] : xb[0];
             const unsigned tag = c.base + (unsigned)j + 1u;
             uint4* dst = c.mymail + j * QB;
@@ -301,6 +302,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     const long long blk = (int)blockIdx.x - tp.start[lev];
     const TileMap tm = tp.tm[lev];
     const bool timed = TIMING && blockIdx.x == gridDim.x - 1;
+    if (timed && tid == 32) tbuf[210] = clock64();
 #define LEAF_T(slot) do { if (timed && tid == 32) tbuf[(slot)] = clock64(); } while (0)
 
     LeafCtx c;
@@ -366,13 +368,16 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
 
     // Reflectors are kept UNNORMALISED: v = a_j + sign(alpha) ||a_j|| e_j, H = I - t v v', t = 1 / (||a_j|| (||a_j|| + |alpha|)).
     // One block-wide barrier per step; the owners of column j+1 publish it from inside step j.
-#pragma unroll 1
-    for (int jj = 0; jj < QB / 2; ++jj) {
-        LEAF_T(1 + 2 * jj);
-        leaf_step<0>(2 * jj, xa, xb, sm, c);
-        LEAF_T(2 + 2 * jj);
-        leaf_step<1>(2 * jj + 1, xa, xb, sm, c);
+#define LEAF_LOOP(LZ, PB)                                                   \
+    _Pragma("unroll 1") for (int jj = 0; jj < QB / 2; ++jj) {                \
+        LEAF_T(1 + 2 * jj);                                                  \
+        leaf_step<0, LZ, PB>(2 * jj, xa, xb, sm, c);                         \
+        LEAF_T(2 + 2 * jj);                                                  \
+        leaf_step<1, LZ, PB>(2 * jj + 1, xa, xb, sm, c);                     \
     }
+    if (!c.lazy) { if (c.publish) { LEAF_LOOP(false, true) } else { LEAF_LOOP(false, false) } }
+    else         { if (c.publish) { LEAF_LOOP(true, true) } else { LEAF_LOOP(true, false) } }
+#undef LEAF_LOOP
     __syncthreads();
     LEAF_T(200);
 
@@ -405,6 +410,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
         }
     }
 
+    LEAF_T(202);
     // ---- T = U^{-1},  U = diag(1/t) + striu(V'V)  (U[k][i] = Zs[i][k], k < i).  Recursive blocked inversion of the upper
     //      triangular U:  [U11 U12; 0 U22]^{-1} = [T11, -T11 U12 T22; 0, T22], block size 1, 2, 4, 8, 16. ----
     {
@@ -413,31 +419,37 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
             sm.Tm[r][cc] = (r == cc) ? sm.taus[r] : 0.0;
         }
         __syncthreads();
-        for (int b = 1; b < QB; b <<= 1) {
-            // element (i, jn) of every pair's off-diagonal block: 16 b elements in all
-            const int ne = (QB / 2) * b;
-            const int pr = tid / (b * b), rem = tid - pr * b * b, i = rem / b, jn = rem - i * b;
-            const int r0 = 2 * b * pr;
-            if (tid < ne) {      // W = U12 T22
-                double acc = 0.0;
-                for (int k = 0; k <= jn; ++k) acc = fma(sm.Zs[r0 + b + k][r0 + i], sm.Tm[r0 + b + k][r0 + b + jn], acc);
-                sm.Wm[r0 + i][r0 + b + jn] = acc;
-            }
-            __syncthreads();
-            if (tid < ne) {      // T12 = -T11 W
-                double acc = 0.0;
-                for (int k = i; k < b; ++k) acc = fma(sm.Tm[r0 + i][r0 + k], sm.Wm[r0 + k][r0 + b + jn], acc);
-                sm.Tm[r0 + i][r0 + b + jn] = -acc;
-            }
-            __syncthreads();
+#define LEAF_TINV_LEVEL(B)                                                                                               \
+        {                                                                                                                \
+            /* element (i, jn) of every pair's off-diagonal block: 16 B elements in all */                               \
+            const int pr = tid / ((B) * (B)), rem = tid % ((B) * (B)), i = rem / (B), jn = rem % (B);                    \
+            const int r0 = 2 * (B) * pr;                                                                                 \
+            const bool act = tid < (QB / 2) * (B);                                                                       \
+            if (act) { /* W = U12 T22 */                                                                                 \
+                double acc = 0.0;                                                                                        \
+                _Pragma("unroll") for (int k = 0; k < (B); ++k)                                                          \
+                    acc = fma(sm.Zs[r0 + (B) + k][r0 + i], (k <= jn) ? sm.Tm[r0 + (B) + k][r0 + (B) + jn] : 0.0, acc);   \
+                sm.Wm[r0 + i][r0 + (B) + jn] = acc;                                                                      \
+            }                                                                                                            \
+            __syncthreads();                                                                                             \
+            if (act) { /* T12 = -T11 W */                                                                                \
+                double acc = 0.0;                                                                                        \
+                _Pragma("unroll") for (int k = 0; k < (B); ++k)                                                          \
+                    acc = fma((k >= i) ? sm.Tm[r0 + i][r0 + k] : 0.0, sm.Wm[r0 + k][r0 + (B) + jn], acc);                \
+                sm.Tm[r0 + i][r0 + (B) + jn] = -acc;                                                                     \
+            }                                                                                                            \
+            __syncthreads();                                                                                             \
         }
+        LEAF_TINV_LEVEL(1) LEAF_TINV_LEVEL(2) LEAF_TINV_LEVEL(4) LEAF_TINV_LEVEL(8) LEAF_TINV_LEVEL(16)
+#undef LEAF_TINV_LEVEL
+        LEAF_T(203);
         double* __restrict__ Tb = tp.T[lev] + blk * (long long)(QB * QWS);     // Tb[c * QWS + k] = T[k][c]  (smem image of the update kernels)
         for (int e = tid; e < QB * QB; e += LEAF_THREADS) {
             const int cc = e >> 5, k = e & 31;
             Tb[cc * QWS + k] = sm.Tm[k][cc];
         }
     }
-    if (timed && tid == 0) tbuf[201] = clock64();
+    LEAF_T(201);
 #undef LEAF_T
 }
 
