@@ -198,61 +198,82 @@ __global__ void add_diag_kernel(long long n, double* __restrict__ C, long long l
 
 // ---------------------------------------------------------------------------------------------------
 // blocked right-looking upper Cholesky:  for each 32-column block k:
-//   panel kernel : R11 = chol(C11) (every CTA redundantly, one warp), R12 = R11^{-T} C12 (thread per column)
+//   panel kernel : R11 = chol(C11) and R11^{-1} (every CTA redundantly, one warp, registers), R12 = R11^{-T} C12
 //   update kernel: C22 -= R12' R12 on the upper 64 x 64 tiles
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+#define PP_THREADS 128
+__global__ void __launch_bounds__(PP_THREADS)
 potrf_panel_kernel(int n, double* __restrict__ C, long long ldc, int k0, int* __restrict__ info) {
-    __shared__ double Dm[32][33];
+    // R11 = chol(C11) in registers of warp 0 (lane = column, every CTA redundantly), then its inverse, so that the
+    // row block R12 = R11^{-T} C12 is 32 independent dot products per column instead of a dependent substitution.
+    __shared__ __align__(16) double Rm[32][34];    // Rm[j][c] = R11[j][c]   (row j published at step j)
+    __shared__ __align__(16) double Ri[32][34];    // Ri[i][c] = (R11^{-1})[i][c]
+    __shared__ double invd[32];
     const int tid = threadIdx.x, lane = tid & 31;
     const int w = (n - k0 < 32) ? (n - k0) : 32;
-    for (int e = tid; e < 32 * 32; e += 256) {
-        const int r = e & 31, c = e >> 5;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < w && c < w && r <= c) v = C[(long long)(k0 + c) * ldc + k0 + r];
-        else if (r < w && c < w) v = 0.0;
-        Dm[r][c] = v;
-    }
-    __syncthreads();
     if (tid < 32) {
-        // lane = column c of the block
+        double a[32];
+        {
+            const double* __restrict__ col = C + (long long)(k0 + (lane < w ? lane : 0)) * ldc + k0;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) a[r] = (lane < w && r <= lane) ? col[r] : ((r == lane) ? 1.0 : 0.0);
+        }
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
-            double d = Dm[j][j];
+            double d = __shfl_sync(0xffffffffu, a[j], j);
             if (j < w && !(d > 0.0)) {
                 if (blockIdx.x == 0 && lane == 0) atomicMin(info, k0 + j + 1);
                 d = 1.0;
             }
-            d = sqrt(d);
+            const double rs = rsqrt(d);
+            const double rjc = (lane > j) ? a[j] * rs : ((lane == j) ? d * rs : 0.0);     // R[j][lane]
+            a[j] = rjc;
+            Rm[j][lane] = rjc;
+            if (lane == j) invd[j] = rs;
             __syncwarp();
-            if (lane == j) Dm[j][j] = d;
-            double rjc = 0.0;
-            if (lane > j) { rjc = Dm[j][lane] / d; Dm[j][lane] = rjc; }
-            __syncwarp();
-            if (lane > j) {
-                for (int i = j + 1; i <= lane; ++i) Dm[i][lane] = fma(-Dm[j][i], rjc, Dm[i][lane]);
+#pragma unroll
+            for (int i = j + 1; i < 32; ++i) {
+                const double rji = Rm[j][i];
+                if (i <= lane) a[i] = fma(-rji, rjc, a[i]);
             }
-            __syncwarp();
         }
+        if (blockIdx.x == 0 && lane < w) {
+            double* __restrict__ col = C + (long long)(k0 + lane) * ldc + k0;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (r <= lane) col[r] = a[r];
+        }
+        __syncwarp();
+        // inverse: lane = column c solves R x = e_c by back substitution in AXPY form
+        double x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.0;           // running sums s[i], then the solution
+#pragma unroll
+        for (int i = 31; i >= 0; --i) {
+            const double xi = (i == lane) ? invd[i] : ((i < lane) ? -x[i] * invd[i] : 0.0);
+            x[i] = xi;
+#pragma unroll
+            for (int k = 0; k < i; ++k) x[k] = fma(Rm[k][i], xi, x[k]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Ri[i][lane] = x[i];
     }
     __syncthreads();
-    if (blockIdx.x == 0) {
-        for (int e = tid; e < 32 * 32; e += 256) {
-            const int r = e & 31, c = e >> 5;
-            if (r < w && c < w && r <= c) C[(long long)(k0 + c) * ldc + k0 + r] = Dm[r][c];
-        }
-    }
-    const int c = k0 + w + blockIdx.x * 256 + tid;
+    const int c = k0 + w + blockIdx.x * PP_THREADS + tid;
     if (c < n) {
         double* __restrict__ col = C + (long long)c * ldc + k0;
-        double y[32];
+        double cv[32], y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = (j < w) ? col[j] : 0.0;
+        for (int j = 0; j < 32; ++j) { cv[j] = (j < w) ? col[j] : 0.0; y[j] = 0.0; }
+        // y = R11^{-T} c :  y[j] = sum_{i <= j} Ri[i][j] c[i]
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            double a = y[j];
+        for (int i = 0; i < 32; ++i) {
 #pragma unroll
-            for (int i = 0; i < j; ++i) a = fma(-Dm[i][j], y[i], a);
-            y[j] = a / Dm[j][j];
+            for (int j = i & ~1; j < 32; j += 2) {
+                const double2 r = *reinterpret_cast<const double2*>(&Ri[i][j]);
+                if (j >= i) y[j] = fma(r.x, cv[i], y[j]);
+                y[j + 1] = fma(r.y, cv[i], y[j + 1]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -311,9 +332,18 @@ int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p) {
     p->rhs = p->C + p->ldc * n;
     int64_t ntb = cdiv64(n, SY_TS);
     int64_t pairs = ntb * (ntb + 1) / 2;
-    int64_t ksplit = ctx->num_sms / pairs;
-    if (ksplit < 1) ksplit = 1;
-    if (ksplit > 8) ksplit = 8;
+    // split K so that the launch fills whole waves of SMs (one 128 x 128 tile CTA per SM): the smallest split <= 8
+    // whose last wave is at least 95 % full, else the fullest one  (n = 4000: 528 tile pairs -> 3 slabs, 10.7 / 11 waves)
+    int64_t ksplit = 1;
+    {
+        double best = 0.0;
+        for (int64_t sp = 1; sp <= 8; ++sp) {
+            const double waves = (double)(pairs * sp) / ctx->num_sms;
+            const double eff = waves / (double)cdiv64(pairs * sp, ctx->num_sms);
+            if (eff > best + 1e-9) { best = eff; ksplit = sp; }
+            if (eff >= 0.95) break;
+        }
+    }
     p->part_cap = ksplit > 1 ? ksplit : 0;
     if (p->part_cap) {
         size_t pb = (size_t)p->part_cap * p->ldc * n * sizeof(double);
@@ -379,8 +409,8 @@ int potrf_upper(lso_ctx* ctx, CholPlan* p, int* info_out) {
     for (int k0 = 0; k0 < n; k0 += 32) {
         const int w = (n - k0 < 32) ? (n - k0) : 32;
         const int rest = n - k0 - w;
-        int g = rest > 0 ? (rest + 255) / 256 : 1;
-        potrf_panel_kernel<<<g, 256, 0, ctx->stream>>>(n, p->C, p->ldc, k0, p->d_info);
+        int g = rest > 0 ? (rest + PP_THREADS - 1) / PP_THREADS : 1;
+        potrf_panel_kernel<<<g, PP_THREADS, 0, ctx->stream>>>(n, p->C, p->ldc, k0, p->d_info);
         LSO_CHECK_LAUNCH(ctx);
         if (rest > 0) {
             int nt = (rest + 63) / 64;

@@ -985,20 +985,25 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
         PP_TM(4);
         // ---- Wfin' = -Wsum' T  on the tensor pipe: warp w4 forms columns [8 w4, 8 w4 + 8) for both row fragments ----
         {
-            double ct[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            double ct[2][4][2];                             // 4 accumulators per fragment: dependent chains of 2 DMMAs
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ct[mi][q][0] = ct[mi][q][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const double b = Ts[(8 * w4 + g) * QWS + 4 * ks + t];
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) {
                     const double a = Wsum[(8 * mi + g) * QWS + 4 * ks + t];
-                    dmma(ct[mi][ks & 1], a, b);
+                    dmma(ct[mi][ks & 3], a, b);
                 }
             }
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
                 *reinterpret_cast<double2*>(Wfin + (8 * mi + g) * QWS + 8 * w4 + 2 * t) =
-                    make_double2(-(ct[mi][0][0] + ct[mi][1][0]), -(ct[mi][0][1] + ct[mi][1][1]));
+                    make_double2(-((ct[mi][0][0] + ct[mi][1][0]) + (ct[mi][2][0] + ct[mi][3][0])),
+                                 -((ct[mi][0][1] + ct[mi][1][1]) + (ct[mi][2][1] + ct[mi][3][1])));
         }
         PP_TM(5);
         group_sync(grp);
