@@ -1057,16 +1057,20 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
 }
 
 // =================================================================================================
-// upper-triangular solve (single CTA; n is at most a few thousand on this path)
+// upper-triangular solve (single CTA; n is at most a few thousand on this path).  Left-looking by 32 x 32 diagonal
+// blocks: the already-solved part is folded into the block's right-hand side by all 32 warps with coalesced loads
+// (TRANS = 0: lanes = the block's 32 rows, warps stride over the solved columns; TRANS = 1: warp = one column of the
+// block, lanes stride over the solved rows), then warp 0 solves the diagonal block with shuffles.
 // =================================================================================================
 #define TRI_THREADS 1024
 template <int TRANS>
 __global__ void __launch_bounds__(TRI_THREADS, 1)
 tri_solve_kernel(int n, const double* __restrict__ R, long long ld, const double* c, double* xout) {
     extern __shared__ double tsm[];
-    double* xs = tsm;             // [n]
-    double* D = tsm + n;          // [32][33] diagonal block
-    const int tid = threadIdx.x, lane = tid & 31;
+    double* xs = tsm;                 // [n] right-hand side, overwritten by the solution
+    double* D = tsm + n;              // [32][33] diagonal block
+    double* red = D + 32 * 33;        // [32][33] partial sums
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     for (int i = tid; i < n; i += TRI_THREADS) xs[i] = c[i];
     const int nb = (n + 31) / 32;
     for (int bi = 0; bi < nb; ++bi) {
@@ -1076,40 +1080,63 @@ tri_solve_kernel(int n, const double* __restrict__ R, long long ld, const double
         __syncthreads();
         {   // diagonal block into smem: D[r*33 + cc] = R[j0+r][j0+cc]
             const int r = tid & 31, cc = tid >> 5;
-            if (r < w && cc < w) D[r * 33 + cc] = R[(long long)(j0 + cc) * ld + j0 + r];
+            D[r * 33 + cc] = (r < w && cc < w) ? R[(long long)(j0 + cc) * ld + j0 + r] : ((r == cc) ? 1.0 : 0.0);
+        }
+        double acc = 0.0;
+        if (!TRANS) {
+            // s_i = sum_{k >= j0 + 32} R[i][k] x[k],  i = j0 + lane ; warp strides over k
+            if (lane < w) {
+                const double* __restrict__ p = R + j0 + lane;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int k = j0 + 32 + wrp;
+                for (; k + 96 < n; k += 128) {
+                    a0 = fma(p[(long long)k * ld], xs[k], a0);
+                    a1 = fma(p[(long long)(k + 32) * ld], xs[k + 32], a1);
+                    a2 = fma(p[(long long)(k + 64) * ld], xs[k + 64], a2);
+                    a3 = fma(p[(long long)(k + 96) * ld], xs[k + 96], a3);
+                }
+                for (; k < n; k += 32) a0 = fma(p[(long long)k * ld], xs[k], a0);
+                acc = (a0 + a1) + (a2 + a3);
+            }
+            red[wrp * 33 + lane] = acc;
+        } else {
+            // s_j = sum_{i < j0} R[i][j] z[i],  j = j0 + wrp ; lanes stride over i
+            if (wrp < w) {
+                const double* __restrict__ p = R + (long long)(j0 + wrp) * ld;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int i = lane;
+                for (; i + 96 < j0; i += 128) {
+                    a0 = fma(p[i], xs[i], a0);
+                    a1 = fma(p[i + 32], xs[i + 32], a1);
+                    a2 = fma(p[i + 64], xs[i + 64], a2);
+                    a3 = fma(p[i + 96], xs[i + 96], a3);
+                }
+                for (; i < j0; i += 32) a0 = fma(p[i], xs[i], a0);
+                acc = (a0 + a1) + (a2 + a3);
+            }
+            red[lane * 33 + wrp] = acc;      // red[part][entry]: the same layout as TRANS = 0
         }
         __syncthreads();
         if (tid < 32) {
-            double xi = (lane < w) ? xs[j0 + lane] : 0.0;
+            double s = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) s += red[q * 33 + lane];
+            double xi = (lane < w) ? xs[j0 + lane] - s : 0.0;
+            const double inv = 1.0 / D[lane * 33 + lane];
             if (!TRANS) {
                 for (int jj = w - 1; jj >= 0; --jj) {
-                    double xj = __shfl_sync(0xffffffffu, xi, jj) / D[jj * 33 + jj];
+                    const double xj = __shfl_sync(0xffffffffu, xi, jj) * __shfl_sync(0xffffffffu, inv, jj);
                     if (lane == jj) xi = xj;
                     else if (lane < jj) xi = fma(-D[lane * 33 + jj], xj, xi);
                 }
             } else {   // R' is lower triangular: L[i][j] = R[j][i]
                 for (int jj = 0; jj < w; ++jj) {
-                    double xj = __shfl_sync(0xffffffffu, xi, jj) / D[jj * 33 + jj];
+                    const double xj = __shfl_sync(0xffffffffu, xi, jj) * __shfl_sync(0xffffffffu, inv, jj);
                     if (lane == jj) xi = xj;
                     else if (lane > jj && lane < w) xi = fma(-D[jj * 33 + lane], xj, xi);
                 }
             }
             if (lane < w) xs[j0 + lane] = xi;
-        }
-        __syncthreads();
-        if (!TRANS) {
-            for (int i = tid; i < j0; i += TRI_THREADS) {
-                double acc = xs[i];
-                for (int jj = 0; jj < w; ++jj) acc = fma(-R[(long long)(j0 + jj) * ld + i], xs[j0 + jj], acc);
-                xs[i] = acc;
-            }
-        } else {
-            for (int i = j0 + w + tid; i < n; i += TRI_THREADS) {
-                double acc = xs[i];
-                const double* __restrict__ col = R + (long long)i * ld + j0;
-                for (int jj = 0; jj < w; ++jj) acc = fma(-col[jj], xs[j0 + jj], acc);
-                xs[i] = acc;
-            }
         }
     }
     __syncthreads();
@@ -1119,7 +1146,7 @@ tri_solve_kernel(int n, const double* __restrict__ R, long long ld, const double
 int tri_solve(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, const double* d_c, double* d_x, int trans) {
     if (n == 0) return LSO_OK;
     LSO_REQUIRE(ctx, n <= 24000, "triangular solve: n too large for the single-CTA kernel");
-    size_t smem = (size_t)(n + 32 * 33) * 8;
+    size_t smem = (size_t)(n + 2 * 32 * 33) * 8;
     static bool attr_done = false;
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(tri_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
