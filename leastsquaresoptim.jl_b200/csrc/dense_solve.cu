@@ -241,25 +241,26 @@ __global__ void pack_R_kernel(long long n, const double* __restrict__ A, long lo
     }
 }
 
-// stack: rows [k*n, (k+1)*n) = R_k ; rows [P*n, P*n + n) = diag(sqrt(damp)); rhs column = [c_0; ...; c_{P-1}; 0]
-__global__ void stack_assemble_kernel(long long n, int P, const double* __restrict__ gathered,
+// stack of the P upper-triangular R_k (and diag(sqrt(damp)) as one more triangle when damping is present), rows
+// INTERLEAVED: stack row Q*r + i = row r of triangle i  (Q = P or P + 1).  Stack row rho then has no entry left of
+// column floor(rho / Q), so panel j of the factorisation only involves the rows below Q*32*(j+1) (QRPlan::band):
+// the replicated QR of the stack costs half of a dense one.  rhs column = the c_k interleaved the same way.
+__global__ void stack_assemble_kernel(long long n, int P, int Q, const double* __restrict__ gathered,
                                       const double* __restrict__ damp, double* __restrict__ A, long long ld,
                                       long long Npad) {
     const long long col = blockIdx.y;
     double* __restrict__ dst = A + col * ld;
-    const long long rowsR = (long long)P * n;
-    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < ld; r += (long long)gridDim.x * blockDim.x) {
+    const long long rows = (long long)Q * n;
+    for (long long rho = blockIdx.x * (long long)blockDim.x + threadIdx.x; rho < ld; rho += (long long)gridDim.x * blockDim.x) {
         double v = 0.0;
-        if (col < n || col == Npad) {
+        if ((col < n || col == Npad) && rho < rows) {
+            const long long r = rho / Q;
+            const int i = (int)(rho - r * Q);
             const long long scol = (col < n) ? col : n;
-            if (r < rowsR) {
-                const long long k = r / n, rr = r - k * n;
-                v = gathered[k * n * (n + 1) + scol * n + rr];
-            } else if (col < n && damp != nullptr && r == rowsR + col) {
-                v = sqrt(damp[col]);
-            }
+            if (i < P) v = gathered[(long long)i * n * (n + 1) + scol * n + r];
+            else if (col < n && r == col) v = sqrt(damp[col]);
         }
-        dst[r] = v;
+        dst[rho] = v;
     }
 }
 
@@ -292,8 +293,11 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     {
         QRPlan* ps = &ws->plan_stack;
         dim3 grid((unsigned)std::min<int64_t>(cdiv64(ps->ld, 256), 64), (unsigned)ps->Nc);
-        stack_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(n, P, ws->d_gather, d_damp, ps->A, ps->ld, ps->Npad);
+        const int Q = d_damp ? P + 1 : P;
+        stack_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(n, P, Q, ws->d_gather, d_damp, ps->A, ps->ld, ps->Npad);
         LSO_CHECK_LAUNCH(ctx);
+        ps->M = (int64_t)Q * n;       // rows in use (the workspace was sized for P + 1 triangles)
+        ps->band = Q;
         LSO_TRY(qr_factor(ctx, ps));
     }
     return qr_finish(ws, &ws->plan_stack, d_x, rank_out);

@@ -1285,6 +1285,7 @@ struct PanelLevels {
 static void panel_levels(const QRPlan* plan, int64_t c0, PanelLevels& pl) {
     int L = 0;
     int64_t rows = roundup64(plan->M, QB) - c0;
+    if (plan->band > 0) rows = std::min<int64_t>(rows, plan->band * (c0 + QB) - c0);   // the rest is zero in these columns
     for (;;) {
         const int64_t nb = cdiv64(rows, QH);
         pl.nblk[L] = nb;

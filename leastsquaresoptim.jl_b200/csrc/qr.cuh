@@ -32,6 +32,8 @@ struct QRPlan {
     int64_t Npad = 0;    // N rounded up to QB (extra columns are zero => identity reflectors)
     int64_t Nc = 0;      // total columns incl. right-hand-side tile: Npad + QCT
     int64_t ld = 0;      // leading dimension: roundup(M, QB) + QH zero rows of padding
+    int64_t band = 0;    // > 0: row rho has no entry left of column rho / band (interleaved stack of triangles), so
+                         // panel j only involves the rows above band * QB * (j + 1); 0 = dense
     double* A = nullptr; // ld x Nc, column-major
     int nlevels = 0;
     uint4* mail = nullptr;      // mailbox of the fused panel-tree kernel: [block][row][column] {lo32, tag, hi32, tag}
