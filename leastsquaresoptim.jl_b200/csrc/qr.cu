@@ -795,12 +795,11 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
 //   consumer warp w of a group owns tile rows [64w, 64w+64): its K-slice of W' = X'V (GEMM1) and its output rows of
 //                   X' += Wfin' V' (GEMM2).  A warp only ever touches its own row slice of the staged tile.
 // =================================================================================================
-#define PP_NST 3
+#define PP_NST 4
 #define PP_GW 4                                     /* warps per consumer group */
 #define PP_T_BYTES (QB * QWS * 8)
-#define PP_WP_BYTES (PP_GW * QCT * QWP * 8)         /* per group; Wfin aliases its head */
 #define PP_WS_BYTES (QCT * QWS * 8)
-#define PP_SMEM_BYTES (AM_VS_BYTES + PP_T_BYTES + PP_NST * AM_XS_BYTES + 2 * PP_WP_BYTES + 2 * PP_WS_BYTES + 128)
+#define PP_SMEM_BYTES (AM_VS_BYTES + PP_T_BYTES + PP_NST * AM_XS_BYTES + 4 * PP_WS_BYTES + 128)
 
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
@@ -818,7 +817,7 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     double* Ts = (double*)(ppsm + AM_VS_BYTES);                            // Ts[i*QWS + k] = T[k][i]  (contiguous after Vs)
     double* Xs = (double*)(ppsm + AM_VS_BYTES + PP_T_BYTES);               // [PP_NST][QCT][QS]
     unsigned char* wbase = ppsm + AM_VS_BYTES + PP_T_BYTES + PP_NST * AM_XS_BYTES;
-    uint64_t* bars = (uint64_t*)(wbase + 2 * PP_WP_BYTES + 2 * PP_WS_BYTES);
+    uint64_t* bars = (uint64_t*)(wbase + 4 * PP_WS_BYTES);
     const uint32_t bar_full = smem_u32(bars), bar_out = smem_u32(bars + PP_NST), bar_v = smem_u32(bars + 2 * PP_NST),
                    bar_vfree = smem_u32(bars + 2 * PP_NST + 1);
 
@@ -908,9 +907,8 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     const int grp = wrp >> 2, w4 = wrp & 3;
     const int gtid = tid & 127;
     const int g = lane >> 2, t = lane & 3;
-    double* Wp = (double*)(wbase + grp * PP_WP_BYTES);          // [PP_GW][QCT][QWP] partial (V'X)' per warp
-    double* Wfin = Wp;                                          // [QCT][QWS]  -(T'V'X)', aliases the partials
-    double* Wsum = (double*)(wbase + 2 * PP_WP_BYTES + grp * PP_WS_BYTES);   // [QCT][QWS]
+    double* Wsum = (double*)(wbase + (2 * grp) * PP_WS_BYTES);          // [QCT][QWS]  (V'X)'
+    double* Wfin = (double*)(wbase + (2 * grp + 1) * PP_WS_BYTES);      // [QCT][QWS]  -(T'V'X)'
     long long blk = blk0;
     int tile = tile0;
     long long cur_blk = -1;
@@ -931,6 +929,17 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
         PP_TM(0);
         double* Xst = Xs + s * QCT * QS;
 
+        // this warp's rows of the staged tile become the GEMM2 accumulators now: after GEMM1 nobody reads the slice any
+        // more, so the split-K partials of GEMM1 are parked in it (no separate partial buffers -> a 4th stage fits)
+        double c2[2][8][2];
+        const int rbase = 64 * w4 + 2 * t;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
+                c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
+            }
         // ---- GEMM1 (transposed): partial (V'X)'_w = X[64w:64w+64, :]' V[64w:64w+64, :]   (QCT x QB) ----
         {
             double c1[2][4][2];
@@ -951,12 +960,13 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma(c1[mi][ni], a[mi], b[ni]);
             }
-            double* wp = Wp + w4 * QCT * QWP;
+            __syncwarp();       // every lane has finished reading the warp's slice
+            // partial element (column c = 8 mi + g, reflector k = 8 ni + 2 t) -> Xst[c][64 w + k]
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
-                    *reinterpret_cast<double2*>(wp + (8 * mi + g) * QWP + 8 * ni + 2 * t) =
+                    *reinterpret_cast<double2*>(Xst + (8 * mi + g) * QS + 64 * w4 + 8 * ni + 2 * t) =
                         make_double2(c1[mi][ni][0], c1[mi][ni][1]);
         }
         PP_TM(1);
@@ -965,12 +975,12 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
         // ---- reduce the 4 partials: Wsum[c][k] = (V'X)[k][c] ----
         {
             const int c = gtid >> 3, k4 = (gtid & 7) * 4;
-            const double* w0 = Wp + c * QWP + k4;
+            const double* w0 = Xst + c * QS + k4;
             double2 p[PP_GW][2];
 #pragma unroll
             for (int w = 0; w < PP_GW; ++w) {
-                p[w][0] = *reinterpret_cast<const double2*>(w0 + w * QCT * QWP);
-                p[w][1] = *reinterpret_cast<const double2*>(w0 + w * QCT * QWP + 2);
+                p[w][0] = *reinterpret_cast<const double2*>(w0 + 64 * w);
+                p[w][1] = *reinterpret_cast<const double2*>(w0 + 64 * w + 2);
             }
             double2 r0, r1;
             r0.x = (p[0][0].x + p[1][0].x) + (p[2][0].x + p[3][0].x);
@@ -1010,15 +1020,6 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
         PP_TM(6);
         // ---- GEMM2 (transposed): X[64w:64w+64, :]' += Wfin' V[64w:64w+64, :]' ; written back into the stage ----
         {
-            double c2[2][8][2];
-            const int rbase = 64 * w4 + 2 * t;
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 8; ++ni) {
-                    const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
-                    c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
-                }
             PP_TM(7);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -1356,8 +1357,6 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
             int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
             if (mark) lso_prof_mark(ctx);
             if (ctx->opt_qr_apply == 2) {
-                // two jobs per CTA keep both consumer groups busy when there are fewer jobs than 2 x SMs
-                if (jtot < 2 * (int64_t)ctx->num_sms) grid = (int)((jtot + 1) / 2);
                 if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
                     qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
                                                                               plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
