@@ -128,6 +128,8 @@ struct TreeParams {
     double* T[QR_MAX_LEVELS];
     uint4* mail;                      // mailbox: [block][row][column] {lo32, tag, hi32, tag}
     unsigned base;                    // tag of row r in this launch = base + r + 1
+    int* zero_ptr;                    // child counters of the fused trailing update that follows: zeroed here
+    int zero_n;
 };
 
 struct LeafSmem {
@@ -303,6 +305,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     const TileMap tm = tp.tm[lev];
     const bool timed = TIMING && blockIdx.x == gridDim.x - 1;
     if (timed && tid == 32) tbuf[210] = clock64();
+    for (int i = blockIdx.x * LEAF_THREADS + tid; i < tp.zero_n; i += gridDim.x * LEAF_THREADS) tp.zero_ptr[i] = 0;
 #define LEAF_T(slot) do { if (timed && tid == 32) tbuf[(slot)] = clock64(); } while (0)
 
     LeafCtx c;
@@ -803,10 +806,58 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
 
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
+// One launch can cover ONE tree level or ALL of them ("fused"): the job list of a CTA is then its slice of level 0,
+// followed by its slice of level 1, ...  A job of level l > 0 (block b, tile t) needs the head rows that its up to
+// 8 children at level l-1 wrote for tile t; the producer warp counts finished children per (parent block, tile) in
+// global memory (children are published once their bulk stores have COMPLETED) and waits on that counter before it
+// loads the tile.  Every CTA finishes its jobs of one level before touching the next, so the waits cannot cycle
+// (all CTAs are resident: grid <= number of SMs, one CTA per SM).
+struct ApplyLevels {
+    int nlev;
+    TileMap tm[QR_MAX_LEVELS];
+    const double* V[QR_MAX_LEVELS];
+    const double* T[QR_MAX_LEVELS];
+    int* cnt[QR_MAX_LEVELS];          // level l >= 1: [nb_l * ntiles] finished-children counters (zero at launch)
+};
+
+// walks the job list of one CTA: level-major, block-major within a level
+struct JobWalk {
+    int lev, tile, left;              // left = jobs remaining in the current level, including the current one
+    long long blk;
+};
+__device__ __forceinline__ void jw_enter_level(JobWalk& w, const ApplyLevels& L, int ntiles) {
+    // skip levels in which this CTA has no job
+    for (; w.lev < L.nlev; ++w.lev) {
+        const long long jtot = L.tm[w.lev].nb * ntiles;
+        const long long qb = (jtot * blockIdx.x) / gridDim.x, qe = (jtot * (blockIdx.x + 1)) / gridDim.x;
+        if (qe > qb) {
+            w.left = (int)(qe - qb);
+            w.blk = qb / ntiles;
+            w.tile = (int)(qb - w.blk * ntiles);
+            return;
+        }
+    }
+    w.left = 0;
+}
+__device__ __forceinline__ void jw_next(JobWalk& w, const ApplyLevels& L, int ntiles) {
+    if (--w.left > 0) {
+        if (++w.tile == ntiles) { w.tile = 0; ++w.blk; }
+    } else {
+        ++w.lev;
+        jw_enter_level(w, L, ntiles);
+    }
+}
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+
 template <bool ATIMING>
 __global__ void __launch_bounds__(288, 1)
-qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int ntiles, long long nblocks,
-                     TileMap tm, const double* __restrict__ V, const double* __restrict__ T, long long* __restrict__ tbuf) {
+qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int ntiles, ApplyLevels L,
+                     long long* __restrict__ tbuf) {
     long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = 0;
     const long long tstart = ATIMING ? clock64() : 0;
@@ -822,10 +873,11 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
                    bar_vfree = smem_u32(bars + 2 * PP_NST + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const long long jtot = nblocks * ntiles;
-    const long long q_begin = (jtot * blockIdx.x) / gridDim.x;
-    const long long q_end = (jtot * (blockIdx.x + 1)) / gridDim.x;
-    const int njobs = (int)(q_end - q_begin);
+    int njobs = 0;
+    for (int l = 0; l < L.nlev; ++l) {
+        const long long jtot = L.tm[l].nb * ntiles;
+        njobs += (int)((jtot * (blockIdx.x + 1)) / gridDim.x - (jtot * blockIdx.x) / gridDim.x);
+    }
 
     if (tid == 0) {
         for (int s = 0; s < PP_NST; ++s) {
@@ -840,43 +892,105 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     __syncthreads();
     if (njobs <= 0) return;
 
-    const long long blk0 = q_begin / ntiles;
-    const int tile0 = (int)(q_begin - blk0 * ntiles);
+    JobWalk jw;
+    jw.lev = 0; jw.tile = 0; jw.left = 0; jw.blk = 0;
+    jw_enter_level(jw, L, ntiles);
 
     if (wrp == 8) {
         // =========================== producer warp: all global traffic, via the TMA unit ===========================
-        long long blk = blk0;
-        int tile = tile0;
         int seg_i = -1;
+        int cur_lev = -1;
         long long cur_blk = -1;
         long long hist_blk[PP_NST];
-        int hist_tile[PP_NST];
+        int hist_tile[PP_NST], hist_lev[PP_NST], hist_left[PP_NST];
+        int next_store = 0;                     // jobs [0, next_store) of this CTA have had their stores issued
+        // jobs whose stores have been issued but which have not been published to their parent yet (published in
+        // batches: one completion wait + one release per batch keeps the fence off the per-tile path)
+        int pq_lev[8], pq_tile[8], npq = 0;
+        long long pq_blk[8];
         const int pcol = lane & (QCT - 1), pseg = lane >> 4;      // 2 copies per column: head, body
-        for (int u = 0; u < njobs + PP_NST; ++u) {
-            const int s = u % PP_NST;
-            if (u >= PP_NST) {
-                // stage s holds the finished tile of job u - PP_NST: store it, and wait until the copy engine has read it
-                mbar_wait(bar_out + 8 * s, (uint32_t)(((u / PP_NST) - 1) & 1));
-                const long long sb = hist_blk[s];
-                const long long cbase = ctrail + (long long)hist_tile[s] * QCT;
-                const uint32_t xs = smem_u32(Xs + s * QCT * QS);
-                const int snv = tm_body_rows(tm, sb);
-                double* colp = A + (cbase + pcol) * ld + tm.r0;
-                if (pseg == 0) bulk_s2g(colp + QB * sb, xs + (uint32_t)(pcol * QS) * 8u, QB * 8u);
-                else if (snv > 0) bulk_s2g(colp + QB * tm.nb + QBODY * sb, xs + (uint32_t)(pcol * QS + QB) * 8u, (uint32_t)snv * 8u);
-                bulk_commit();
-                if (u < njobs) bulk_wait_read0();
+        const bool chained = L.nlev > 1;
+
+        // tell the parent blocks that the first `cnt` queued jobs have written their head rows (their bulk stores have
+        // completed in every lane: bulk groups are per thread)
+        auto publish = [&](int cnt) {
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                for (int q = 0; q < cnt; ++q) {
+                    if (pq_lev[q] + 1 < L.nlev) {
+                        const long long nbp = L.tm[pq_lev[q] + 1].nb;
+                        const long long pb = (pq_blk[q] < nbp) ? pq_blk[q] : (pq_blk[q] - nbp) / (QG - 1);
+                        atomicAdd(L.cnt[pq_lev[q] + 1] + pb * ntiles + pq_tile[q], 1);
+                    }
+                }
             }
-            if (u >= njobs) continue;
-            if (blk != cur_blk) {
+            for (int q = cnt; q < npq; ++q) { pq_lev[q - cnt] = pq_lev[q]; pq_tile[q - cnt] = pq_tile[q]; pq_blk[q - cnt] = pq_blk[q]; }
+            npq -= cnt;
+        };
+        // issue the stores of the oldest unstored job (its stage holds the finished tile once bar_out completes)
+        auto store_next = [&]() {
+            const int j = next_store, s = j % PP_NST;
+            mbar_wait(bar_out + 8 * s, (uint32_t)((j / PP_NST) & 1));
+            const long long sb = hist_blk[s];
+            const TileMap& stm = L.tm[hist_lev[s]];
+            const long long cbase = ctrail + (long long)hist_tile[s] * QCT;
+            const uint32_t xs = smem_u32(Xs + s * QCT * QS);
+            const int snv = tm_body_rows(stm, sb);
+            double* colp = A + (cbase + pcol) * ld + stm.r0;
+            if (pseg == 0) bulk_s2g(colp + QB * sb, xs + (uint32_t)(pcol * QS) * 8u, QB * 8u);
+            else if (snv > 0) bulk_s2g(colp + QB * stm.nb + QBODY * sb, xs + (uint32_t)(pcol * QS + QB) * 8u, (uint32_t)snv * 8u);
+            bulk_commit();
+            if (chained) {
+                // everything but the group committed just now is complete after wait_group 1.  Level-0 jobs far from the
+                // end of the CTA's list are published lazily (8 at a time); upper-level jobs and the last jobs of a level,
+                // which some parent is about to wait for, one store step after their own
+                const bool urgent = hist_lev[s] > 0 || hist_left[s] <= 8;
+                if (npq > 0 && (urgent || npq == 8)) { bulk_wait1(); publish(npq); }
+                pq_lev[npq] = hist_lev[s]; pq_tile[npq] = hist_tile[s]; pq_blk[npq] = sb; ++npq;
+            }
+            ++next_store;
+        };
+
+        for (int u = 0; u < njobs; ++u) {
+            const int s = u % PP_NST;
+            if (next_store <= u - PP_NST) {      // the stage must have been stored and read by the copy engine
+                while (next_store <= u - PP_NST) store_next();
+                bulk_wait_read0();
+            }
+            const TileMap& tm = L.tm[jw.lev];
+            const long long blk = jw.blk;
+            const int tile = jw.tile;
+            if (ATIMING && lane == 0 && jw.lev != cur_lev) {
+                if (blockIdx.x == gridDim.x / 2) tbuf[16 + jw.lev] = gtimer_ns() - tstart_ns;
+                atomicMax((unsigned long long*)&tbuf[26 + jw.lev], (unsigned long long)gtimer_ns());      // slowest CTA to enter the level
+                if (jw.lev == 0) atomicMin((unsigned long long*)&tbuf[24], (unsigned long long)gtimer_ns());
+            }
+            if (jw.lev != cur_lev || blk != cur_blk) {
                 if (seg_i >= 0) mbar_wait(bar_vfree, (uint32_t)(seg_i & 1));   // both groups are done with the old V
+                cur_lev = jw.lev;
                 cur_blk = blk;
                 ++seg_i;
                 if (lane == 0) {
                     mbar_expect_tx(bar_v, AM_VS_BYTES + PP_T_BYTES);
-                    bulk_g2s(smem_u32(Vs), V + blk * (long long)(QB * QS), AM_VS_BYTES, bar_v);
-                    bulk_g2s(smem_u32(Ts), T + blk * (long long)(QB * QWS), PP_T_BYTES, bar_v);
+                    bulk_g2s(smem_u32(Vs), L.V[jw.lev] + blk * (long long)(QB * QS), AM_VS_BYTES, bar_v);
+                    bulk_g2s(smem_u32(Ts), L.T[jw.lev] + blk * (long long)(QB * QWS), PP_T_BYTES, bar_v);
                 }
+            }
+            if (chained && jw.lev > 0) {
+                // wait until every child of this block has written its head rows of this tile
+                const long long nbc = L.tm[jw.lev - 1].nb;
+                long long nch = nbc - tm.nb - (QG - 1) * blk;
+                nch = 1 + (nch < 0 ? 0 : (nch > QG - 1 ? QG - 1 : nch));
+                const int* cp = L.cnt[jw.lev] + blk * ntiles + tile;
+                if (ld_acquire_s32(cp) < (int)nch) {
+                    // before spinning, hand over everything this CTA still owes (a child may be one of its own last jobs)
+                    while (next_store < u) store_next();
+                    bulk_wait0();
+                    publish(npq);
+                    while (ld_acquire_s32(cp) < (int)nch) __nanosleep(100);
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy acquire -> async-proxy loads below
             }
             double* xst = Xs + s * QCT * QS;
             const int nv = tm_body_rows(tm, blk);
@@ -897,9 +1011,17 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
             }
             hist_blk[s] = blk;
             hist_tile[s] = tile;
-            if (++tile == ntiles) { tile = 0; ++blk; }
+            hist_lev[s] = jw.lev;
+            hist_left[s] = jw.left;
+            jw_next(jw, L, ntiles);
         }
+        while (next_store < njobs) store_next();
         bulk_wait0();      // all stores have completed (not just been read) before the CTA retires
+        if (chained) publish(npq);
+        if (ATIMING && lane == 0) {
+            if (blockIdx.x == gridDim.x / 2) tbuf[16 + L.nlev] = gtimer_ns() - tstart_ns;
+            atomicMax((unsigned long long*)&tbuf[25], (unsigned long long)gtimer_ns());
+        }
         return;
     }
 
@@ -909,15 +1031,14 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     const int g = lane >> 2, t = lane & 3;
     double* Wsum = (double*)(wbase + (2 * grp) * PP_WS_BYTES);          // [QCT][QWS]  (V'X)'
     double* Wfin = (double*)(wbase + (2 * grp + 1) * PP_WS_BYTES);      // [QCT][QWS]  -(T'V'X)'
-    long long blk = blk0;
-    int tile = tile0;
     long long cur_blk = -1;
+    int cur_lev = -1;
     int seg_i = -1;
     bool need_v = false;
     for (int u = 0; u < njobs; ++u) {
-        if (blk != cur_blk) { cur_blk = blk; ++seg_i; need_v = true; }
-        const bool last_of_seg = (u + 1 == njobs) || (tile + 1 == ntiles);
-        if (++tile == ntiles) { tile = 0; ++blk; }
+        if (jw.lev != cur_lev || jw.blk != cur_blk) { cur_lev = jw.lev; cur_blk = jw.blk; ++seg_i; need_v = true; }
+        const bool last_of_seg = (jw.left == 1) || (jw.tile + 1 == ntiles);     // the next job has another V
+        jw_next(jw, L, ntiles);
         if ((u & 1) != grp) {
             if (last_of_seg) mbar_arrive(bar_vfree);     // this thread's jobs of the segment are all behind it
             continue;
@@ -1205,6 +1326,10 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaMalloc(&plan->mail, (size_t)tot * QB * QB * sizeof(uint4)));
         LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->mail, 0, (size_t)tot * QB * QB * sizeof(uint4), ctx->stream));
         plan->prog_base = 0;
+        int64_t upper = 0;
+        for (int l = 1; l < L; ++l) upper += plan->lev[l].nblocks;
+        const size_t cb = (size_t)(upper > 0 ? upper : 1) * (size_t)(plan->Nc / QCT) * sizeof(int);
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&plan->apply_cnt, cb));
     }
     {   // the panel stream gets the highest priority: its (small, latency-bound) kernels must be placed as soon as
         // they are ready, underneath / ahead of the bulk trailing update
@@ -1246,6 +1371,7 @@ void qr_plan_destroy(QRPlan* plan) {
     for (cudaEvent_t ev : plan->ev_next) cudaEventDestroy(ev);
     cudaFree(plan->A);
     cudaFree(plan->mail);
+    cudaFree(plan->apply_cnt);
     for (int l = 0; l < plan->nlevels; ++l)
         for (int b = 0; b < 2; ++b) {
             cudaFree(plan->lev[l].V[b]);
@@ -1257,12 +1383,14 @@ void qr_plan_destroy(QRPlan* plan) {
 static long long* g_apply_tbuf = nullptr;    // debug: per-phase clock64 sums of CTA 0 / warp 0 of the first level-0 update
 extern "C" int lso_debug_apply_timing(lso_ctx* ctx, long long* h_out /* 16 */) {
     if (!g_apply_tbuf) {
-        LSO_CHECK_CUDA(ctx, cudaMalloc(&g_apply_tbuf, 16 * sizeof(long long)));
-        LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf, 0, 16 * sizeof(long long)));
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&g_apply_tbuf, 32 * sizeof(long long)));
+        LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf, 0, 32 * sizeof(long long)));
         return LSO_OK;
     }
     LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    LSO_CHECK_CUDA(ctx, cudaMemcpy(h_out, g_apply_tbuf, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    LSO_CHECK_CUDA(ctx, cudaMemcpy(h_out, g_apply_tbuf, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf, 0, 32 * sizeof(long long)));      // re-arm
+    LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf + 24, 0xff, sizeof(long long)));
     return LSO_OK;
 }
 static long long* g_leaf_tbuf = nullptr;     // debug: per-phase clock64 stamps of the single-block leaf (LSO_LEAF_TIMING)
@@ -1310,7 +1438,8 @@ static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id)
     cudaEventRecord(e, st);
     g_tl.push_back({e, what, k, stream_id});
 }
-static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st) {
+static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st,
+                             int ntiles_fused = 0) {
     TreeParams tp;
     tp.nlev = pl.L;
     int total = 0;
@@ -1331,11 +1460,40 @@ static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const Panel
     }
     plan->prog_base += 64;            // counters of earlier launches are all below the new base
     tp.base = plan->prog_base;
+    tp.zero_ptr = plan->apply_cnt;
+    tp.zero_n = 0;
+    for (int l = 1; l < pl.L; ++l) tp.zero_n += (int)pl.nblk[l] * ntiles_fused;
     if (g_leaf_tbuf && pl.nblk[0] <= 64)
         qr_tree_kernel_t<true><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);
     else
         qr_tree_kernel_t<false><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, nullptr);
     LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}
+
+// all tree levels of the panel's update in ONE launch (levels chained through per-tile child counters)
+static int launch_apply_fused(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int buf, int64_t cfirst, int ntiles, cudaStream_t st) {
+    if (ntiles <= 0) return LSO_OK;
+    ApplyLevels L;
+    L.nlev = pl.L;
+    size_t off = 0;
+    for (int l = 0; l < pl.L; ++l) {
+        L.tm[l] = pl.tm[l];
+        L.V[l] = plan->lev[l].V[buf];
+        L.T[l] = plan->lev[l].T[buf];
+        L.cnt[l] = (l == 0) ? nullptr : plan->apply_cnt + off;
+        if (l > 0) off += (size_t)pl.nblk[l] * ntiles;
+    }
+    const int64_t jtot = pl.nblk[0] * ntiles;
+    const int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
+    lso_prof_mark(ctx);
+    if (g_apply_tbuf && cfirst == 2 * QB)
+        qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, g_apply_tbuf);
+    else
+        qr_apply_pp_kernel_t<false><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
+    lso_prof_mark(ctx);
+    LSO_CHECK_LAUNCH(ctx);
+    tl_mark(st, "apply (all levels) end", cfirst / QB - 1, 0);
     return LSO_OK;
 }
 
@@ -1356,13 +1514,17 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
             int64_t jtot = pl.nblk[l] * ntiles;
             int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
             if (mark) lso_prof_mark(ctx);
-            if (ctx->opt_qr_apply == 2) {
-                if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
-                    qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
-                                                                              plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
+            if (ctx->opt_qr_apply >= 2) {
+                ApplyLevels L;
+                L.nlev = 1;
+                L.tm[0] = pl.tm[l];
+                L.V[0] = plan->lev[l].V[buf];
+                L.T[0] = plan->lev[l].T[buf];
+                L.cnt[0] = nullptr;
+                if (g_apply_tbuf && l == 0 && cfirst == 2 * QB)
+                    qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, g_apply_tbuf);
                 else
-                    qr_apply_pp_kernel_t<false><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
-                                                                               plan->lev[l].V[buf], plan->lev[l].T[buf], nullptr);
+                    qr_apply_pp_kernel_t<false><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
             } else if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
                 qr_apply_mma_kernel_t<true><<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
                                                                            plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
@@ -1412,9 +1574,13 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
         for (int64_t k = 0; k < npanels; ++k) {
             const int64_t c0 = k * QB, ctrail = c0 + QB;
             panel_levels(plan, c0, cur);
-            LSO_TRY(launch_leaf_chain(ctx, plan, c0, cur, 0, U));
+            const bool fused = ctx->opt_qr_apply == 3 && cur.L > 1;
+            LSO_TRY(launch_leaf_chain(ctx, plan, c0, cur, 0, U, fused ? (int)((plan->Nc - ctrail) / QCT) : 0));
             tl_mark(U, "leaf chain end", k, 0);
-            LSO_TRY(launch_apply(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U, true));
+            if (fused)
+                LSO_TRY(launch_apply_fused(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U));
+            else
+                LSO_TRY(launch_apply(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U, true));
         }
         tl_dump(U, plan->panel_stream);
         return LSO_OK;
