@@ -1021,6 +1021,9 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
         if (ATIMING && lane == 0) {
             if (blockIdx.x == gridDim.x / 2) tbuf[16 + L.nlev] = gtimer_ns() - tstart_ns;
             atomicMax((unsigned long long*)&tbuf[25], (unsigned long long)gtimer_ns());
+            atomicAdd((unsigned long long*)&tbuf[30], (unsigned long long)gtimer_ns());
+            atomicAdd((unsigned long long*)&tbuf[31], 1ull);
+            atomicMin((unsigned long long*)&tbuf[23], (unsigned long long)gtimer_ns());
         }
         return;
     }
@@ -1391,6 +1394,7 @@ extern "C" int lso_debug_apply_timing(lso_ctx* ctx, long long* h_out /* 16 */) {
     LSO_CHECK_CUDA(ctx, cudaMemcpy(h_out, g_apply_tbuf, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
     LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf, 0, 32 * sizeof(long long)));      // re-arm
     LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf + 24, 0xff, sizeof(long long)));
+    LSO_CHECK_CUDA(ctx, cudaMemset(g_apply_tbuf + 23, 0xff, sizeof(long long)));
     return LSO_OK;
 }
 static long long* g_leaf_tbuf = nullptr;     // debug: per-phase clock64 stamps of the single-block leaf (LSO_LEAF_TIMING)

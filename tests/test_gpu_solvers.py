@@ -26,10 +26,12 @@ SHAPES = [(2, 2), (9, 6), (40, 40), (100, 33), (300, 64), (777, 65), (3000, 100)
           (2304, 32), (70000, 40)]
 
 
-@pytest.mark.parametrize("apply_kernel", [1, 0])
+@pytest.mark.parametrize("apply_kernel", [2, 3, 1, 0])
 @pytest.mark.parametrize("m,n", SHAPES)
 def test_qr_damped(ctx, m, n, apply_kernel):
-    """ldiv!(x, J, y, damp, A::DenseQRAllocatedSolver) — dense_qr.jl:56-88"""
+    """ldiv!(x, J, y, damp, A::DenseQRAllocatedSolver) — dense_qr.jl:56-88.  Trailing-update kernels: 2 = ping-pong DMMA
+    kernel, one launch per tree level (the default), 3 = the same kernel with all tree levels in one launch, 1 = the
+    first-generation DMMA kernel, 0 = plain-FMA cross-check kernel."""
     from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
     if apply_kernel == 0 and m * n > 400000:
         pytest.skip("plain-FMA cross-check kernel: small shapes only")
@@ -58,7 +60,7 @@ def test_qr_damped(ctx, m, n, apply_kernel):
             Rg = ws.factor()
             assert rel(np.abs(Rg), np.abs(Rref)) <= 1e-11
     finally:
-        ctx.set_option("qr_apply", 1)
+        ctx.set_option("qr_apply", 2)
 
 
 @pytest.mark.parametrize("m,n", [(2, 2), (9, 6), (40, 40), (300, 64), (5000, 257), (20000, 96)])

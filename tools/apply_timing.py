@@ -31,3 +31,4 @@ print("CTA 0 total cycles in kernel", int(buf[11]), "=> per tile", buf[11] / nj)
 print("CTA 0 wall ns", int(buf[12]), "=> effective SM clock %.0f MHz" % (buf[11] / max(buf[12], 1) * 1e3))
 print("producer of the middle CTA: ns since kernel start at the first job of each level, then at exit:", [int(v) for v in buf[16:22]])
 t0 = int(buf[24]); print("all CTAs: first job at 0, slowest CTA enters level l at (us):", [round((int(v) - t0) / 1e3, 1) if v else None for v in buf[26:30]], "last exit", round((int(buf[25]) - t0) / 1e3, 1))
+n = max(int(buf[31]), 1); print("producer exit times over the %d CTAs (us after the first job): first %.1f, mean %.1f, last %.1f" % (n, (int(buf[23]) - t0) / 1e3, (int(buf[30]) / n - t0) / 1e3, (int(buf[25]) - t0) / 1e3))
