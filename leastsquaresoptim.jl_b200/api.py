@@ -319,6 +319,7 @@ class LMRun:
                                               ftrial=DeviceVector(ctx, m), fpredict=DeviceVector(ctx, m),
                                               red=DeviceVector(ctx, 8)))
         self.dx, self.dtd, self.ftrial, self.fpredict, self.red = w["dx"], w["dtd"], w["ftrial"], w["fpredict"], w["red"]
+        self.grad = anls.workspace("lm_grad", lambda: dict(g=DeviceVector(ctx, n)))["g"]
         self.dlo, self.dhi = _bounds(ctx, anls.x, lower, upper)
         self.sharded = getattr(ctx, "nranks", 1) > 1
         self.Δ = float(Δ)
@@ -355,18 +356,19 @@ class LMRun:
             anls.g(x)
             self.g_calls += 1
             self.need_jacobian = False
-        J.colsumabs2(dtd)                                     # :82
+        # :82 colsumabs2!(dtd, J) and :102 mul!(dtd, J', fcur) both read J and fcur, which do not change in between:
+        # one pass over J produces both (the gradient is parked in `grad` until the solver is done with dtd)
+        J.colsumabs2_and_grad(dtd, self.grad, fcur)
         if self.sharded:
             ctx.allreduce(dtd)
+            ctx.allreduce(self.grad)
         _lm_damping(ctx, dtd, 1 / self.Δ)                     # :84-86
         _, lmiter = anls.solver.ldiv(dx, J, fcur, dtd)        # :87
         if self.record_steps:
             self.deltas.append(dx.download())
         _box_project(ctx, dx, x, self.dlo, self.dhi)          # :89-98
         self.mul_calls += lmiter
-        J.mul_t(dtd, fcur, 1.0, 0.0)                          # :102 gradient J'f
-        if self.sharded:
-            ctx.allreduce(dtd)
+        dtd.copyto(self.grad)                                 # :102 gradient J'f (computed above)
         self.mul_calls += 1
         self.maxabs_gr = _maxabs_projected_gradient(ctx, dtd, x, self.dlo, self.dhi)
         x.axpy(-1.0, dx)                                      # :106
@@ -510,6 +512,7 @@ class HostStep:
                                               ftrial=DeviceVector(ctx, m), fpredict=DeviceVector(ctx, m),
                                               red=DeviceVector(ctx, 8)))
         self.dx, self.dtd, self.fpredict, self.red = w["dx"], w["dtd"], w["fpredict"], w["red"]
+        self.grad = anls.workspace("lm_grad", lambda: dict(g=DeviceVector(ctx, n)))["g"]
         self.sharded = getattr(ctx, "nranks", 1) > 1
 
     def run(self, hJ_ptr: int, hf_ptr: int, Δ: float, dx_host: np.ndarray):
@@ -518,14 +521,13 @@ class HostStep:
         self.check(self.lib.lso_upload_async(h, J.ptr, hJ_ptr, a.m * a.n * 8), h)
         self.check(self.lib.lso_upload_async(h, fcur.ptr, hf_ptr, a.m * 8), h)
         ssr = fcur.sumabs2()
-        J.colsumabs2(dtd)
+        J.colsumabs2_and_grad(dtd, self.grad, fcur)          # LM:82 and LM:102 in one pass over J
         if self.sharded:
             ctx.allreduce(dtd)
+            ctx.allreduce(self.grad)
         _lm_damping(ctx, dtd, 1 / Δ)
         a.solver.ldiv(dx, J, fcur, dtd)
-        J.mul_t(dtd, fcur, 1.0, 0.0)
-        if self.sharded:
-            ctx.allreduce(dtd)
+        dtd.copyto(self.grad)
         maxabs_gr = dtd.maxabs()
         predicted_ssr = J.predicted_ssr(dx, fcur, self.fpredict)
         if self.sharded:

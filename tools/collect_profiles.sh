@@ -23,3 +23,5 @@ python tools/leaf_timing.py 200 32 > $O/${T}_tree_lone_block_timing.txt 2>&1
 python tools/probe_qr.py > $O/${T}_probe_dense_c2.jsonl 2>&1
 python tools/profile_chol.py 250000 4000 2 > $O/${T}_chol_c4shard.txt 2>&1
 ls -la $O | tail -20
+python tools/probe_configs.py c4 c5 > $O/${T}_probe_configs_c4shard_c5.jsonl 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.txt 2>&1
