@@ -51,6 +51,12 @@ int         lso_ctx_destroy(lso_ctx* ctx);
 const char* lso_last_error(lso_ctx* ctx);          /* ctx may be NULL: last global error */
 int         lso_ctx_sync(lso_ctx* ctx);
 void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-event timing by the caller */
+/* Options (debug / cross-check switches; the defaults are the measured-fastest paths):
+ *   "qr_apply"     0 plain-FMA trailing update, 1 first-generation DMMA kernel, 2 ping-pong DMMA kernel with one launch
+ *                  per tree level (default), 3 the same kernel with all tree levels of a panel in one launch
+ *   "qr_lookahead" 1 = panel trees on a second stream under the previous update (default 0)
+ *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default)
+ *   "profile"      see lso_ctx_profile_read */
 int         lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value);
 int         lso_ctx_launch_count(lso_ctx* ctx, int64_t* out, int reset); /* kernels launched by this library */
 /* With option "profile" = 1 every launch of the dominant kernel of a solve (QR trailing update, syrk, SpMV pair) is

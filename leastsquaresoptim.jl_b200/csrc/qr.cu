@@ -57,6 +57,8 @@ __device__ __forceinline__ int tm_body_rows(const TileMap& tm, long long blk) {
 // reduced through shared memory, and the rank-1 update is applied from the published column.  The T factor of
 // the compact WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V).
 // =================================================================================================
+__device__ __forceinline__ long long gtimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 // Reflector scalars of one Householder step (dlarfg with an unnormalised v):
 //     nrm = sqrt(alpha^2 + s),  beta = -sign(alpha) nrm,  vjj = alpha - beta,  t = 1 / (nrm (nrm + |alpha|)).
 // Fast path: MUFU seeds + two Goldschmidt / Newton steps, no branches on the chain; results are within a couple of
@@ -305,6 +307,13 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     const TileMap tm = tp.tm[lev];
     const bool timed = TIMING && blockIdx.x == gridDim.x - 1;
     if (timed && tid == 32) tbuf[210] = clock64();
+    // trace of selected blocks (globaltimer): start, loop start, loop end, exit
+    int trace_slot = -1;
+    if (TIMING && gridDim.x > 300) {
+        const int sel[9] = {0, 147, 295, 296, 394, tp.start[1], tp.start[2] - 1, tp.start[2], (int)gridDim.x - 1};
+        for (int q = 0; q < 9; ++q) if ((int)blockIdx.x == sel[q]) trace_slot = 220 + 4 * q;
+    }
+    if (trace_slot >= 0 && tid == 0) tbuf[trace_slot] = gtimer_ns();
     for (int i = blockIdx.x * LEAF_THREADS + tid; i < tp.zero_n; i += gridDim.x * LEAF_THREADS) tp.zero_ptr[i] = 0;
 #define LEAF_T(slot) do { if (timed && tid == 32) tbuf[(slot)] = clock64(); } while (0)
 
@@ -368,6 +377,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     if (rg == 0) *reinterpret_cast<double2*>(&sm.rowbuf[0][2 * cp]) = make_double2(xa[0], xb[0]);
     __syncwarp();
     LEAF_T(0);
+    if (trace_slot >= 0 && tid == 0) tbuf[trace_slot + 1] = gtimer_ns();
 
     // Reflectors are kept UNNORMALISED: v = a_j + sign(alpha) ||a_j|| e_j, H = I - t v v', t = 1 / (||a_j|| (||a_j|| + |alpha|)).
     // One block-wide barrier per step; the owners of column j+1 publish it from inside step j.
@@ -383,6 +393,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
 #undef LEAF_LOOP
     __syncthreads();
     LEAF_T(200);
+    if (trace_slot >= 0 && tid == 0) tbuf[trace_slot + 2] = gtimer_ns();
 
     // ---- V (explicit diagonal entry, zeros above) to the workspace; R head back into the matrix ----
     {
@@ -453,6 +464,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
         }
     }
     LEAF_T(201);
+    if (trace_slot >= 0 && tid == 0) tbuf[trace_slot + 3] = gtimer_ns();
 #undef LEAF_T
 }
 
@@ -566,7 +578,6 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ long long gtimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1])
@@ -1467,7 +1478,7 @@ static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const Panel
     tp.zero_ptr = plan->apply_cnt;
     tp.zero_n = 0;
     for (int l = 1; l < pl.L; ++l) tp.zero_n += (int)pl.nblk[l] * ntiles_fused;
-    if (g_leaf_tbuf && pl.nblk[0] <= 64)
+    if (g_leaf_tbuf && (pl.nblk[0] <= 64 || (getenv("LSO_TREE_TRACE") && c0 == QB)))
         qr_tree_kernel_t<true><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);
     else
         qr_tree_kernel_t<false><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, nullptr);
