@@ -1048,9 +1048,13 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     long long cur_blk = -1;
     int cur_lev = -1;
     int seg_i = -1;
-    bool need_v = false;
     for (int u = 0; u < njobs; ++u) {
-        if (jw.lev != cur_lev || jw.blk != cur_blk) { cur_lev = jw.lev; cur_blk = jw.blk; ++seg_i; need_v = true; }
+        if (jw.lev != cur_lev || jw.blk != cur_blk) {
+            // EVERY consumer thread waits for EVERY V, also for blocks in which its group has no tile: a parity wait
+            // is only meaningful against the phase that immediately precedes it, so no phase of bar_v may be skipped
+            cur_lev = jw.lev; cur_blk = jw.blk; ++seg_i;
+            mbar_wait(bar_v, (uint32_t)(seg_i & 1));
+        }
         const bool last_of_seg = (jw.left == 1) || (jw.tile + 1 == ntiles);     // the next job has another V
         jw_next(jw, L, ntiles);
         if ((u & 1) != grp) {
@@ -1059,7 +1063,6 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
         }
         const int s = u % PP_NST;
         if (ATIMING && blockIdx.x == 0 && tid == 0) { if (u == 0) tprev = clock64(); else PP_TM(9); }
-        if (need_v) { mbar_wait(bar_v, (uint32_t)(seg_i & 1)); need_v = false; }
         mbar_wait(bar_full + 8 * s, (uint32_t)((u / PP_NST) & 1));
         PP_TM(0);
         double* Xst = Xs + s * QCT * QS;

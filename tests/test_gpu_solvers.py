@@ -23,7 +23,9 @@ def make_J(m, n, seed, scaled=True):
 
 
 SHAPES = [(2, 2), (9, 6), (40, 40), (100, 33), (300, 64), (777, 65), (3000, 100), (5000, 257), (20000, 96),
-          (2304, 32), (70000, 40)]
+          (2304, 32), (70000, 40),
+          (1100000, 32),    # 6 tree levels, 15 waves of leaf blocks: parents wait on children that are dispatched later
+          (300000, 64)]     # 5 tree levels, two panels
 
 
 @pytest.mark.parametrize("apply_kernel", [2, 3, 1, 0])
@@ -33,6 +35,8 @@ def test_qr_damped(ctx, m, n, apply_kernel):
     kernel, one launch per tree level (the default), 3 = the same kernel with all tree levels in one launch, 1 = the
     first-generation DMMA kernel, 0 = plain-FMA cross-check kernel."""
     from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    if apply_kernel in (0, 1) and m * n > 400000 and m > 100000:
+        pytest.skip("cross-check kernels: not at the deep-tree shapes")
     if apply_kernel == 0 and m * n > 400000:
         pytest.skip("plain-FMA cross-check kernel: small shapes only")
     ctx.set_option("qr_apply", apply_kernel)
