@@ -161,6 +161,10 @@ int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count);
 /* TSQR over row shards for the QR path: every rank passes its shard of J and y; all ranks get x. */
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                          const double* d_damp, double* d_x, int* rank_out);
+/* Test hook: the sharded algorithm (local QR per shard, interleaved stack of the R factors, banded QR of the stack)
+ * with the P shards emulated on one device: d_J is (P * m) x n where m is the workspace's shard row count. */
+int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,
+                                       const double* d_damp, double* d_x, int* rank_out);
 
 /* ---- sparse operator: SparseMatrixCSC mul! both ways + colsumabs2! (utils.jl:146-151;
  *      lsmr.jl:73,76,118,122; levenberg_marquardt.jl:82,102,114)                             ---- */

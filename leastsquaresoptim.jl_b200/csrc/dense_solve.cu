@@ -13,6 +13,7 @@ struct lso_dense_ws {
     QRPlan plan;          // local factorisation of [J; sqrt(D) | y; 0]
     QRPlan plan_stack;    // multi-GPU: QR of the stacked R factors (created on first sharded solve)
     bool have_stack = false;
+    int stack_P = 0;
     double* d_gather = nullptr;   // multi-GPU: nranks * (n x (n+1)) gathered [R | Q'y]
     // Cholesky
     CholPlan chol;
@@ -264,6 +265,49 @@ __global__ void stack_assemble_kernel(long long n, int P, int Q, const double* _
     }
 }
 
+// local QR of [J_k | y_k] and its n x (n+1) [R | Q'y] packed into `slot`
+static int shard_local_R(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, double* slot) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, n, d_J, ld, d_y, nullptr));
+    LSO_TRY(qr_factor(ctx, &ws->plan));
+    dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 64), (unsigned)(n + 1));
+    pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, ws->plan.A, ws->plan.ld, ws->plan.Npad, slot);
+    LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}
+static int shard_ensure_stack(lso_dense_ws* ws, int P) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    if (ws->have_stack && ws->stack_P != P) {
+        qr_plan_destroy(&ws->plan_stack);
+        cudaFree(ws->d_gather);
+        ws->d_gather = nullptr;
+        ws->have_stack = false;
+    }
+    if (!ws->have_stack) {
+        LSO_TRY(qr_plan_create(ctx, (int64_t)P * n + n, n, &ws->plan_stack));
+        ws->have_stack = true;
+        ws->stack_P = P;
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_gather, (size_t)(P + 1) * n * (n + 1) * sizeof(double)));
+    }
+    return LSO_OK;
+}
+// replicated QR of the interleaved stack of the P gathered triangles (+ the damping triangle), then the solve
+static int shard_stack_solve(lso_dense_ws* ws, int P, const double* d_damp, double* d_x, int* rank_out) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    QRPlan* ps = &ws->plan_stack;
+    dim3 grid((unsigned)std::min<int64_t>(cdiv64(ps->ld, 256), 64), (unsigned)ps->Nc);
+    const int Q = d_damp ? P + 1 : P;
+    stack_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(n, P, Q, ws->d_gather, d_damp, ps->A, ps->ld, ps->Npad);
+    LSO_CHECK_LAUNCH(ctx);
+    ps->M = (int64_t)Q * n;       // rows in use (the workspace was sized for P + 1 triangles)
+    ps->band = Q;
+    LSO_TRY(qr_factor(ctx, ps));
+    return qr_finish(ws, ps, d_x, rank_out);
+}
+
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
                          double* d_x, int* rank_out) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
@@ -275,32 +319,27 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     LSO_REQUIRE(ctx, ws->m >= ws->n, "sharded QR: each shard needs rows >= columns");
     const int64_t n = ws->n;
     const int P = ctx->nranks;
-    if (!ws->have_stack) {
-        LSO_TRY(qr_plan_create(ctx, (int64_t)P * n + n, n, &ws->plan_stack));
-        ws->have_stack = true;
-        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_gather, (size_t)(P + 1) * n * (n + 1) * sizeof(double)));
-    }
-    // local QR of [J_k | y_k]
-    LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, n, d_J, ld, d_y, nullptr));
-    LSO_TRY(qr_factor(ctx, &ws->plan));
+    LSO_TRY(shard_ensure_stack(ws, P));
     double* sendbuf = ws->d_gather + (size_t)P * n * (n + 1);
-    {
-        dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 64), (unsigned)(n + 1));
-        pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, ws->plan.A, ws->plan.ld, ws->plan.Npad, sendbuf);
-        LSO_CHECK_LAUNCH(ctx);
-    }
+    LSO_TRY(shard_local_R(ws, d_J, ld, d_y, sendbuf));
     LSO_TRY(lso_comm_allgather(ctx, sendbuf, ws->d_gather, n * (n + 1)));
-    {
-        QRPlan* ps = &ws->plan_stack;
-        dim3 grid((unsigned)std::min<int64_t>(cdiv64(ps->ld, 256), 64), (unsigned)ps->Nc);
-        const int Q = d_damp ? P + 1 : P;
-        stack_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(n, P, Q, ws->d_gather, d_damp, ps->A, ps->ld, ps->Npad);
-        LSO_CHECK_LAUNCH(ctx);
-        ps->M = (int64_t)Q * n;       // rows in use (the workspace was sized for P + 1 triangles)
-        ps->band = Q;
-        LSO_TRY(qr_factor(ctx, ps));
-    }
-    return qr_finish(ws, &ws->plan_stack, d_x, rank_out);
+    return shard_stack_solve(ws, P, d_damp, d_x, rank_out);
+}
+
+// Test hook: the sharded algorithm with the P shards emulated on ONE device (the rows of J are cut into P equal
+// chunks of ws->m rows that are factorised one after the other; no communicator needed).  d_J is (P * ws->m) x n.
+int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,
+                                       const double* d_damp, double* d_x, int* rank_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && ws->damped == 0, "create the workspace for QR with damped = 0");
+    LSO_REQUIRE(ctx, P >= 1 && P <= 64 && d_J && d_y && d_x, "bad arguments");
+    LSO_REQUIRE(ctx, ws->m >= ws->n, "each shard needs rows >= columns");
+    const int64_t n = ws->n;
+    LSO_TRY(shard_ensure_stack(ws, P));
+    for (int k = 0; k < P; ++k)
+        LSO_TRY(shard_local_R(ws, d_J + (size_t)k * ws->m, ld, d_y + (size_t)k * ws->m, ws->d_gather + (size_t)k * n * (n + 1)));
+    return shard_stack_solve(ws, P, d_damp, d_x, rank_out);
 }
 
 }  // extern "C"

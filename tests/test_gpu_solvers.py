@@ -259,3 +259,32 @@ def test_qr_zero_and_tiny_damping(ctx):
     ws0 = DenseQRAllocatedSolver(ctx, 200, 10, damped=False)
     ws0.ldiv(x, DenseMatrix(ctx, 200, 10, np.zeros((200, 10))), DeviceVector(ctx, 200, yh))
     assert ws0.last_rank == 0 and np.all(x.download() == 0.0)
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+@pytest.mark.parametrize("ms,n,damped", [(700, 64, True), (5000, 257, True), (3000, 96, False), (40, 40, True)])
+def test_qr_sharded_algorithm_emulated_on_one_gpu(ctx, P, ms, n, damped):
+    """The multi-GPU QR path (local QR per row shard, R factors stacked with interleaved rows, banded QR of the stack)
+    with the P shards emulated on one device through the test hook: same answer as the oracle's solve of the whole
+    system, for P up to the 8 ranks of the scaling run."""
+    import ctypes as C
+    from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    from lsob200._lib import check, lib
+    m = P * ms
+    Jh, yh, rng = make_J(m, n, 11 * m + n + P)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0 if damped else None
+    ws = DenseQRAllocatedSolver(ctx, ms, n, damped=False)          # shard workspace: the damping rows join the stack
+    J, y, x = DenseMatrix(ctx, m, n, Jh), DeviceVector(ctx, m, yh), DeviceVector(ctx, n)
+    d = DeviceVector(ctx, n, damp) if damped else None
+    rank = C.c_int()
+    for rep in range(2):
+        check(lib().lso_debug_qr_solve_emulated_shards(ws._h, P, J.ptr, J.ld, y.ptr, d.ptr if d is not None else None, x.ptr,
+                                                       C.byref(rank)), ctx.handle)
+        xg = x.download()
+        if rep == 0:
+            x0 = xg.copy()
+    assert np.array_equal(xg, x0)
+    xr, _ = O.qr_ldiv(Jh, yh, damp)
+    assert rank.value == n
+    assert rel(xg, xr) <= TOL, rel(xg, xr)
