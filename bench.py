@@ -283,7 +283,8 @@ def main():
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "qr_apply_mma_kernel (CAQR trailing update, mma.sync m8n8k4 f64 = DMMA, cp.async.bulk fed)",
+        "kernel": "qr_apply_pp_kernel_t (CAQR trailing update: mma.sync m8n8k4 f64 = DMMA, two ping-pong consumer groups, "
+                  "all global traffic as cp.async.bulk loads / stores issued by a producer warp)",
         "bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
         "frac": achieved / dmma_peak if dmma_peak else None, "traffic": traffic,
         "peak_source": "fp64 DMMA issue-bound micro-benchmark measured in this run (lso_bench_fp64_mma_peak); "
