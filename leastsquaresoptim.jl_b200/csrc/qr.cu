@@ -810,12 +810,15 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
 //                   X' += Wfin' V' (GEMM2).  A warp only ever touches its own row slice of the staged tile.
 // =================================================================================================
 #define PP_NST 4
-#define PP_GW 4                                     /* warps per consumer group */
+#define PP_GW 4                                     /* warps per consumer group (8 measured 8 % slower: more barrier skew) */
+#define PP_WR (QH / PP_GW)                           /* tile rows owned by one consumer warp */
+#define PP_GT (32 * PP_GW)                          /* threads per consumer group */
+#define PP_THREADS (32 * (2 * PP_GW + 1))           /* two consumer groups + the producer warp */
 #define PP_T_BYTES (QB * QWS * 8)
 #define PP_WS_BYTES (QCT * QWS * 8)
 #define PP_SMEM_BYTES (AM_VS_BYTES + PP_T_BYTES + PP_NST * AM_XS_BYTES + 4 * PP_WS_BYTES + 128)
 
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(PP_GT) : "memory"); }
 
 // One launch can cover ONE tree level or ALL of them ("fused"): the job list of a CTA is then its slice of level 0,
 // followed by its slice of level 1, ...  A job of level l > 0 (block b, tile t) needs the head rows that its up to
@@ -866,7 +869,7 @@ __device__ __forceinline__ int ld_acquire_s32(const int* p) {
 __device__ __forceinline__ void bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 
 template <bool ATIMING>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(PP_THREADS, 1)
 qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int ntiles, ApplyLevels L,
                      long long* __restrict__ tbuf) {
     long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -893,10 +896,10 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     if (tid == 0) {
         for (int s = 0; s < PP_NST; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_out + 8 * s, 128);
+            mbar_init(bar_out + 8 * s, PP_GT);
         }
         mbar_init(bar_v, 1);
-        mbar_init(bar_vfree, 256);
+        mbar_init(bar_vfree, 2 * PP_GT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
@@ -907,7 +910,7 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     jw.lev = 0; jw.tile = 0; jw.left = 0; jw.blk = 0;
     jw_enter_level(jw, L, ntiles);
 
-    if (wrp == 8) {
+    if (wrp == 2 * PP_GW) {
         // =========================== producer warp: all global traffic, via the TMA unit ===========================
         int seg_i = -1;
         int cur_lev = -1;
@@ -1040,8 +1043,8 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
     }
 
     // =============================== consumer groups ===============================
-    const int grp = wrp >> 2, w4 = wrp & 3;
-    const int gtid = tid & 127;
+    const int grp = wrp / PP_GW, w4 = wrp % PP_GW;
+    const int gtid = tid % PP_GT;
     const int g = lane >> 2, t = lane & 3;
     double* Wsum = (double*)(wbase + (2 * grp) * PP_WS_BYTES);          // [QCT][QWS]  (V'X)'
     double* Wfin = (double*)(wbase + (2 * grp + 1) * PP_WS_BYTES);      // [QCT][QWS]  -(T'V'X)'
@@ -1069,12 +1072,12 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
 
         // this warp's rows of the staged tile become the GEMM2 accumulators now: after GEMM1 nobody reads the slice any
         // more, so the split-K partials of GEMM1 are parked in it (no separate partial buffers -> a 4th stage fits)
-        double c2[2][8][2];
-        const int rbase = 64 * w4 + 2 * t;
+        double c2[2][PP_WR / 8][2];
+        const int rbase = PP_WR * w4 + 2 * t;
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
+            for (int ni = 0; ni < PP_WR / 8; ++ni) {
                 const double2 v = *reinterpret_cast<const double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni);
                 c2[mi][ni][0] = v.x; c2[mi][ni][1] = v.y;
             }
@@ -1086,8 +1089,8 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) c1[mi][ni][0] = c1[mi][ni][1] = 0.0;
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-                const int k0 = 64 * w4 + 4 * ks + t;
+            for (int ks = 0; ks < PP_WR / 4; ++ks) {
+                const int k0 = PP_WR * w4 + 4 * ks + t;
                 double a[2], b[4];
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) a[mi] = Xst[(8 * mi + g) * QS + k0];
@@ -1099,59 +1102,57 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
                     for (int ni = 0; ni < 4; ++ni) dmma(c1[mi][ni], a[mi], b[ni]);
             }
             __syncwarp();       // every lane has finished reading the warp's slice
-            // partial element (column c = 8 mi + g, reflector k = 8 ni + 2 t) -> Xst[c][64 w + k]
+            // partial element (column c = 8 mi + g, reflector k = 8 ni + 2 t) -> Xst[c][PP_WR w + k]
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
-                    *reinterpret_cast<double2*>(Xst + (8 * mi + g) * QS + 64 * w4 + 8 * ni + 2 * t) =
+                    *reinterpret_cast<double2*>(Xst + (8 * mi + g) * QS + PP_WR * w4 + 8 * ni + 2 * t) =
                         make_double2(c1[mi][ni][0], c1[mi][ni][1]);
         }
         PP_TM(1);
         group_sync(grp);
         PP_TM(2);
-        // ---- reduce the 4 partials: Wsum[c][k] = (V'X)[k][c] ----
+        // ---- reduce the PP_GW partials: Wsum[c][k] = (V'X)[k][c] ----
         {
-            const int c = gtid >> 3, k4 = (gtid & 7) * 4;
-            const double* w0 = Xst + c * QS + k4;
-            double2 p[PP_GW][2];
+            constexpr int NK = (QCT * QB) / PP_GT;           // outputs per thread: 4 (128 threads) or 2 (256 threads)
+            const int c = gtid / (QB / NK), k0r = (gtid % (QB / NK)) * NK;
+            const double* w0 = Xst + c * QS + k0r;
+            double2 p[PP_GW][NK / 2];
 #pragma unroll
-            for (int w = 0; w < PP_GW; ++w) {
-                p[w][0] = *reinterpret_cast<const double2*>(w0 + 64 * w);
-                p[w][1] = *reinterpret_cast<const double2*>(w0 + 64 * w + 2);
-            }
-            double2 r0, r1;
-            r0.x = (p[0][0].x + p[1][0].x) + (p[2][0].x + p[3][0].x);
-            r0.y = (p[0][0].y + p[1][0].y) + (p[2][0].y + p[3][0].y);
-            r1.x = (p[0][1].x + p[1][1].x) + (p[2][1].x + p[3][1].x);
-            r1.y = (p[0][1].y + p[1][1].y) + (p[2][1].y + p[3][1].y);
-            *reinterpret_cast<double2*>(Wsum + c * QWS + k4) = r0;
-            *reinterpret_cast<double2*>(Wsum + c * QWS + k4 + 2) = r1;
+            for (int w = 0; w < PP_GW; ++w)
+#pragma unroll
+                for (int h = 0; h < NK / 2; ++h) p[w][h] = *reinterpret_cast<const double2*>(w0 + PP_WR * w + 2 * h);
+#pragma unroll
+            for (int st = 1; st < PP_GW; st <<= 1)
+#pragma unroll
+                for (int w = 0; w < PP_GW; w += 2 * st)
+#pragma unroll
+                    for (int h = 0; h < NK / 2; ++h) { p[w][h].x += p[w + st][h].x; p[w][h].y += p[w + st][h].y; }
+#pragma unroll
+            for (int h = 0; h < NK / 2; ++h) *reinterpret_cast<double2*>(Wsum + c * QWS + k0r + 2 * h) = p[0][h];
         }
         PP_TM(3);
         group_sync(grp);
         PP_TM(4);
-        // ---- Wfin' = -Wsum' T  on the tensor pipe: warp w4 forms columns [8 w4, 8 w4 + 8) for both row fragments ----
+        // ---- Wfin' = -Wsum' T  on the tensor pipe: the 2 x 4 fragments (8 x 8 each) are spread over the group's warps ----
         {
-            double ct[2][4][2];                             // 4 accumulators per fragment: dependent chains of 2 DMMAs
+            constexpr int NF = 8 / PP_GW;                    // fragments per warp: 2 (4 warps) or 1 (8 warps)
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int f = 0; f < NF; ++f) {
+                const int fr = w4 * NF + f, mi = fr & 1, ni = fr >> 1;
+                double ct[4][2];                             // 4 accumulators: dependent chains of 2 DMMAs
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ct[mi][q][0] = ct[mi][q][1] = 0.0;
+                for (int q = 0; q < 4; ++q) ct[q][0] = ct[q][1] = 0.0;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const double b = Ts[(8 * w4 + g) * QWS + 4 * ks + t];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi) {
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double b = Ts[(8 * ni + g) * QWS + 4 * ks + t];
                     const double a = Wsum[(8 * mi + g) * QWS + 4 * ks + t];
-                    dmma(ct[mi][ks & 3], a, b);
+                    dmma(ct[ks & 3], a, b);
                 }
+                *reinterpret_cast<double2*>(Wfin + (8 * mi + g) * QWS + 8 * ni + 2 * t) =
+                    make_double2(-((ct[0][0] + ct[1][0]) + (ct[2][0] + ct[3][0])), -((ct[0][1] + ct[1][1]) + (ct[2][1] + ct[3][1])));
             }
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-                *reinterpret_cast<double2*>(Wfin + (8 * mi + g) * QWS + 8 * w4 + 2 * t) =
-                    make_double2(-((ct[mi][0][0] + ct[mi][1][0]) + (ct[mi][2][0] + ct[mi][3][0])),
-                                 -((ct[mi][0][1] + ct[mi][1][1]) + (ct[mi][2][1] + ct[mi][3][1])));
         }
         PP_TM(5);
         group_sync(grp);
@@ -1162,15 +1163,15 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int k0 = 4 * ks + t;
-                double a[2], b[8];
+                double a[2], b[PP_WR / 8];
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) a[mi] = Wfin[(8 * mi + g) * QWS + k0];
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni) b[ni] = Vs[k0 * QS + 64 * w4 + 8 * ni + g];
+                for (int ni = 0; ni < PP_WR / 8; ++ni) b[ni] = Vs[k0 * QS + PP_WR * w4 + 8 * ni + g];
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 8; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
+                    for (int ni = 0; ni < PP_WR / 8; ++ni) dmma(c2[mi][ni], a[mi], b[ni]);
             }
             if (ATIMING && blockIdx.x == 0 && tid == 0) { if (c2[0][0][0] == 1.2345e-300) tacc[11] = 1; }
             PP_TM(8);
@@ -1178,7 +1179,7 @@ qr_apply_pp_kernel_t(double* __restrict__ A, long long ld, long long ctrail, int
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni)
+                for (int ni = 0; ni < PP_WR / 8; ++ni)
                     *reinterpret_cast<double2*>(Xst + (8 * mi + g) * QS + rbase + 8 * ni) =
                         make_double2(c2[mi][ni][0], c2[mi][ni][1]);
         }
@@ -1506,9 +1507,9 @@ static int launch_apply_fused(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl,
     const int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
     lso_prof_mark(ctx);
     if (g_apply_tbuf && cfirst == 2 * QB)
-        qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, g_apply_tbuf);
+        qr_apply_pp_kernel_t<true><<<grid, PP_THREADS, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, g_apply_tbuf);
     else
-        qr_apply_pp_kernel_t<false><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
+        qr_apply_pp_kernel_t<false><<<grid, PP_THREADS, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
     lso_prof_mark(ctx);
     LSO_CHECK_LAUNCH(ctx);
     tl_mark(st, "apply (all levels) end", cfirst / QB - 1, 0);
@@ -1540,9 +1541,9 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
                 L.T[0] = plan->lev[l].T[buf];
                 L.cnt[0] = nullptr;
                 if (g_apply_tbuf && l == 0 && cfirst == 2 * QB)
-                    qr_apply_pp_kernel_t<true><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, g_apply_tbuf);
+                    qr_apply_pp_kernel_t<true><<<grid, PP_THREADS, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, g_apply_tbuf);
                 else
-                    qr_apply_pp_kernel_t<false><<<grid, 288, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
+                    qr_apply_pp_kernel_t<false><<<grid, PP_THREADS, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
             } else if (g_apply_tbuf && l == 0 && cfirst <= 2 * QB)
                 qr_apply_mma_kernel_t<true><<<grid, 288, AM_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, pl.nblk[l], pl.tm[l],
                                                                            plan->lev[l].V[buf], plan->lev[l].T[buf], g_apply_tbuf);
