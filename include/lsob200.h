@@ -53,7 +53,8 @@ int         lso_ctx_sync(lso_ctx* ctx);
 void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-event timing by the caller */
 /* Options (debug / cross-check switches; the defaults are the measured-fastest paths):
  *   "qr_apply"     0 plain-FMA trailing update, 1 first-generation DMMA kernel, 2 ping-pong DMMA kernel with one launch
- *                  per tree level (default), 3 the same kernel with all tree levels of a panel in one launch
+ *                  per tree level (default), 3 the same kernel with all tree levels of a panel in one launch,
+ *                  4 levels 0 and 1 one launch each and the levels above chained in one launch
  *   "qr_lookahead" 1 = panel trees on a second stream under the previous update (default 0)
  *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default)
  *   "profile"      see lso_ctx_profile_read */

@@ -1458,7 +1458,7 @@ static void tl_mark(cudaStream_t st, const char* what, int64_t k, int stream_id)
     g_tl.push_back({e, what, k, stream_id});
 }
 static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const PanelLevels& pl, int buf, cudaStream_t st,
-                             int ntiles_fused = 0) {
+                             int zero_n = 0) {
     TreeParams tp;
     tp.nlev = pl.L;
     int total = 0;
@@ -1480,8 +1480,7 @@ static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const Panel
     plan->prog_base += 64;            // counters of earlier launches are all below the new base
     tp.base = plan->prog_base;
     tp.zero_ptr = plan->apply_cnt;
-    tp.zero_n = 0;
-    for (int l = 1; l < pl.L; ++l) tp.zero_n += (int)pl.nblk[l] * ntiles_fused;
+    tp.zero_n = zero_n;
     if (g_leaf_tbuf && (pl.nblk[0] <= 64 || (getenv("LSO_TREE_TRACE") && c0 == QB)))
         qr_tree_kernel_t<true><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);
     else
@@ -1491,19 +1490,21 @@ static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const Panel
 }
 
 // all tree levels of the panel's update in ONE launch (levels chained through per-tile child counters)
-static int launch_apply_fused(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int buf, int64_t cfirst, int ntiles, cudaStream_t st) {
-    if (ntiles <= 0) return LSO_OK;
+static int launch_apply_fused(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int buf, int64_t cfirst, int ntiles, cudaStream_t st,
+                              int lfirst = 0) {
+    if (ntiles <= 0 || lfirst >= pl.L) return LSO_OK;
     ApplyLevels L;
-    L.nlev = pl.L;
+    L.nlev = pl.L - lfirst;
     size_t off = 0;
-    for (int l = 0; l < pl.L; ++l) {
-        L.tm[l] = pl.tm[l];
-        L.V[l] = plan->lev[l].V[buf];
-        L.T[l] = plan->lev[l].T[buf];
-        L.cnt[l] = (l == 0) ? nullptr : plan->apply_cnt + off;
-        if (l > 0) off += (size_t)pl.nblk[l] * ntiles;
+    for (int l = lfirst; l < pl.L; ++l) {
+        const int q = l - lfirst;
+        L.tm[q] = pl.tm[l];
+        L.V[q] = plan->lev[l].V[buf];
+        L.T[q] = plan->lev[l].T[buf];
+        L.cnt[q] = (q == 0) ? nullptr : plan->apply_cnt + off;
+        if (q > 0) off += (size_t)pl.nblk[l] * ntiles;
     }
-    const int64_t jtot = pl.nblk[0] * ntiles;
+    const int64_t jtot = pl.nblk[lfirst] * ntiles;
     const int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
     lso_prof_mark(ctx);
     if (g_apply_tbuf && cfirst == 2 * QB)
@@ -1512,15 +1513,15 @@ static int launch_apply_fused(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl,
         qr_apply_pp_kernel_t<false><<<grid, PP_THREADS, PP_SMEM_BYTES, st>>>(plan->A, plan->ld, cfirst, ntiles, L, nullptr);
     lso_prof_mark(ctx);
     LSO_CHECK_LAUNCH(ctx);
-    tl_mark(st, "apply (all levels) end", cfirst / QB - 1, 0);
+    tl_mark(st, lfirst == 0 ? "apply (all levels) end" : "apply (upper levels, fused) end", cfirst / QB - 1, 0);
     return LSO_OK;
 }
 
 // apply the panel's block reflectors (all tree levels) to columns [cfirst, cfirst + ntiles*QCT)
 static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int buf, int64_t cfirst, int ntiles,
-                        cudaStream_t st, bool mark) {
+                        cudaStream_t st, bool mark, int lend = QR_MAX_LEVELS) {
     if (ntiles <= 0) return LSO_OK;
-    for (int l = 0; l < pl.L; ++l) {
+    for (int l = 0; l < pl.L && l < lend; ++l) {
         if (ctx->opt_qr_apply == 0) {
             int64_t chunks = cdiv64((int64_t)ctx->num_sms * 2, pl.nblk[l]);
             if (chunks > ntiles) chunks = ntiles;
@@ -1593,13 +1594,28 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
         for (int64_t k = 0; k < npanels; ++k) {
             const int64_t c0 = k * QB, ctrail = c0 + QB;
             panel_levels(plan, c0, cur);
+            // qr_apply = 3: all levels in one launch; 4: levels 0 and 1 one launch each, the (tiny, latency-bound) levels
+            // >= 2 chained in one launch
             const bool fused = ctx->opt_qr_apply == 3 && cur.L > 1;
-            LSO_TRY(launch_leaf_chain(ctx, plan, c0, cur, 0, U, fused ? (int)((plan->Nc - ctrail) / QCT) : 0));
+            const bool fused_upper = ctx->opt_qr_apply == 4 && cur.L > 3;
+            const int nt = (int)((plan->Nc - ctrail) / QCT);
+            int zero_n = 0;
+            if (fused) for (int l = 1; l < cur.L; ++l) zero_n += (int)cur.nblk[l] * nt;
+            if (fused_upper) for (int l = 3; l < cur.L; ++l) zero_n += (int)cur.nblk[l] * nt;
+            LSO_TRY(launch_leaf_chain(ctx, plan, c0, cur, 0, U, zero_n));
             tl_mark(U, "leaf chain end", k, 0);
-            if (fused)
-                LSO_TRY(launch_apply_fused(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U));
-            else
-                LSO_TRY(launch_apply(ctx, plan, cur, 0, ctrail, (int)((plan->Nc - ctrail) / QCT), U, true));
+            if (fused) {
+                LSO_TRY(launch_apply_fused(ctx, plan, cur, 0, ctrail, nt, U));
+            } else if (fused_upper) {
+                const int64_t save = ctx->opt_qr_apply;
+                ctx->opt_qr_apply = 2;
+                const int st_ = launch_apply(ctx, plan, cur, 0, ctrail, nt, U, true, 2);
+                ctx->opt_qr_apply = save;
+                LSO_TRY(st_);
+                LSO_TRY(launch_apply_fused(ctx, plan, cur, 0, ctrail, nt, U, 2));
+            } else {
+                LSO_TRY(launch_apply(ctx, plan, cur, 0, ctrail, nt, U, true));
+            }
         }
         tl_dump(U, plan->panel_stream);
         return LSO_OK;

@@ -28,7 +28,7 @@ SHAPES = [(2, 2), (9, 6), (40, 40), (100, 33), (300, 64), (777, 65), (3000, 100)
           (300000, 64)]     # 5 tree levels, two panels
 
 
-@pytest.mark.parametrize("apply_kernel", [2, 3, 1, 0])
+@pytest.mark.parametrize("apply_kernel", [2, 3, 4, 1, 0])
 @pytest.mark.parametrize("m,n", SHAPES)
 def test_qr_damped(ctx, m, n, apply_kernel):
     """ldiv!(x, J, y, damp, A::DenseQRAllocatedSolver) — dense_qr.jl:56-88.  Trailing-update kernels: 2 = ping-pong DMMA
