@@ -288,3 +288,29 @@ def test_qr_sharded_algorithm_emulated_on_one_gpu(ctx, P, ms, n, damped):
     xr, _ = O.qr_ldiv(Jh, yh, damp)
     assert rank.value == n
     assert rel(xg, xr) <= TOL, rel(xg, xr)
+
+
+def test_qr_and_cholesky_at_the_bench_shape(ctx):
+    """BASELINE.json configs[1] at full size (100 000 x 1 000, power-of-two column scales as in the bench's synthetic
+    model): the damped QR solve against the oracle's dgelsy (‖δ_gpu − δ_ref‖/‖δ_ref‖ ≤ 1e-10, the north-star tolerance),
+    the damped Cholesky solve against the same reference, and the residual identity J'(Jδ − y) + Dδ = 0."""
+    from lsob200 import DenseCholeskyAllocatedSolver, DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    m, n = 100_000, 1_000
+    rng = np.random.default_rng(20240608)
+    Jh = np.asfortranarray(rng.uniform(-1.0, 1.0, (m, n)) * np.exp2(rng.integers(-6, 7, n)))
+    yh = rng.standard_normal(m)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0
+    J, y, d, x = DenseMatrix(ctx, m, n, Jh), DeviceVector(ctx, m, yh), DeviceVector(ctx, n, damp), DeviceVector(ctx, n)
+    ws = DenseQRAllocatedSolver(ctx, m, n, damped=True)
+    ws.ldiv(x, J, y, d)
+    xq = x.download()
+    xr, rank = O.qr_ldiv(Jh, yh, damp)
+    assert rank == n
+    assert rel(xq, xr) <= TOL, rel(xq, xr)
+    g = Jh.T @ (Jh @ xq - yh) + damp * xq                      # normal equations of the damped system
+    assert np.linalg.norm(g) <= 1e-9 * np.linalg.norm(Jh.T @ yh)
+    del ws
+    wc = DenseCholeskyAllocatedSolver(ctx, m, n, damped=True)
+    wc.ldiv(x, J, y, d)
+    assert rel(x.download(), xr) <= 1e-7          # cond^2 path: looser by construction (tests above quantify it)
