@@ -314,3 +314,21 @@ def test_qr_and_cholesky_at_the_bench_shape(ctx):
     wc = DenseCholeskyAllocatedSolver(ctx, m, n, damped=True)
     wc.ldiv(x, J, y, d)
     assert rel(x.download(), xr) <= 1e-7          # cond^2 path: looser by construction (tests above quantify it)
+
+
+@pytest.mark.parametrize("damped", [True, False])
+def test_qr_many_panels(ctx, damped):
+    """66 panels, n not a multiple of the panel width, m / n small (the C5 regime: n = 10 000 columns at m = 200 000):
+    damped (LM) and undamped (Dogleg) forms."""
+    from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    m, n = 9000, 2100
+    Jh, yh, rng = make_J(m, n, 4242 + damped)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0 if damped else None
+    J, y, x = DenseMatrix(ctx, m, n, Jh), DeviceVector(ctx, m, yh), DeviceVector(ctx, n)
+    d = DeviceVector(ctx, n, damp) if damped else None
+    ws = DenseQRAllocatedSolver(ctx, m, n, damped=damped)
+    ws.ldiv(x, J, y, d)
+    xr, rank = O.qr_ldiv(Jh, yh, damp)
+    assert rank == n and ws.last_rank == n
+    assert rel(x.download(), xr) <= TOL
