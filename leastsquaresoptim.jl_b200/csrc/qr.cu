@@ -6,15 +6,17 @@
 // Only R and Q'b are needed for the least-squares solve, so the right-hand side rides along as an
 // extra column and V is discarded after each panel:
 //   for each panel of QB columns:
-//     level 0 : every QH-row block is factorised independently by one CTA (leaf kernel, registers)
+//     level 0 : every QH-row block is factorised independently by one CTA (registers)
 //     level l : the QB-row heads (R factors) of QG blocks of level l-1 are stacked and factorised
-//               the same way (TSQR reduction tree), until one R remains
+//               the same way (TSQR reduction tree), until one R remains; all levels run in ONE launch,
+//               pipelined step by step (a parent starts its step j once its children have finished theirs)
 //     then every level's block reflectors  I - V T' V'  are applied to the trailing columns, one
 //     pass over the trailing matrix per level (level 0 touches every row once; level l touches
 //     1/QG^l of the rows).  No global reduction, no grid-wide sync.
 // The trailing update is the flop carrier (4*QB flop per 8-byte element) and runs on the fp64
-// tensor pipe (mma.sync m8n8k4 -> DMMA), fed by cp.async.bulk (TMA unit, UBLKCP) through an mbarrier
-// ring with a dedicated producer warp.  tcgen05.mma has no f64 kind, see DESIGN.md.
+// tensor pipe (mma.sync m8n8k4 -> DMMA); ALL its global traffic is cp.async.bulk (TMA unit, UBLKCP)
+// loads and stores through an mbarrier ring, issued by a dedicated producer warp.  tcgen05.mma has no
+// f64 kind, see DESIGN.md.
 #include "qr.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -46,16 +48,9 @@ __device__ __forceinline__ int tm_body_rows(const TileMap& tm, long long blk) {
 }
 
 // =================================================================================================
-// leaf kernel: Householder QR of one QH x QB block.  256 threads: lane = column, warp g = row group.
-// Each thread keeps 32 entries of its column in registers:
-//     x[0..3]   head rows  g, g+8, g+16, g+24   (the 32 head rows end up holding R; spreading them over the 8
-//               warps makes every warp do the same work and leaves only 4 entries per thread that need a
-//               "row > j" predicate or a runtime-indexed pivot-row read)
-//     x[4..31]  body rows  32 + 28 g ... 32 + 28 g + 27  (one contiguous run; always below the diagonal)
-// Per Householder step: the owner lane publishes the pivot column (zeros above the diagonal), every thread
-// forms its partial v'a_k (or v_k'v_j for already factorised columns) in ONE pass, the 8 row groups are
-// reduced through shared memory, and the rank-1 update is applied from the published column.  The T factor of
-// the compact WY form is recovered after the loop from T^{-1} = diag(1/tau) + striu(V'V).
+// panel factorisation (qr_tree_kernel_t below): Householder QR of QH x QB blocks held in registers, the whole TSQR
+// tree of a panel in one launch.  The T factor of the compact WY form is recovered after the loop from
+// T^{-1} = diag(1/tau) + striu(V'V).
 // =================================================================================================
 __device__ __forceinline__ long long gtimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -535,7 +530,8 @@ qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
 }
 
 // =================================================================================================
-// trailing update, tensor-pipe version: persistent CTAs, producer warp + 8 consumer warps.
+// trailing update, first-generation tensor-pipe version (ctx option qr_apply = 1; kept as a cross-check):
+// persistent CTAs, producer warp + 8 consumer warps, results stored by the consumers.
 // =================================================================================================
 #define AM_NST 2
 #define AM_VS_BYTES (QB * QS * 8)
@@ -804,7 +800,7 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
 // trailing update, ping-pong version (ctx option qr_apply = 2, the default).
 // Two independent consumer groups of 4 warps work on alternate tiles, so that one group's reduction / T-multiply /
 // barrier phases run underneath the other group's DMMA phases, and NO consumer thread touches global memory:
-//   producer warp : cp.async.bulk loads of V|T (per block) and of X tiles into a 3-stage ring, and cp.async.bulk
+//   producer warp : cp.async.bulk loads of V|T (per block) and of X tiles into a 4-stage ring, and cp.async.bulk
 //                   STORES of the finished tiles straight from the ring (results are written back in place)
 //   consumer warp w of a group owns tile rows [64w, 64w+64): its K-slice of W' = X'V (GEMM1) and its output rows of
 //                   X' += Wfin' V' (GEMM2).  A warp only ever touches its own row slice of the staged tile.
