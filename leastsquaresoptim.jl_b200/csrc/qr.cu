@@ -108,8 +108,8 @@ __device__ __forceinline__ void leaf_scalars(double alpha, double s, double& bet
 // after the other (QB + 3 (L-1) steps instead of QB L).  Rows travel through an L2-resident mailbox in 16-byte
 // units {lo32, tag, hi32, tag} (the NCCL "LL" idea: the data carries its own flag; every 8-byte half is single-copy
 // atomic, the tag is unique per launch and row), so neither side executes a fence: the child fires and forgets,
-// the parent polls the data itself.  Blocks are numbered children first, so a waiting parent never occupies a slot
-// that one of its children still needs.
+// the parent polls the data itself.  Blocks are numbered children first AND a block's id is the order in which its
+// CTA actually started (atomic ticket), so a waiting parent never occupies a slot that one of its children still needs.
 #define LEAF_THREADS 256
 #define LEAF_NG 16          /* row groups */
 #define LEAF_NX 16          /* rows (slots) per thread */
@@ -127,6 +127,8 @@ struct TreeParams {
     unsigned base;                    // tag of row r in this launch = base + r + 1
     int* zero_ptr;                    // child counters of the fused trailing update that follows: zeroed here
     int zero_n;
+    unsigned* ticket;                 // start-order counter (monotonic over launches) and its value before this launch
+    unsigned ticket_base;
 };
 
 struct LeafSmem {
@@ -296,17 +298,24 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     __shared__ __align__(16) LeafSmem sm;
 
     const int tid = threadIdx.x;
+    // Logical block id = order in which the CTAs actually START (a ticket), not blockIdx: the children of a block have
+    // smaller logical ids, so by the time a parent exists every child has been given an SM slot and makes progress,
+    // whatever order the hardware dispatches CTAs in (the same device as the dynamic tile ids of decoupled look-back scans).
+    __shared__ unsigned s_ticket;
+    if (tid == 0) s_ticket = atomicAdd(tp.ticket, 1u) - tp.ticket_base;
+    __syncthreads();
+    const int bid = (int)s_ticket;
     int lev = 0;
-    while (lev + 1 < tp.nlev && (int)blockIdx.x >= tp.start[lev + 1]) ++lev;
-    const long long blk = (int)blockIdx.x - tp.start[lev];
+    while (lev + 1 < tp.nlev && bid >= tp.start[lev + 1]) ++lev;
+    const long long blk = bid - tp.start[lev];
     const TileMap tm = tp.tm[lev];
-    const bool timed = TIMING && blockIdx.x == gridDim.x - 1;
+    const bool timed = TIMING && bid == (int)gridDim.x - 1;
     if (timed && tid == 32) tbuf[210] = clock64();
     // trace of selected blocks (globaltimer): start, loop start, loop end, exit
     int trace_slot = -1;
     if (TIMING && gridDim.x > 300) {
         const int sel[9] = {0, 147, 295, 296, 394, tp.start[1], tp.start[2] - 1, tp.start[2], (int)gridDim.x - 1};
-        for (int q = 0; q < 9; ++q) if ((int)blockIdx.x == sel[q]) trace_slot = 220 + 4 * q;
+        for (int q = 0; q < 9; ++q) if (bid == sel[q]) trace_slot = 220 + 4 * q;
     }
     if (trace_slot >= 0 && tid == 0) tbuf[trace_slot] = gtimer_ns();
     for (int i = blockIdx.x * LEAF_THREADS + tid; i < tp.zero_n; i += gridDim.x * LEAF_THREADS) tp.zero_ptr[i] = 0;
@@ -321,7 +330,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     const int cp = c.cp, rg = c.rg;
     double* __restrict__ cola = A + (c0 + 2 * cp) * ld;
     double* __restrict__ colb = cola + ld;
-    c.mymail = tp.mail + (long long)blockIdx.x * (QB * QB) + 2 * cp;
+    c.mymail = tp.mail + (long long)bid * (QB * QB) + 2 * cp;
     double* __restrict__ heada = cola + tm.r0 + QB * blk;     // head row 0 of this block, column a
     const int body0 = QB + LEAF_BR * rg;              // level 0: first body row (tile coordinates)
 
@@ -1344,6 +1353,9 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         for (int l = 1; l < L; ++l) upper += plan->lev[l].nblocks;
         const size_t cb = (size_t)(upper > 0 ? upper : 1) * (size_t)(plan->Nc / QCT) * sizeof(int);
         LSO_CHECK_CUDA(ctx, cudaMalloc(&plan->apply_cnt, cb));
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&plan->ticket, sizeof(unsigned)));
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->ticket, 0, sizeof(unsigned), ctx->stream));
+        plan->ticket_base = 0;
     }
     {   // the panel stream gets the highest priority: its (small, latency-bound) kernels must be placed as soon as
         // they are ready, underneath / ahead of the bulk trailing update
@@ -1386,6 +1398,7 @@ void qr_plan_destroy(QRPlan* plan) {
     cudaFree(plan->A);
     cudaFree(plan->mail);
     cudaFree(plan->apply_cnt);
+    cudaFree(plan->ticket);
     for (int l = 0; l < plan->nlevels; ++l)
         for (int b = 0; b < 2; ++b) {
             cudaFree(plan->lev[l].V[b]);
@@ -1476,6 +1489,9 @@ static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const Panel
     plan->prog_base += 64;            // counters of earlier launches are all below the new base
     tp.base = plan->prog_base;
     tp.zero_ptr = plan->apply_cnt;
+    tp.ticket = plan->ticket;
+    tp.ticket_base = plan->ticket_base;
+    plan->ticket_base += (unsigned)total;       // unsigned wrap-around is harmless: ids are differences
     tp.zero_n = zero_n;
     if (g_leaf_tbuf && (pl.nblk[0] <= 64 || (getenv("LSO_TREE_TRACE") && c0 == QB)))
         qr_tree_kernel_t<true><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);

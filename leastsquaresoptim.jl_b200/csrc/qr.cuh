@@ -38,6 +38,8 @@ struct QRPlan {
     int nlevels = 0;
     uint4* mail = nullptr;      // mailbox of the fused panel-tree kernel: [block][row][column] {lo32, tag, hi32, tag}
     int* apply_cnt = nullptr;   // finished-children counters of the fused (all levels in one launch) trailing update
+    unsigned* ticket = nullptr; // start-order counter of the panel-tree kernel (logical block ids)
+    unsigned ticket_base = 0;
     unsigned prog_base = 0;     // tag base of the current launch (row r carries tag base + r + 1)
     QRLevel lev[QR_MAX_LEVELS];
     // look-ahead: panel factorisations run on a second stream, overlapped with the previous trailing update
