@@ -89,6 +89,49 @@ __device__ __forceinline__ void leaf_scalars(double alpha, double s, double& bet
     vjj = alpha - beta;                                 // = sign(alpha) (|alpha| + nrm)
 }
 
+#define AM_VS_BYTES (QB * QS * 8)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+
 // ---- panel factorisation: the whole TSQR tree of a panel in ONE launch, levels pipelined step by step ----
 // 256 threads per block.  The step time of a Householder factorisation held in registers is set by the length of
 // one warp's dependent instruction stream and by the shared-memory pipe (every pivot-column value a thread needs
@@ -116,6 +159,7 @@ __device__ __forceinline__ void leaf_scalars(double alpha, double s, double& bet
 #define LEAF_BR 14          /* body rows per thread at level 0 */
 #define LEAF_D 3            /* a parent requests row j + LEAF_D of its children at step j */
 #define LEAF_NSTG 4         /* staging buffers for pulled rows */
+#define TREE_DSMEM_BYTES (AM_VS_BYTES + 64)   /* block image + mbarrier */
 
 struct TreeParams {
     int nlev;
@@ -302,7 +346,16 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     // smaller logical ids, so by the time a parent exists every child has been given an SM slot and makes progress,
     // whatever order the hardware dispatches CTAs in (the same device as the dynamic tile ids of decoupled look-back scans).
     __shared__ unsigned s_ticket;
-    if (tid == 0) s_ticket = atomicAdd(tp.ticket, 1u) - tp.ticket_base;
+    // dynamic shared memory: the block as a [QB][QS] image (loaded and stored by the TMA unit, coalesced), + one mbarrier
+    extern __shared__ __align__(128) unsigned char tree_dsm[];
+    double* vt = (double*)tree_dsm;
+    const uint32_t ld_bar = smem_u32(tree_dsm + AM_VS_BYTES);
+    if (tid == 0) {
+        s_ticket = atomicAdd(tp.ticket, 1u) - tp.ticket_base;
+        mbar_init(ld_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
     __syncthreads();
     const int bid = (int)s_ticket;
     int lev = 0;
@@ -336,19 +389,32 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
 
     double xa[LEAF_NX], xb[LEAF_NX];
     if (!c.lazy) {
+        // the block comes in as two bulk copies per column (head 256 B, body <= 1792 B), then every thread picks its
+        // 2 x 16 entries out of shared memory
+        const int nv = tm_body_rows(tm, blk);
+        if (c.wrp == 0) {
+            if (c.lane == 0) mbar_expect_tx(ld_bar, (uint32_t)(QB * (QB + nv)) * 8u);
+            __syncwarp();
+            const double* colp = A + (c0 + c.lane) * ld + tm.r0;
+            const uint32_t dst = smem_u32(vt + c.lane * QS);
+            bulk_g2s(dst, colp + QB * blk, QB * 8u, ld_bar);
+            if (nv > 0) bulk_g2s(dst + QB * 8u, colp + QB * tm.nb + QBODY * blk, (uint32_t)nv * 8u, ld_bar);
+        }
+        mbar_wait(ld_bar, 0);
+        const double* ta = vt + (2 * cp) * QS;
+        const double* tb = ta + QS;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            long long mrow;
-            const bool ok = tm_row(tm, blk, rg + LEAF_NG * i, mrow);
-            xa[i] = ok ? cola[mrow] : 0.0;
-            xb[i] = ok ? colb[mrow] : 0.0;
+            const int p = rg + LEAF_NG * i;
+            xa[i] = ta[p];
+            xb[i] = tb[p];
         }
 #pragma unroll
         for (int i = 0; i < LEAF_BR; i += 2) {
-            long long mrow;
-            const bool ok = tm_row(tm, blk, body0 + i, mrow);
+            const int p = body0 + i;
+            const bool ok = (p - QB) < nv;
             double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-            if (ok) { va = *reinterpret_cast<const double2*>(cola + mrow); vb = *reinterpret_cast<const double2*>(colb + mrow); }
+            if (ok) { va = *reinterpret_cast<const double2*>(ta + p); vb = *reinterpret_cast<const double2*>(tb + p); }
             xa[2 + i] = va.x; xa[3 + i] = va.y;
             xb[2 + i] = vb.x; xb[3 + i] = vb.y;
         }
@@ -399,10 +465,11 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
     LEAF_T(200);
     if (trace_slot >= 0 && tid == 0) tbuf[trace_slot + 2] = gtimer_ns();
 
-    // ---- V (explicit diagonal entry, zeros above) to the workspace; R head back into the matrix ----
+    // ---- V (explicit diagonal entry, zeros above) to the workspace as ONE bulk store of its shared-memory image;
+    //      R head back into the matrix ----
     {
-        double* __restrict__ Va = tp.V[lev] + blk * (long long)(QB * QS) + (2 * cp) * QS;
-        double* __restrict__ Vbp = Va + QS;
+        double* Va = vt + (2 * cp) * QS;
+        double* Vbp = Va + QS;
         const int ca = 2 * cp, cbn = 2 * cp + 1;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -425,6 +492,12 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
                 Va[r] = xa[i];
                 Vbp[r] = xb[i];
             }
+        }
+        fence_async_smem();                  // generic-proxy writes -> visible to the bulk-copy engine
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(tp.V[lev] + blk * (long long)(QB * QS), smem_u32(vt), AM_VS_BYTES);
+            bulk_commit();
         }
     }
 
@@ -467,6 +540,7 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
             Tb[cc * QWS + k] = sm.Tm[k][cc];
         }
     }
+    if (tid == 0) bulk_wait0();             // the image must stay in shared memory until the copy engine is done with it
     LEAF_T(201);
     if (trace_slot >= 0 && tid == 0) tbuf[trace_slot + 3] = gtimer_ns();
 #undef LEAF_T
@@ -543,51 +617,9 @@ qr_apply_fma_kernel(double* __restrict__ A, long long ld, long long ctrail, int 
 // persistent CTAs, producer warp + 8 consumer warps, results stored by the consumers.
 // =================================================================================================
 #define AM_NST 2
-#define AM_VS_BYTES (QB * QS * 8)
 #define AM_XS_BYTES (QCT * QS * 8)
 #define QWP (QB + 8)    /* stride of the per-warp partial buffers: 16-byte stores of 8 lanes hit 32 distinct banks */
 #define AM_SMEM_BYTES (AM_VS_BYTES + AM_NST * AM_XS_BYTES + 8 * QCT * QWP * 8 + 2 * QCT * QWS * 8 + QB * QWS * 8 + 64)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c[0]), "+d"(c[1])
-                 : "d"(a), "d"(b));
-}
 
 template <bool ATIMING>
 __global__ void __launch_bounds__(288, 1)
@@ -1383,6 +1415,8 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_pp_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_tree_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_tree_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TREE_DSMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_tree_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TREE_DSMEM_BYTES));
         attr_done = true;
     }
     return LSO_OK;
@@ -1494,9 +1528,9 @@ static int launch_leaf_chain(lso_ctx* ctx, QRPlan* plan, int64_t c0, const Panel
     plan->ticket_base += (unsigned)total;       // unsigned wrap-around is harmless: ids are differences
     tp.zero_n = zero_n;
     if (g_leaf_tbuf && (pl.nblk[0] <= 64 || (getenv("LSO_TREE_TRACE") && c0 == QB)))
-        qr_tree_kernel_t<true><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);
+        qr_tree_kernel_t<true><<<total, LEAF_THREADS, TREE_DSMEM_BYTES, st>>>(plan->A, plan->ld, c0, tp, g_leaf_tbuf);
     else
-        qr_tree_kernel_t<false><<<total, LEAF_THREADS, 0, st>>>(plan->A, plan->ld, c0, tp, nullptr);
+        qr_tree_kernel_t<false><<<total, LEAF_THREADS, TREE_DSMEM_BYTES, st>>>(plan->A, plan->ld, c0, tp, nullptr);
     LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
 }
