@@ -476,8 +476,13 @@ qr_tree_kernel_t(double* __restrict__ A, long long ld, long long c0, TreeParams 
             const int r = rg + LEAF_NG * i;                       // head row
             Va[r] = (r >= ca) ? xa[i] : 0.0;
             Vbp[r] = (r >= cbn) ? xb[i] : 0.0;
-            heada[r] = (r < ca) ? xa[i] : ((r == ca) ? sm.rdiag[ca] : 0.0);
-            heada[ld + r] = (r < cbn) ? xb[i] : ((r == cbn) ? sm.rdiag[cbn] : 0.0);
+            if (!c.publish) {
+                // Only the ROOT writes its R into the matrix.  The head rows of the blocks below it are the same matrix
+                // rows (block b of every level heads at r0 + QB b); their R factors travel through the mailbox and nobody
+                // reads them from the matrix, and writing them would race with the root's write a few steps later.
+                heada[r] = (r < ca) ? xa[i] : ((r == ca) ? sm.rdiag[ca] : 0.0);
+                heada[ld + r] = (r < cbn) ? xb[i] : ((r == cbn) ? sm.rdiag[cbn] : 0.0);
+            }
         }
         if (!c.lazy) {
 #pragma unroll

@@ -332,3 +332,26 @@ def test_qr_many_panels(ctx, damped):
     xr, rank = O.qr_ldiv(Jh, yh, damp)
     assert rank == n and ws.last_rank == n
     assert rel(x.download(), xr) <= TOL
+
+
+def test_qr_bit_reproducible_when_all_tree_levels_run_concurrently(ctx):
+    """49 059 x 300: 192 + 24 + 3 + 1 tree blocks fit on the machine at once, so every level of the panel tree runs
+    concurrently from the first step on.  Regression test for a write race on the R head rows (block b of every tree
+    level heads at the same matrix rows; only the root may write them): six solves must agree bit for bit and with
+    the oracle."""
+    from lsob200 import DenseMatrix, DenseQRAllocatedSolver, DeviceVector
+    m, n = 49059, 300
+    Jh, yh, rng = make_J(m, n, 5)
+    for damped in (False, True):
+        dtd = np.einsum("ij,ij->j", Jh, Jh)
+        damp = dtd / 10.0 if damped else None
+        ws = DenseQRAllocatedSolver(ctx, m, n, damped=damped)
+        J, y, x = DenseMatrix(ctx, m, n, Jh), DeviceVector(ctx, m, yh), DeviceVector(ctx, n)
+        d = DeviceVector(ctx, n, damp) if damped else None
+        xs = []
+        for _ in range(6):
+            ws.ldiv(x, J, y, d)
+            xs.append(x.download())
+        assert all(np.array_equal(xs[0], v) for v in xs)
+        xr, _ = O.qr_ldiv(Jh, yh, damp)
+        assert rel(xs[0], xr) <= TOL
