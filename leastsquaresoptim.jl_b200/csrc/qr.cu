@@ -852,6 +852,7 @@ qr_apply_mma_kernel_t(double* __restrict__ A, long long ld, long long ctrail, in
 //                   X' += Wfin' V' (GEMM2).  A warp only ever touches its own row slice of the staged tile.
 // =================================================================================================
 #define PP_NST 4
+static_assert(PP_NST % 2 == 0, "a stage must always be used by the same consumer group: its full / out barriers are waited on by exactly one group per use, so that no phase is ever skipped");
 #define PP_GW 4                                     /* warps per consumer group (8 measured 8 % slower: more barrier skew) */
 #define PP_WR (QH / PP_GW)                           /* tile rows owned by one consumer warp */
 #define PP_GT (32 * PP_GW)                          /* threads per consumer group */
