@@ -57,12 +57,21 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *                  4 levels 0 and 1 one launch each and the levels above chained in one launch
  *   "qr_lookahead" 1 = panel trees on a second stream under the previous update (default 0)
  *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default)
+ *   "spmv"         0 first-generation warp-per-segment sparse products, 1 stream kernels (default)
+ *   "lsmr_fused"   0 LSMR with host-side scalars (3 syncs per iteration), 1 fused device-resident LSMR (default)
  *   "profile"      see lso_ctx_profile_read */
 int         lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value);
 int         lso_ctx_launch_count(lso_ctx* ctx, int64_t* out, int reset); /* kernels launched by this library */
 /* With option "profile" = 1 every launch of the dominant kernel of a solve (QR trailing update, syrk, SpMV pair) is
  * bracketed by CUDA events on the context stream; this returns their summed duration and count, and resets. */
 int         lso_ctx_profile_read(lso_ctx* ctx, double* total_ms, int64_t* launches);
+/* Algorithmic work issued through this context since the last reset (the numerators of bench.py's rooflines):
+ *   "qr_update_flops"  trailing-update flops of the QR factorisations (sum over panels of 4*32*active rows*trailing columns)
+ *   "qr_flops"         2 M n^2 - 2/3 n^3 per factorisation          "syrk_flops"  m n (n+1) per J'J
+ *   "spmv_bytes"       12 B per stored entry + 8 B per vector element per sparse product */
+int         lso_ctx_stat(lso_ctx* ctx, const char* key, double* out, int reset);
+/* second channel of the same option: the collective of a sharded solve (ncclAllReduce / ncclAllGather) */
+int         lso_ctx_profile_read_collective(lso_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* ---- device memory (Julia GC owns nothing on the device; finalizers call *_free) ----- */
 int lso_dev_alloc(lso_ctx* ctx, size_t nbytes, void** d_out);
@@ -140,9 +149,8 @@ int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* 
                  const double* d_damp, double* d_x, int* rank_out);
 /* ldiv!(x, J, y, damp, A::DenseCholeskyAllocatedSolver) — dense_cholesky.jl:43-59 (d_damp != NULL)
  * ldiv!(x, J, y, A::DenseCholeskyAllocatedSolver)       — dense_cholesky.jl:29-35 (d_damp == NULL)
- * When the context has a communicator (lso_comm_init_rank), J and y are this rank's row shard and
- * [J'J | J'y] is all-reduced over NCCL before the (replicated) factorisation.
- * Returns info > 0 when the matrix is not positive definite / rank deficient. */
+ * Always a LOCAL solve of the J it is given (also on a context that has a communicator); the row-sharded form is
+ * lso_chol_solve_sharded.  Returns info > 0 when the matrix is not positive definite / rank deficient. */
 int lso_chol_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                    const double* d_damp, double* d_x);
 /* Host-buffer forms (what `ldiv!` on plain Julia Arrays binds): copy J, y, damp H2D, solve, copy x D2H. */
@@ -159,6 +167,15 @@ int lso_comm_unique_id(void* id128 /* 128 bytes out */);
 int lso_comm_init_rank(lso_ctx* ctx, int nranks, int rank, const void* id128);
 int lso_comm_destroy(lso_ctx* ctx);
 int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count);
+/* Row-sharded Cholesky path (BASELINE.json configs[3]): every rank passes its row shard of J and y; the packed
+ * [upper(J'J) by columns | J'y] (n(n+1)/2 + n doubles) is summed by ONE ncclAllReduce per solve, the factorisation and
+ * the solves are replicated, all ranks get x.  Math of dense_cholesky.jl:43-59 / :29-35 on the whole J. */
+int lso_chol_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
+                           const double* d_damp, double* d_x);
+/* Test hook: the same algorithm (partial products per shard, packed, summed in rank order) with the P shards emulated on
+ * one device: d_J is (P * m) x n where m is the workspace's shard row count. */
+int lso_debug_chol_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,
+                                         const double* d_damp, double* d_x);
 /* TSQR over row shards for the QR path: every rank passes its shard of J and y; all ranks get x. */
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                          const double* d_damp, double* d_x, int* rank_out);
@@ -172,13 +189,30 @@ int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_
 int lso_csc_create(lso_ctx* ctx, int64_t m, int64_t n, int64_t nnz,
                    const int64_t* h_colptr_1based, const int64_t* h_rowval_1based, lso_csc** out);
 int lso_csc_destroy(lso_csc* A);
+/* g! changed the sparsity PATTERN (setindex! into a sparse J, test/nonlinearsolvers.jl:526-530): re-import colptr /
+ * rowval (same m, n; nnz may differ), rebuild the CSR mirror and the CTA partitions; values are zeroed. */
+int lso_csc_update_pattern(lso_csc* A, int64_t nnz, const int64_t* h_colptr_1based, const int64_t* h_rowval_1based);
 int lso_csc_set_values_host(lso_csc* A, const double* h_nzval);     /* after g!(J,x) wrote nonzeros(J) */
 int lso_csc_set_values_dev(lso_csc* A, const double* d_nzval);
 double* lso_csc_values(lso_csc* A);                                  /* device nzval (CSC order), writable by device g! */
 int lso_csc_values_changed(lso_csc* A);                              /* refresh the CSR mirror after writing lso_csc_values */
+/* A device g! may write BOTH images and skip the mirror gather (12 + 16 B per entry of random traffic):
+ * lso_csc_values_csr is nzval in CSR order (entry k of it is entry lso_csc_csr_perm[k] of lso_csc_values; int32, 0-based
+ * rowptr / colidx), lso_csc_values_changed_both declares both images current. lso_csc_gather_csr permutes any
+ * nnz-vector from CSC into CSR order (e.g. constant factors of the Jacobian, once per pattern). */
+double* lso_csc_values_csr(lso_csc* A);
+const int* lso_csc_csr_rowptr(lso_csc* A);
+const int* lso_csc_csr_colidx(lso_csc* A);
+const int* lso_csc_csr_perm(lso_csc* A);
+int lso_csc_values_changed_both(lso_csc* A);
+int lso_csc_gather_csr(lso_csc* A, const double* d_in_csc_order, double* d_out_csr_order);
 int lso_csc_mul_n(lso_csc* A, double alpha, const double* d_x, double beta, double* d_y);   /* y = α J x + β y  */
 int lso_csc_mul_t(lso_csc* A, double alpha, const double* d_y, double beta, double* d_x);   /* x = α J'y + β x  */
-int lso_csc_colsumabs2(lso_csc* A, double* d_out);
+int lso_csc_colsumabs2(lso_csc* A, double* d_out);                   /* cached per J (utils.jl:146-151) */
+/* fused: dtd = colsumabs2(J) and g = J'f in ONE pass over the CSC image (LM:82 + LM:102) */
+int lso_csc_colsumabs2_gemv_t(lso_csc* A, const double* d_f, double* d_dtd, double* d_g);
+/* fused: fpredict = J*δ - f ; *ssr_out = sum(abs2, fpredict)  (LM:114-117; dogleg:171-174). d_fpredict may be NULL. */
+int lso_csc_predicted_ssr(lso_csc* A, const double* d_delta, const double* d_f, double* d_fpredict, double* ssr_out);
 
 /* ---- LSMR solvers: src/solver/iterative_lsmr.jl:161-198 (undamped) and :221-259 (damped),
  *      running src/utils/lsmr.jl:53-238 on the device.  Exactly one of (A_csc) or (d_J, ld) is
@@ -194,6 +228,19 @@ int lso_lsmr_solve(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_J, int64_t l
                    const double* d_y, double* d_damp, double* d_x,
                    double atol, double btol, double conlim, int64_t maxiter,
                    int64_t* iters_out, int* istop_out);
+/* User preconditioner (README.md:47; iterative_lsmr.jl:143-145, 216-218: `preconditioner!(P, x, J, λ)` has been run
+ * by the caller): either d_P_diag, the vector of an InverseDiagonal (iterative_lsmr.jl:117-122; stays on the fused
+ * sparse path), or precond_apply, `ldiv!(out, P, in)` as a callback on device pointers that enqueues its work on
+ * lso_ctx_stream (generic path: the reference's wrappers op for op).  Both NULL = the default preconditioner. */
+typedef int (*lso_precond_fn)(void* user, int64_t n, const double* d_in, double* d_out);
+int lso_lsmr_solve_ex(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_J, int64_t ld,
+                      const double* d_y, double* d_damp, double* d_x,
+                      double atol, double btol, double conlim, int64_t maxiter,
+                      const double* d_P_diag, lso_precond_fn precond_apply, void* precond_user,
+                      int64_t* iters_out, int* istop_out);
+/* kernel launches and host synchronisations of the last solve on this workspace (lsmr.jl:116-231 runs on the device:
+ * 3 launches per iteration, at most one synchronisation per iteration) */
+int lso_lsmr_ws_stats(lso_lsmr_ws* ws, int64_t* launches_out, int64_t* syncs_out);
 
 /* ---- synthetic workload generators and residual models used by bench.py / tests
  *      (counter-based hash, bit-identical on CPU and GPU).  Harness, not boundary. ---- */
@@ -203,11 +250,14 @@ int lso_synth_vector(lso_ctx* ctx, int64_t n, int64_t offset, uint64_t seed, dou
 /* r = t + c t^2 - b with t = A x ;  J = diag(1 + 2 c t) A */
 int lso_synth_residual(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, int64_t ld, const double* d_x,
                        const double* d_b, double c, double* d_t, double* d_r);
+int lso_synth_residual_from_t(lso_ctx* ctx, int64_t m, const double* d_t, const double* d_b, double c, double* d_r);
 int lso_synth_jacobian(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, int64_t ld, const double* d_t,
                        double c, double* d_J, int64_t ldJ);
 int lso_synth_csc_pattern(int64_t m, int64_t n, int64_t nnz_per_col, uint64_t seed,
                           int64_t* h_colptr_1based, int64_t* h_rowval_1based); /* host, deterministic */
 int lso_synth_csc_jacobian(lso_csc* A, const double* d_Aval, const double* d_t, double c); /* nzval = (1+2c t[row]) * Aval */
+/* the same device g! writing both the CSC and the CSR image (d_Aval_csr = lso_csc_gather_csr of d_Aval) */
+int lso_synth_csc_jacobian_both(lso_csc* A, const double* d_Aval, const double* d_Aval_csr, const double* d_t, double c);
 
 /* ---- micro-benchmarks that give the roofline denominators this library reports against ---- */
 int lso_bench_fp64_mma_peak(lso_ctx* ctx, int iters, double* tflops_out);   /* DMMA m8n8k4 issue-bound loop */

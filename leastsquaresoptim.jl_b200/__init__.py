@@ -11,7 +11,7 @@ from ._lib import (DimensionMismatch, IsFiniteException, LsoError, PosDefExcepti
 from .device import Context, CSCMatrix, DenseMatrix, DeviceVector, wdot, wnorm
 from .solvers import (DenseCholeskyAllocatedSolver, DenseQRAllocatedSolver, LSMRAllocatedSolver,
                       LSMRDampenedAllocatedSolver)
-from .api import (LSMR, QR, Cholesky, Dogleg, LeastSquaresProblem, LeastSquaresResult, LevenbergMarquardt, LMRun, HostStep,
+from .api import (LSMR, QR, Cholesky, Dogleg, DoglegRun, LeastSquaresProblem, LeastSquaresResult, LevenbergMarquardt, LMRun, HostStep,
                   allocate, optimize, optimize_)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -52,7 +52,12 @@ class Cholesky(AbstractSolver):
 
 
 class LSMR(AbstractSolver):
-    pass
+    """`LSMR(preconditioner!, P)` (types.jl:81-85, README.md:47).  `preconditioner` is passed to the allocated solver:
+    None = default; a callable `(x, J, damp) -> DeviceVector` returning the vector of an InverseDiagonal; or a tuple
+    `(update(x, J, damp), apply(out_ptr, in_ptr, n))` for a general `ldiv!(out, P, in)`."""
+
+    def __init__(self, preconditioner=None):
+        self.preconditioner = preconditioner
 
 
 class AbstractOptimizer:
@@ -191,6 +196,7 @@ class _Allocated:
                 nls.J = nls.J.tocsc()
                 nls.J.sort_indices()
                 self.J = CSCMatrix.from_scipy(ctx, nls.J)
+                self._pattern = (nls.J.indptr.copy(), nls.J.indices.copy())
             else:
                 self.J = DenseMatrix(ctx, m, n)
             self._hx = np.empty(n)
@@ -204,6 +210,10 @@ class _Allocated:
         damped = isinstance(optimizer, LevenbergMarquardt)
         if sharded and getattr(ctx, "nranks", 1) <= 1:
             raise ValueError("sharded=True needs a communicator on the context (Context.comm_init)")
+        if sharded and (not damped or isinstance(solver, LSMR) or self.sparse):
+            # the row-sharded paths are LM(QR) (TSQR) and LM(Cholesky) (one all-reduce); Dogleg's m-dimension
+            # reductions are not all-reduced and LSMR stays single-GPU (BASELINE.json north_star)
+            raise ValueError("sharded=True is only implemented for LevenbergMarquardt with QR() or Cholesky() on a dense J")
         if isinstance(solver, QR):
             # row-sharded J: local QR of [J_k | y_k] needs the undamped m_k x n workspace; the sqrt(damp) rows join
             # the stack of R factors (lso_qr_solve_sharded)
@@ -211,9 +221,10 @@ class _Allocated:
         elif isinstance(solver, Cholesky):
             if self.sparse:
                 raise TypeError("MethodError: no Cholesky solver for sparse Jacobians (dense_cholesky.jl:19)")
-            self.solver = DenseCholeskyAllocatedSolver(ctx, m, n, damped)
+            self.solver = DenseCholeskyAllocatedSolver(ctx, m, n, damped, sharded=sharded)
         elif isinstance(solver, LSMR):
-            self.solver = LSMRDampenedAllocatedSolver(ctx, m, n) if damped else LSMRAllocatedSolver(ctx, m, n)
+            pc = getattr(solver, "preconditioner", None)
+            self.solver = (LSMRDampenedAllocatedSolver(ctx, m, n, pc) if damped else LSMRAllocatedSolver(ctx, m, n, pc))
         else:
             raise TypeError(f"unknown solver {solver!r}")
 
@@ -240,11 +251,26 @@ class _Allocated:
             x.download(self._hx)
             self.nls.g_(self.nls.J, self._hx)
             if self.sparse:
-                self.J.set_values(self.nls.J.data)
+                Jh = self.nls.J
+                if not Jh.has_sorted_indices:
+                    Jh.sort_indices()
+                if Jh.nnz != self.J.nnz or not self._same_pattern(Jh):
+                    # g! changed the sparsity pattern (setindex! into a sparse J, test/nonlinearsolvers.jl:526-530)
+                    self.J.update_pattern(Jh.indptr, Jh.indices, Jh.data)
+                    self._pattern = (Jh.indptr.copy(), Jh.indices.copy())
+                else:
+                    self.J.set_values(Jh.data)
             else:
                 self.J.upload(self.nls.J)
         else:
             self.nls.g_(self.J, x)
+
+    def _same_pattern(self, Jh) -> bool:
+        pat = getattr(self, "_pattern", None)
+        if pat is None:
+            self._pattern = pat = (Jh.indptr.copy(), Jh.indices.copy())
+            return True       # the device image was built from this very pattern in __init__
+        return np.array_equal(pat[0], Jh.indptr) and np.array_equal(pat[1], Jh.indices)
 
     def finish(self, x: DeviceVector):
         if self.host:
@@ -321,7 +347,7 @@ class LMRun:
         self.dx, self.dtd, self.ftrial, self.fpredict, self.red = w["dx"], w["dtd"], w["ftrial"], w["fpredict"], w["red"]
         self.grad = anls.workspace("lm_grad", lambda: dict(g=DeviceVector(ctx, n)))["g"]
         self.dlo, self.dhi = _bounds(ctx, anls.x, lower, upper)
-        self.sharded = getattr(ctx, "nranks", 1) > 1
+        self.sharded = bool(anls.sharded)       # ONE source of truth: the flag the problem was allocated with
         self.Δ = float(Δ)
         self.decrease_factor = 2.0
         self.f_calls = self.g_calls = self.mul_calls = 0
@@ -415,87 +441,116 @@ def _optimize_lm(anls: _Allocated, **kw):
 
 
 # ---- Dogleg (dogleg.jl:41-203) ---------------------------------------------------------------------------------
-def _optimize_dogleg(anls: _Allocated, x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, iterations=1000, Δ=1.0,
-                     store_trace=False, lower=None, upper=None, record_steps=False):
-    import ctypes as C
-    from ._lib import check, lib
-    ctx, n, m = anls.ctx, anls.n, anls.m
-    x, fcur, J = anls.x, anls.fcur, anls.J
-    dgn, dgr, dx, dtd = (DeviceVector(ctx, n) for _ in range(4))
-    ftrial, fpredict = DeviceVector(ctx, m), DeviceVector(ctx, m)
-    dlo, dhi = _bounds(ctx, x, lower, upper)
-    reuse = False
-    wnorm_dgn = wnorm_dgr = 0.0
-    α = 0.0
-    f_calls = g_calls = mul_calls = 0
-    converged = x_converged = f_converged = g_converged = False
-    anls.f(fcur, x)
-    f_calls += 1
-    ssr = fcur.sumabs2()
-    maxabs_gr = math.inf
-    it = 0
-    tr = [OptimizationState(0, ssr, maxabs_gr)] if store_trace else []
-    deltas = []
-    while not converged and it < iterations:
-        it += 1
+class DoglegRun:
+    """State of one `optimize!` run with Dogleg; `iterate()` is one pass of the `while` body (dogleg.jl:77-199)."""
+
+    def __init__(self, anls: "_Allocated", x_tol=1e-8, f_tol=1e-8, g_tol=1e-8, iterations=1000, Δ=1.0,
+                 store_trace=False, lower=None, upper=None, record_steps=False):
+        self.anls = anls
+        ctx, n, m = anls.ctx, anls.n, anls.m
+        self.ctx = ctx
+        self.x_tol, self.f_tol, self.g_tol, self.iterations = x_tol, f_tol, g_tol, iterations
+        self.store_trace, self.record_steps = store_trace, record_steps
+        # AllocatedDogleg (dogleg.jl:7-30): allocated once per problem, reused by every run on it
+        w = anls.workspace("dogleg", lambda: dict(dgn=DeviceVector(ctx, n), dgr=DeviceVector(ctx, n), dx=DeviceVector(ctx, n),
+                                                  dtd=DeviceVector(ctx, n), ftrial=DeviceVector(ctx, m),
+                                                  fpredict=DeviceVector(ctx, m)))
+        self.dgn, self.dgr, self.dx, self.dtd = w["dgn"], w["dgr"], w["dx"], w["dtd"]
+        self.ftrial, self.fpredict = w["ftrial"], w["fpredict"]
+        self.dlo, self.dhi = _bounds(ctx, anls.x, lower, upper)
+        self.Δ = float(Δ)
+        self.reuse = False
+        self.wnorm_dgn = self.wnorm_dgr = 0.0
+        self.α = 0.0
+        self.f_calls = self.g_calls = self.mul_calls = 0
+        self.converged = self.x_converged = self.f_converged = self.g_converged = False
+        anls.f(anls.fcur, anls.x)
+        self.f_calls += 1
+        self.ssr = anls.fcur.sumabs2()
+        self.maxabs_gr = math.inf
+        self.it = 0
+        self.tr = [OptimizationState(0, self.ssr, self.maxabs_gr)] if store_trace else []
+        self.deltas = []
+
+    def iterate(self):
+        import ctypes as C
+        from ._lib import check, lib
+        anls, ctx, n = self.anls, self.ctx, self.anls.n
+        x, fcur, J = anls.x, anls.fcur, anls.J
+        dgn, dgr, dx, dtd, ftrial, fpredict = self.dgn, self.dgr, self.dx, self.dtd, self.ftrial, self.fpredict
+        dlo, dhi = self.dlo, self.dhi
+        self.it += 1
         x.check_finite()
-        if not reuse:
+        if not self.reuse:
             anls.g(x)
-            g_calls += 1
+            self.g_calls += 1
             J.colsumabs2(dtd)                               # :85
             dtd.clamp(MIN_DIAGONAL, MAX_DIAGONAL)           # :90  (absolute floor, unlike LM)
-            if it == 1:
+            if self.it == 1:
                 wnorm_x = wnorm(x, dtd)
                 if wnorm_x > 0:
-                    Δ *= wnorm_x
+                    self.Δ *= wnorm_x
             J.mul_t(dgr, fcur, 1.0, 0.0)                    # :99
-            mul_calls += 1
-            maxabs_gr = _maxabs_projected_gradient(ctx, dgr, x, dlo, dhi)
+            self.mul_calls += 1
+            self.maxabs_gr = _maxabs_projected_gradient(ctx, dgr, x, dlo, dhi)
             dgr.div_(dgr, dtd)                              # :105  δgr = D⁻¹ g
-            wnorm_dgr = wnorm(dgr, dtd)
+            self.wnorm_dgr = wnorm(dgr, dtd)
             J.mul(fpredict, dgr, 1.0, 0.0)                  # :109
-            mul_calls += 1
+            self.mul_calls += 1
             denom = fpredict.sumabs2()
-            α = wnorm_dgr ** 2 / denom if denom != 0 else (math.nan if wnorm_dgr == 0 else math.inf)   # :111 (0/0 -> NaN)
+            w2 = self.wnorm_dgr ** 2
+            self.α = w2 / denom if denom != 0 else (math.nan if w2 == 0 else math.inf)   # :111 (0/0 -> NaN)
             dgn.fill(0.0)                                   # :114
             _, ls_iter = anls.solver.ldiv(dgn, J, fcur)     # :115
-            if record_steps:
-                deltas.append(dgn.download())
-            mul_calls += ls_iter
-            wnorm_dgn = wnorm(dgn, dtd)
+            if self.record_steps:
+                self.deltas.append(dgn.download())
+            self.mul_calls += ls_iter
+            self.wnorm_dgn = wnorm(dgn, dtd)
         # δx: Gauss-Newton inside / scaled Cauchy / dogleg blend (:120-145)
         out = C.c_double()
-        check(lib().lso_dogleg_blend(ctx.handle, n, dx.ptr, dgn.ptr, dgr.ptr, dtd.ptr, Δ, α, wnorm_dgn, wnorm_dgr,
-                                     C.byref(out)), ctx.handle)
+        check(lib().lso_dogleg_blend(ctx.handle, n, dx.ptr, dgn.ptr, dgr.ptr, dtd.ptr, self.Δ, self.α, self.wnorm_dgn,
+                                     self.wnorm_dgr, C.byref(out)), ctx.handle)
         wnorm_dx = out.value
         _box_project(ctx, dx, x, dlo, dhi)                  # :148-157
         x.axpy(-1.0, dx)                                    # :160
         anls.f(ftrial, x)
-        f_calls += 1
+        self.f_calls += 1
         trial_ssr = ftrial.sumabs2()
         predicted_ssr = J.predicted_ssr(dx, fcur, fpredict)  # :171-174
-        mul_calls += 1
+        self.mul_calls += 1
+        ssr = self.ssr
         predicted_reduction = abs(ssr - predicted_ssr)
         ρ = (ssr - trial_ssr) / predicted_reduction if predicted_reduction > 0 else 0.0
         step_accepted = ρ >= MIN_STEP_QUALITY
-        x_converged, f_converged, g_converged, converged = assess_convergence(
-            dx, maxabs_gr, ssr, trial_ssr, x_tol, f_tol, g_tol, step_accepted)
+        self.x_converged, self.f_converged, self.g_converged, self.converged = assess_convergence(
+            dx, self.maxabs_gr, ssr, trial_ssr, self.x_tol, self.f_tol, self.g_tol, step_accepted)
         if step_accepted:
-            reuse = False
+            self.reuse = False
             fcur.copyto(ftrial)
-            ssr = trial_ssr
+            self.ssr = trial_ssr
         else:
-            reuse = True
+            self.reuse = True
             x.axpy(1.0, dx)
         if ρ < DECREASE_THRESHOLD:
-            Δ = max(MIN_DELTA, Δ * 0.5)
+            self.Δ = max(MIN_DELTA, self.Δ * 0.5)
         elif ρ > INCREASE_THRESHOLD:
-            Δ = max(Δ, 3.0 * wnorm_dx)
-        if store_trace:
-            tr.append(OptimizationState(it, ssr, maxabs_gr))
-    xmin = anls.finish(x)
-    return LeastSquaresResult("Dogleg", xmin, ssr, it, converged, x_converged, x_tol, f_converged, f_tol,
-                              g_converged, g_tol, tr, f_calls, g_calls, mul_calls, deltas)
+            self.Δ = max(self.Δ, 3.0 * wnorm_dx)
+        if self.store_trace:
+            self.tr.append(OptimizationState(self.it, self.ssr, self.maxabs_gr))
+        return step_accepted
+
+    def result(self):
+        xmin = self.anls.finish(self.anls.x)
+        return LeastSquaresResult("Dogleg", xmin, self.ssr, self.it, self.converged, self.x_converged, self.x_tol,
+                                  self.f_converged, self.f_tol, self.g_converged, self.g_tol, self.tr, self.f_calls,
+                                  self.g_calls, self.mul_calls, self.deltas)
+
+
+def _optimize_dogleg(anls: _Allocated, **kw):
+    run = DoglegRun(anls, **kw)
+    while not run.converged and run.it < run.iterations:
+        run.iterate()
+    return run.result()
 
 
 class HostStep:
@@ -513,7 +568,7 @@ class HostStep:
                                               red=DeviceVector(ctx, 8)))
         self.dx, self.dtd, self.fpredict, self.red = w["dx"], w["dtd"], w["fpredict"], w["red"]
         self.grad = anls.workspace("lm_grad", lambda: dict(g=DeviceVector(ctx, n)))["g"]
-        self.sharded = getattr(ctx, "nranks", 1) > 1
+        self.sharded = bool(anls.sharded)
 
     def run(self, hJ_ptr: int, hf_ptr: int, Δ: float, dx_host: np.ndarray):
         a, ctx, h = self.anls, self.ctx, self.ctx.handle
@@ -543,6 +598,8 @@ class HostStep:
 def optimize_(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, **kwargs) -> LeastSquaresResult:
     """`optimize!(nls, optimizer; kwargs...)` — types.jl:207-209 + LeastSquaresProblemAllocated (:152-157)."""
     anls = nls if isinstance(nls, _Allocated) else allocate(nls, optimizer)
+    kwargs.pop("show_trace", None)      # printing the trace (utils.jl:116-128) is host-side display, off the path
+    kwargs.pop("show_every", None)
     if isinstance(anls.optimizer, LevenbergMarquardt):
         return _optimize_lm(anls, **kwargs)
     return _optimize_dogleg(anls, **kwargs)

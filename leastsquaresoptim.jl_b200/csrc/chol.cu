@@ -319,7 +319,7 @@ __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p) {
     *p = CholPlan();
-    LSO_REQUIRE(ctx, n <= 46000, "Cholesky path: n too large");
+    LSO_REQUIRE(ctx, n <= 24000, "Cholesky path: n too large (the single-CTA triangular solves hold the right-hand side in shared memory)");
     p->n = n;
     p->ldc = roundup64(n, 32);
     size_t cbytes = (size_t)(p->ldc * n + roundup64(n, 32)) * sizeof(double);
@@ -355,7 +355,18 @@ int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p) {
         LSO_CHECK_CUDA(ctx, cudaMemsetAsync(p->part, 0, pb, ctx->stream));
     }
     LSO_CHECK_CUDA(ctx, cudaMalloc(&p->d_info, sizeof(int)));
-    static bool attr_done = false;
+    {   // packed all-reduce buffer [upper(J'J) by columns | J'y]: n(n+1)/2 + n doubles, x2 for the
+        // emulated-shards test hook's running sum
+        const size_t pk = (size_t)(n * (n + 1) / 2 + n);
+        e = cudaMalloc(&p->packed, 2 * pk * sizeof(double));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return lso_set_error(ctx, LSO_ERR_ALLOC, "Cholesky all-reduce buffer: cudaMalloc(%zu): %s", 2 * pk * sizeof(double), cudaGetErrorString(e));
+        }
+        p->packed_len = (int64_t)pk;
+    }
+    static bool attr_done_dev[LSO_MAX_DEVICES] = {};      // function attributes are per device
+    bool& attr_done = attr_done_dev[ctx->device % LSO_MAX_DEVICES];
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(syrk_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(syrk_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
@@ -369,11 +380,13 @@ void chol_plan_destroy(CholPlan* p) {
     cudaFree(p->C);
     cudaFree(p->part);
     cudaFree(p->d_info);
+    cudaFree(p->packed);
     *p = CholPlan();
 }
 
 int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld) {
     const int64_t slab = p->ldc * n;
+    ctx->stat_syrk_flops += (double)m * (double)n * (double)(n + 1);
     int64_t ksplit = p->part_cap > 1 ? p->part_cap : 1;
     // keep every split at least a few chunks long
     while (ksplit > 1 && cdiv64(m, ksplit) < 4 * SY_KC) --ksplit;
@@ -429,12 +442,52 @@ extern "C" int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count
 extern "C" int lso_dense_gemv_t(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const double* d_J, int64_t ld,
                                 const double* d_y, double beta, double* d_x);
 
-int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
-               const double* d_damp, double* d_x) {
+// [upper(C) by columns | rhs]  <->  the ldc x n workspace.  MODE 0: pack, 1: unpack, 2: packed accumulate (dst += src)
+template <int MODE>
+__global__ void chol_pack_kernel(long long n, double* __restrict__ C, long long ldc, double* __restrict__ rhs,
+                                 double* __restrict__ packed, const double* __restrict__ src) {
+    const long long j = blockIdx.y;                       // column 0..n-1, n = the right-hand side
+    if (MODE == 2) {
+        const long long len = n * (n + 1) / 2 + n;
+        for (long long i = (blockIdx.y * (long long)gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < len;
+             i += (long long)gridDim.y * gridDim.x * blockDim.x)
+            packed[i] += src[i];
+        return;
+    }
+    if (j < n) {
+        double* __restrict__ pk = packed + j * (j + 1) / 2;
+        double* __restrict__ col = C + j * ldc;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= j; i += (long long)gridDim.x * blockDim.x) {
+            if (MODE == 0) pk[i] = col[i]; else col[i] = pk[i];
+        }
+    } else {
+        double* __restrict__ pk = packed + n * (n + 1) / 2;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            if (MODE == 0) pk[i] = rhs[i]; else rhs[i] = pk[i];
+        }
+    }
+}
+
+// local part: C (upper tiles) = J'J, rhs = J'y for this rank's rows
+static int chol_local(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y) {
+    lso_prof_mark(ctx);
     LSO_TRY(syrk_upper(ctx, p, m, n, d_J, ld));                               // mul!(cholm, J', J)
-    LSO_TRY(lso_dense_gemv_t(ctx, m, n, 1.0, d_J, ld, d_y, 0.0, p->rhs));      // mul!(x, J', y)
-    if (ctx->nranks > 1) LSO_TRY(lso_comm_allreduce_sum(ctx, p->C, p->ldc * n + n));
-    if (d_damp) {                                                             // cholm[i,i] += damp[i]
+    lso_prof_mark(ctx);
+    return lso_dense_gemv_t(ctx, m, n, 1.0, d_J, ld, d_y, 0.0, p->rhs);       // mul!(x, J', y)
+}
+static int chol_pack(lso_ctx* ctx, CholPlan* p, int mode, double* packed, const double* src) {
+    const int64_t n = p->n;
+    dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 16), (unsigned)(n + 1));
+    if (mode == 0) chol_pack_kernel<0><<<grid, 256, 0, ctx->stream>>>(n, p->C, p->ldc, p->rhs, packed, nullptr);
+    else if (mode == 1) chol_pack_kernel<1><<<grid, 256, 0, ctx->stream>>>(n, p->C, p->ldc, p->rhs, packed, nullptr);
+    else chol_pack_kernel<2><<<grid, 256, 0, ctx->stream>>>(n, p->C, p->ldc, p->rhs, packed, src);
+    LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}
+// cholm[i,i] += damp[i]; factor; two triangular solves
+static int chol_finish(lso_ctx* ctx, CholPlan* p, const double* d_damp, double* d_x) {
+    const int64_t n = p->n;
+    if (d_damp) {                                                             // dense_cholesky.jl:51-53
         add_diag_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, ctx->stream>>>(n, p->C, p->ldc, d_damp);
         LSO_CHECK_LAUNCH(ctx);
     }
@@ -448,4 +501,32 @@ int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_
     LSO_TRY(tri_solve(ctx, n, p->C, p->ldc, p->rhs, d_x, 1));   // R' z = J'y
     LSO_TRY(tri_solve(ctx, n, p->C, p->ldc, d_x, d_x, 0));      // R x = z
     return LSO_OK;
+}
+
+// sharded != 0: J, y are this rank's row shard; ONE all-reduce of the packed [upper(J'J) | J'y]
+int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
+               const double* d_damp, double* d_x, int sharded) {
+    LSO_TRY(chol_local(ctx, p, m, n, d_J, ld, d_y));
+    if (sharded && ctx->nranks > 1) {
+        LSO_TRY(chol_pack(ctx, p, 0, p->packed, nullptr));
+        lso_prof_mark2(ctx);
+        LSO_TRY(lso_comm_allreduce_sum(ctx, p->packed, p->packed_len));
+        lso_prof_mark2(ctx);
+        LSO_TRY(chol_pack(ctx, p, 1, p->packed, nullptr));
+    }
+    return chol_finish(ctx, p, d_damp, d_x);
+}
+
+// Test hook: the sharded algorithm with the P row shards emulated on ONE device: the P partial [upper(J'J) | J'y] are
+// formed one after the other, packed exactly as for the all-reduce, and summed in rank order.
+int chol_solve_emulated(lso_ctx* ctx, CholPlan* p, int P, int64_t ms, int64_t n, const double* d_J, int64_t ld,
+                        const double* d_y, const double* d_damp, double* d_x) {
+    double* sum = p->packed + p->packed_len;
+    for (int k = 0; k < P; ++k) {
+        LSO_TRY(chol_local(ctx, p, ms, n, d_J + (size_t)k * ms, ld, d_y + (size_t)k * ms));
+        LSO_TRY(chol_pack(ctx, p, 0, k == 0 ? sum : p->packed, nullptr));
+        if (k > 0) LSO_TRY(chol_pack(ctx, p, 2, sum, p->packed));
+    }
+    LSO_TRY(chol_pack(ctx, p, 1, sum, nullptr));
+    return chol_finish(ctx, p, d_damp, d_x);
 }

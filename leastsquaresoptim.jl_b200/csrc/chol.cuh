@@ -10,12 +10,16 @@ struct CholPlan {
     double* part = nullptr;   // split-K partial tiles
     int64_t part_cap = 0;     // number of n*ldc slabs available in part
     int* d_info = nullptr;
+    double* packed = nullptr; // 2 x packed_len: [upper(J'J) by columns | J'y], the all-reduce buffer (+ the test hook's running sum)
+    int64_t packed_len = 0;   // n(n+1)/2 + n
 };
 
 int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p);
 void chol_plan_destroy(CholPlan* p);
 int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
-               const double* d_damp, double* d_x);
+               const double* d_damp, double* d_x, int sharded);
+int chol_solve_emulated(lso_ctx* ctx, CholPlan* p, int P, int64_t ms, int64_t n, const double* d_J, int64_t ld,
+                        const double* d_y, const double* d_damp, double* d_x);
 // C (upper tiles) = J'J for the m x n column-major J
 int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld);
 // in-place upper Cholesky of p->C ; returns LAPACK info (0 ok, k>0: leading minor k not positive definite)

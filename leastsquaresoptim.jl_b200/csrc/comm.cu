@@ -60,6 +60,7 @@ static int nccl_load(lso_ctx* ctx) {
 
 extern "C" int lso_comm_allgather(lso_ctx* ctx, const double* d_send, double* d_recv, int64_t count) {
     LSO_REQUIRE(ctx, ctx && ctx->nccl_comm, "no communicator (call lso_comm_init_rank)");
+    LSO_ENTER(ctx);
     LSO_CHECK_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, (size_t)count, LSO_NCCL_FLOAT64, ctx->nccl_comm, ctx->stream));
     return LSO_OK;
 }
@@ -103,6 +104,7 @@ int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count) {
     LSO_REQUIRE(ctx, ctx && d_buf, "NULL pointer");
     if (ctx->nranks <= 1) return LSO_OK;
     LSO_REQUIRE(ctx, ctx->nccl_comm, "no communicator (call lso_comm_init_rank)");
+    LSO_ENTER(ctx);
     LSO_CHECK_NCCL(ctx, g_nccl.AllReduce(d_buf, d_buf, (size_t)count, LSO_NCCL_FLOAT64, LSO_NCCL_SUM, ctx->nccl_comm,
                                          ctx->stream));
     return LSO_OK;

@@ -4,11 +4,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/lsob200.h"
 
 #define LSO_NUM_SMS_DEFAULT 148
+#define LSO_MAX_DEVICES 64
 
 struct lso_ctx {
     int device = 0;
@@ -20,6 +22,11 @@ struct lso_ctx {
     double* d_scalars = nullptr;       // small device scalar slots
     double* h_scalars = nullptr;       // pinned mirror
     int64_t launches = 0;
+    // statistics (lso_ctx_stat): algorithmic work issued since the last reset
+    double stat_qr_update_flops = 0.0;  // trailing-update flops of the QR factorisations: sum over panels of 4*QB*rows*trailing columns
+    double stat_qr_flops = 0.0;         // 2 M n^2 - 2/3 n^3 per factorisation
+    double stat_syrk_flops = 0.0;       // m n (n + 1) per J'J
+    double stat_spmv_bytes = 0.0;       // 12 B per stored entry + 8 B per vector element, per sparse product
     std::string last_error;
     // options
     int64_t opt_qr_apply = 2;          // 0 = plain-FMA apply kernel, 1 = DMMA apply kernel, 2 = ping-pong DMMA kernel (one launch
@@ -28,9 +35,13 @@ struct lso_ctx {
                                        // latency-bound levels above chained in one launch (saves 0.05 ms per solve at C2)
     int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
     int64_t opt_qr_lookahead = 0;      // 1 = panel trees on a second stream under the previous update (+2% at C2)
+    int64_t opt_spmv = 1;              // 0 = first-generation warp-per-segment sparse products, 1 = stream kernels
+    int64_t opt_lsmr_fused = 1;        // 0 = LSMR scalars on the host, 1 = fused device-resident LSMR (sparse operator)
     int64_t opt_profile = 0;           // 1 = bracket every launch of the dominant kernel with CUDA events
     std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
     size_t prof_used = 0;
+    std::vector<cudaEvent_t> prof2_events;  // second channel: the collective of a sharded solve (all-reduce / all-gather)
+    size_t prof2_used = 0;
     // scratch of the rank-revealing small-R finish (qr_finish.cu), grown on demand
     double* d_finish = nullptr;
     size_t finish_cap = 0;
@@ -71,6 +82,17 @@ int lso_set_error(lso_ctx* ctx, int code, const char* fmt, ...);
         if (!(cond)) return lso_set_error((ctx), LSO_ERR_ARG, "%s (%s:%d)", msg, __FILE__, __LINE__); \
     } while (0)
 
+// Every entry point makes its context's device current first: a process may hold contexts on several GPUs
+// (cudaSetDevice is a no-op costing ~50 ns when the device is already current).
+#define LSO_ENTER(ctx)                                                                          \
+    do {                                                                                        \
+        if ((ctx) != nullptr) {                                                                 \
+            cudaError_t _e = cudaSetDevice((ctx)->device);                                      \
+            if (_e != cudaSuccess)                                                              \
+                return lso_set_error((ctx), LSO_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (ctx)->device, cudaGetErrorString(_e)); \
+        }                                                                                       \
+    } while (0)
+
 #define LSO_TRY(expr)                                                                           \
     do {                                                                                        \
         int _s = (expr);                                                                        \
@@ -86,6 +108,16 @@ static inline void lso_prof_mark(lso_ctx* ctx) {
         ctx->prof_events.push_back(e);
     }
     cudaEventRecord(ctx->prof_events[ctx->prof_used++], ctx->stream);
+}
+
+static inline void lso_prof_mark2(lso_ctx* ctx) {
+    if (!ctx->opt_profile) return;
+    if (ctx->prof2_used == ctx->prof2_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->prof2_events.push_back(e);
+    }
+    cudaEventRecord(ctx->prof2_events[ctx->prof2_used++], ctx->stream);
 }
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -72,6 +72,7 @@ int lso_ctx_destroy(lso_ctx* ctx) {
     cudaFree(ctx->d_finish);
     cudaFree(ctx->d_gemv);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->prof2_events) cudaEventDestroy(e);
     cudaFreeHost(ctx->h_scalars);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -82,6 +83,7 @@ const char* lso_last_error(lso_ctx* ctx) { return ctx ? ctx->last_error.c_str() 
 
 int lso_ctx_sync(lso_ctx* ctx) {
     LSO_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    LSO_ENTER(ctx);
     LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return LSO_OK;
 }
@@ -93,7 +95,9 @@ int lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "qr_apply")) ctx->opt_qr_apply = value;
     else if (!strcmp(key, "syrk")) ctx->opt_syrk = value;
     else if (!strcmp(key, "qr_lookahead")) ctx->opt_qr_lookahead = value;
-    else if (!strcmp(key, "profile")) { ctx->opt_profile = value; ctx->prof_used = 0; }
+    else if (!strcmp(key, "spmv")) ctx->opt_spmv = value;
+    else if (!strcmp(key, "lsmr_fused")) ctx->opt_lsmr_fused = value;
+    else if (!strcmp(key, "profile")) { ctx->opt_profile = value; ctx->prof_used = 0; ctx->prof2_used = 0; }
     else return lso_set_error(ctx, LSO_ERR_ARG, "unknown option '%s'", key);
     return LSO_OK;
 }
@@ -120,6 +124,35 @@ int lso_ctx_profile_read(lso_ctx* ctx, double* total_ms, int64_t* launches) {
     return LSO_OK;
 }
 
+int lso_ctx_stat(lso_ctx* ctx, const char* key, double* out, int reset) {
+    LSO_REQUIRE(ctx, ctx && key && out, "NULL pointer");
+    double* p = nullptr;
+    if (!strcmp(key, "qr_update_flops")) p = &ctx->stat_qr_update_flops;
+    else if (!strcmp(key, "qr_flops")) p = &ctx->stat_qr_flops;
+    else if (!strcmp(key, "syrk_flops")) p = &ctx->stat_syrk_flops;
+    else if (!strcmp(key, "spmv_bytes")) p = &ctx->stat_spmv_bytes;
+    else return lso_set_error(ctx, LSO_ERR_ARG, "unknown statistic '%s'", key);
+    *out = *p;
+    if (reset) *p = 0.0;
+    return LSO_OK;
+}
+
+int lso_ctx_profile_read_collective(lso_ctx* ctx, double* total_ms, int64_t* launches) {
+    LSO_REQUIRE(ctx, ctx && total_ms && launches, "NULL pointer");
+    LSO_ENTER(ctx);
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->prof2_used; i += 2) {
+        float ms = 0.f;
+        LSO_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof2_events[i], ctx->prof2_events[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(ctx->prof2_used / 2);
+    ctx->prof2_used = 0;
+    return LSO_OK;
+}
+
 // ---- memory -------------------------------------------------------------------------------------
 int lso_dev_alloc(lso_ctx* ctx, size_t nbytes, void** d_out) {
     LSO_REQUIRE(ctx, ctx && d_out, "ctx/d_out is NULL");
@@ -136,6 +169,7 @@ int lso_dev_alloc(lso_ctx* ctx, size_t nbytes, void** d_out) {
 int lso_dev_free(lso_ctx* ctx, void* d_ptr) {
     LSO_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     if (!d_ptr) return LSO_OK;
+    LSO_ENTER(ctx);
     LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     LSO_CHECK_CUDA(ctx, cudaFree(d_ptr));
     return LSO_OK;
@@ -143,6 +177,7 @@ int lso_dev_free(lso_ctx* ctx, void* d_ptr) {
 int lso_host_alloc_pinned(lso_ctx* ctx, size_t nbytes, void** h_out) {
     LSO_REQUIRE(ctx, ctx && h_out, "ctx/h_out is NULL");
     if (nbytes == 0) nbytes = 16;
+    LSO_ENTER(ctx);
     cudaError_t e = cudaMallocHost(h_out, nbytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -157,11 +192,13 @@ int lso_host_free_pinned(lso_ctx* ctx, void* h_ptr) {
 }
 int lso_upload_async(lso_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes) {
     LSO_REQUIRE(ctx, ctx && (nbytes == 0 || (d_dst && h_src)), "NULL pointer");
+    LSO_ENTER(ctx);
     if (nbytes) LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     return LSO_OK;
 }
 int lso_download_async(lso_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes) {
     LSO_REQUIRE(ctx, ctx && (nbytes == 0 || (h_dst && d_src)), "NULL pointer");
+    LSO_ENTER(ctx);
     if (nbytes) LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     return LSO_OK;
 }
@@ -178,6 +215,7 @@ int lso_upload_matrix(lso_ctx* ctx, double* d_dst, int64_t ld_dst, const double*
     LSO_REQUIRE(ctx, ctx && d_dst && h_src, "NULL pointer");
     LSO_REQUIRE(ctx, ld_dst >= rows && ld_src >= rows, "leading dimension < rows");
     if (rows == 0 || cols == 0) return LSO_OK;
+    LSO_ENTER(ctx);
     LSO_CHECK_CUDA(ctx, cudaMemcpy2DAsync(d_dst, ld_dst * sizeof(double), h_src, ld_src * sizeof(double),
                                           rows * sizeof(double), cols, cudaMemcpyHostToDevice, ctx->stream));
     return LSO_OK;
@@ -220,6 +258,7 @@ static int ew_launch(lso_ctx* ctx, int64_t n, double* out, const double* x, cons
     LSO_REQUIRE(ctx, n >= 0, "negative length");
     if (n == 0) return LSO_OK;
     LSO_REQUIRE(ctx, out != nullptr, "NULL vector");
+    LSO_ENTER(ctx);
     ew_kernel<OP><<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, out, x, y, a, b);
     LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
@@ -289,6 +328,7 @@ int rd_launch_dev(lso_ctx* ctx, int64_t n, const double* x, const double* y, con
                   const double* hi, double* d_out) {
     LSO_REQUIRE(ctx, n >= 0, "negative length");
     LSO_REQUIRE(ctx, n == 0 || x != nullptr, "NULL vector");
+    LSO_ENTER(ctx);
     int64_t g = cdiv64(n, 256 * 4);
     if (g < 1) g = 1;
     int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -424,6 +464,7 @@ int lso_vec_check_finite(lso_ctx* ctx, int64_t n, const double* d_x, int64_t* fi
     LSO_REQUIRE(ctx, ctx && first_bad, "ctx/first_bad is NULL");
     *first_bad = -1;
     if (n == 0) return LSO_OK;
+    LSO_ENTER(ctx);
     unsigned long long* d_first = (unsigned long long*)(ctx->d_scalars + 1);
     unsigned long long init = (unsigned long long)n;
     LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_first, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
@@ -444,6 +485,7 @@ int lso_vec_box_project(lso_ctx* ctx, int64_t n, double* d_delta, const double* 
     LSO_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     if (n == 0 || (!d_lower && !d_upper)) return LSO_OK;
     LSO_REQUIRE(ctx, d_delta && d_x, "NULL vector");
+    LSO_ENTER(ctx);
     box_project_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, d_delta, d_x, d_lower, d_upper);
     LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
@@ -452,6 +494,7 @@ int lso_vec_box_project(lso_ctx* ctx, int64_t n, double* d_delta, const double* 
 int lso_lm_damping(lso_ctx* ctx, int64_t n, double* d_dtd, double min_diag, double max_diag, double inv_delta) {
     LSO_REQUIRE(ctx, ctx && (n == 0 || d_dtd), "NULL pointer");
     if (n == 0) return LSO_OK;
+    LSO_ENTER(ctx);
     LSO_TRY(lso_dev_sum(ctx, n, d_dtd, ctx->d_scalars + 2));
     lm_damping_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(n, d_dtd, ctx->d_scalars + 2, min_diag, max_diag, inv_delta);
     LSO_CHECK_LAUNCH(ctx);

@@ -84,6 +84,7 @@ static int col_reduce(lso_ctx* ctx, int mode, int64_t m, int64_t n, const double
     if (n == 0) return LSO_OK;
     LSO_REQUIRE(ctx, J != nullptr, "J is NULL");
     LSO_REQUIRE(ctx, n <= 2147483647LL, "n too large");
+    LSO_ENTER(ctx);
     ColSplit cs = choose_split(ctx, m, n);
     const bool direct = (cs.nsplit == 1 && alpha == 1.0 && beta == 0.0);
     if (!direct) LSO_REQUIRE(ctx, 2 * (int64_t)cs.nsplit * n <= LSO_PARTIALS, "n too large for split reduction");
@@ -278,6 +279,7 @@ int lso_dense_gemv_n(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const dou
     LSO_REQUIRE(ctx, m >= 0 && n >= 0 && ld >= m, "bad dimensions");
     if (m == 0) return LSO_OK;
     LSO_REQUIRE(ctx, d_y && (n == 0 || (d_J && d_x)), "NULL pointer");
+    LSO_ENTER(ctx);
     const int cs = gemv_n_chunks(ctx, m, n);
     if (cs > 1) {
         double* part = nullptr;
@@ -303,6 +305,7 @@ int lso_dense_predicted_ssr(lso_ctx* ctx, int64_t m, int64_t n, const double* d_
     LSO_REQUIRE(ctx, m >= 0 && n >= 0 && ld >= m, "bad dimensions");
     if (m == 0) { *ssr_out = 0.0; return LSO_OK; }
     LSO_REQUIRE(ctx, d_f && (n == 0 || (d_J && d_delta)), "NULL pointer");
+    LSO_ENTER(ctx);
     int64_t g = cdiv64(m, 256);
     LSO_REQUIRE(ctx, g <= LSO_PARTIALS, "m too large");
     const int cs = gemv_n_chunks(ctx, m, n);

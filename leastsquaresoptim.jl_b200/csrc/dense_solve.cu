@@ -159,6 +159,7 @@ int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* 
     // dense_qr.jl:61 — the damped form needs the (m+n)-row workspace, the undamped form the m-row one
     LSO_REQUIRE(ctx, (d_damp != nullptr) == (ws->damped != 0), "length(u) should equal length(x) + length(y)");
     LSO_REQUIRE(ctx, ws->plan.M >= ws->n, "QR path requires rows >= columns (underdetermined systems are not supported)");
+    LSO_ENTER(ctx);
     LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, ws->n, d_J, ld, d_y, d_damp));
     LSO_TRY(qr_factor(ctx, &ws->plan));
     return qr_finish(ws, &ws->plan, d_x, rank_out);
@@ -196,7 +197,33 @@ int lso_chol_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double
     LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_CHOLESKY, "workspace was not created for Cholesky");
     LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
     LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
-    return chol_solve(ctx, &ws->chol, ws->m, ws->n, d_J, ld, d_y, d_damp, d_x);
+    LSO_ENTER(ctx);
+    return chol_solve(ctx, &ws->chol, ws->m, ws->n, d_J, ld, d_y, d_damp, d_x, 0);
+}
+
+// Row-sharded J (one rank per GPU): J, y are this rank's rows; [upper(J'J) | J'y] is summed over the ranks by ONE
+// NCCL all-reduce, the factorisation and the solves are replicated (no reference counterpart).
+int lso_chol_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
+                           double* d_x) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_CHOLESKY, "workspace was not created for Cholesky");
+    LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
+    LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
+    LSO_ENTER(ctx);
+    return chol_solve(ctx, &ws->chol, ws->m, ws->n, d_J, ld, d_y, d_damp, d_x, 1);
+}
+
+// Test hook: the sharded Cholesky algorithm with P shards of ws->m rows each emulated on one device (d_J is (P * m) x n).
+int lso_debug_chol_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,
+                                         const double* d_damp, double* d_x) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_CHOLESKY, "workspace was not created for Cholesky");
+    LSO_REQUIRE(ctx, P >= 1 && P <= 64 && d_J && d_y && d_x, "bad arguments");
+    LSO_REQUIRE(ctx, ld >= (int64_t)P * ws->m, "leading dimension < P * m");
+    LSO_ENTER(ctx);
+    return chol_solve_emulated(ctx, &ws->chol, P, ws->m, ws->n, d_J, ld, d_y, d_damp, d_x);
 }
 
 int lso_chol_solve_host(lso_dense_ws* ws, const double* h_J, int64_t ld, const double* h_y, const double* h_damp,
@@ -204,6 +231,7 @@ int lso_chol_solve_host(lso_dense_ws* ws, const double* h_J, int64_t ld, const d
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     lso_ctx* ctx = ws->ctx;
     LSO_REQUIRE(ctx, h_J && h_y && h_x, "NULL pointer");
+    LSO_ENTER(ctx);
     LSO_TRY(ensure_staging(ws, ld));
     LSO_TRY(lso_upload_matrix(ctx, ws->d_J, ws->m, h_J, ld, ws->m, ws->n));
     LSO_TRY(lso_upload_async(ctx, ws->d_y, h_y, ws->m * sizeof(double)));
@@ -217,6 +245,7 @@ int lso_dense_ws_get_factor(lso_dense_ws* ws, double* h_R) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     lso_ctx* ctx = ws->ctx;
     LSO_REQUIRE(ctx, h_R != nullptr, "NULL pointer");
+    LSO_ENTER(ctx);
     const int64_t n = ws->n;
     const double* src = (ws->kind == LSO_SOLVER_QR) ? ws->plan.A : ws->chol.C;
     const int64_t ld = (ws->kind == LSO_SOLVER_QR) ? ws->plan.ld : ws->chol.ldc;
@@ -317,12 +346,15 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     LSO_REQUIRE(ctx, ws->damped == 0, "sharded QR: create the workspace with damped = 0 (damping rows join the stack)");
     LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
     LSO_REQUIRE(ctx, ws->m >= ws->n, "sharded QR: each shard needs rows >= columns");
+    LSO_ENTER(ctx);
     const int64_t n = ws->n;
     const int P = ctx->nranks;
     LSO_TRY(shard_ensure_stack(ws, P));
     double* sendbuf = ws->d_gather + (size_t)P * n * (n + 1);
     LSO_TRY(shard_local_R(ws, d_J, ld, d_y, sendbuf));
+    lso_prof_mark2(ctx);
     LSO_TRY(lso_comm_allgather(ctx, sendbuf, ws->d_gather, n * (n + 1)));
+    lso_prof_mark2(ctx);
     return shard_stack_solve(ws, P, d_damp, d_x, rank_out);
 }
 
@@ -335,6 +367,7 @@ int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_
     LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && ws->damped == 0, "create the workspace for QR with damped = 0");
     LSO_REQUIRE(ctx, P >= 1 && P <= 64 && d_J && d_y && d_x, "bad arguments");
     LSO_REQUIRE(ctx, ws->m >= ws->n, "each shard needs rows >= columns");
+    LSO_ENTER(ctx);
     const int64_t n = ws->n;
     LSO_TRY(shard_ensure_stack(ws, P));
     for (int k = 0; k < P; ++k)

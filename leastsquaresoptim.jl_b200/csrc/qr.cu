@@ -1330,7 +1330,8 @@ int tri_solve(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, const doub
     if (n == 0) return LSO_OK;
     LSO_REQUIRE(ctx, n <= 24000, "triangular solve: n too large for the single-CTA kernel");
     size_t smem = (size_t)(n + 2 * 32 * 33) * 8;
-    static bool attr_done = false;
+    static bool attr_done_dev[LSO_MAX_DEVICES] = {};      // function attributes are per device
+    bool& attr_done = attr_done_dev[ctx->device % LSO_MAX_DEVICES];
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(tri_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(tri_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1411,7 +1412,8 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_rest[k], cudaEventDisableTiming));
         LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&plan->ev_next[k], cudaEventDisableTiming));
     }
-    static bool attr_done = false;
+    static bool attr_done_dev[LSO_MAX_DEVICES] = {};      // function attributes are per device
+    bool& attr_done = attr_done_dev[ctx->device % LSO_MAX_DEVICES];
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_apply_mma_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
@@ -1638,6 +1640,16 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
     g_tl_on = (getenv("LSO_QR_TIMELINE") != nullptr) && plan->M > 50000;
     const int64_t npanels = std::min<int64_t>(plan->Npad / QB, cdiv64(M, QB));   // no rows left beyond that
     if (npanels <= 0) return LSO_OK;
+    {   // algorithmic flops of this factorisation (bench.py roofline): the level-0 update of every panel, real columns only
+        PanelLevels pl;
+        for (int64_t k = 0; k < npanels; ++k) {
+            panel_levels(plan, k * QB, pl);
+            const int64_t trailing = plan->N + 1 - (k + 1) * QB;
+            if (trailing > 0) ctx->stat_qr_update_flops += 4.0 * QB * (double)pl.tm[0].rows * (double)trailing;
+        }
+        const double Mq = (double)M, Nq = (double)plan->N;
+        ctx->stat_qr_flops += 2.0 * Mq * Nq * Nq - 2.0 * Nq * Nq * Nq / 3.0;
+    }
     cudaStream_t U = ctx->stream, P = plan->panel_stream;
     const int LA = QB / QCT;      // tiles that make up the next panel's columns
     PanelLevels cur, nxt;

@@ -61,6 +61,17 @@ __global__ void synth_csc_jacobian_kernel(long long n, const int* __restrict__ c
     }
 }
 
+// CSR image of the same Jacobian: valr[k] = (1 + 2 c t[row]) * aval_csr[k], G lanes per row (rows are contiguous)
+template <int G>
+__global__ void synth_csr_jacobian_kernel(long long m, const int* __restrict__ rowptr, const double* __restrict__ aval_csr,
+                                          const double* __restrict__ t, double c, double* __restrict__ valr) {
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = gid / G;
+    if (i >= m) return;
+    const double w = __dadd_rn(1.0, __dmul_rn(2.0 * c, t[i]));
+    for (int k = rowptr[i] + (int)(gid % G); k < rowptr[i + 1]; k += G) valr[k] = __dmul_rn(w, aval_csr[k]);
+}
+
 // ---- peaks ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* __restrict__ out) {
     double c[8][2];
@@ -158,6 +169,7 @@ extern "C" {
 
 int lso_synth_dense_matrix(lso_ctx* ctx, int64_t m, int64_t n, int64_t row_offset, uint64_t seed, double* d_A, int64_t ld) {
     LSO_REQUIRE(ctx, ctx && d_A && ld >= m && m >= 1 && n >= 1, "bad arguments");
+    LSO_ENTER(ctx);
     dim3 grid((unsigned)std::min<int64_t>(cdiv64(m, 256), 128), (unsigned)n);
     synth_matrix_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, row_offset, seed, d_A, ld);
     LSO_CHECK_LAUNCH(ctx);
@@ -165,6 +177,7 @@ int lso_synth_dense_matrix(lso_ctx* ctx, int64_t m, int64_t n, int64_t row_offse
 }
 int lso_synth_vector(lso_ctx* ctx, int64_t n, int64_t offset, uint64_t seed, double scale, double* d_x) {
     LSO_REQUIRE(ctx, ctx && d_x && n >= 1, "bad arguments");
+    LSO_ENTER(ctx);
     synth_vector_kernel<<<(unsigned)std::min<int64_t>(cdiv64(n, 256), 4096), 256, 0, ctx->stream>>>(n, offset, seed, scale, d_x);
     LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
@@ -172,7 +185,16 @@ int lso_synth_vector(lso_ctx* ctx, int64_t n, int64_t offset, uint64_t seed, dou
 int lso_synth_residual(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, int64_t ld, const double* d_x,
                        const double* d_b, double c, double* d_t, double* d_r) {
     LSO_REQUIRE(ctx, ctx && d_A && d_x && d_b && d_t && d_r, "NULL pointer");
+    LSO_ENTER(ctx);
     LSO_TRY(lso_dense_gemv_n(ctx, m, n, 1.0, d_A, ld, d_x, 0.0, d_t));
+    synth_residual_kernel<<<(unsigned)std::min<int64_t>(cdiv64(m, 256), 4096), 256, 0, ctx->stream>>>(m, d_t, d_b, c, d_r);
+    LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}
+// r = t + c t^2 - b for a t = A x formed by the caller (sparse model: t comes from lso_csc_mul_n)
+int lso_synth_residual_from_t(lso_ctx* ctx, int64_t m, const double* d_t, const double* d_b, double c, double* d_r) {
+    LSO_REQUIRE(ctx, ctx && d_t && d_b && d_r && m >= 1, "bad arguments");
+    LSO_ENTER(ctx);
     synth_residual_kernel<<<(unsigned)std::min<int64_t>(cdiv64(m, 256), 4096), 256, 0, ctx->stream>>>(m, d_t, d_b, c, d_r);
     LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
@@ -180,6 +202,7 @@ int lso_synth_residual(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, in
 int lso_synth_jacobian(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, int64_t ld, const double* d_t, double c,
                        double* d_J, int64_t ldJ) {
     LSO_REQUIRE(ctx, ctx && d_A && d_t && d_J && ld >= m && ldJ >= m, "bad arguments");
+    LSO_ENTER(ctx);
     dim3 grid((unsigned)std::min<int64_t>(cdiv64(m, 256), 128), (unsigned)n);
     synth_jacobian_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, d_A, ld, d_t, c, d_J, ldJ);
     LSO_CHECK_LAUNCH(ctx);
@@ -202,14 +225,30 @@ int lso_synth_csc_jacobian(lso_csc* A, const double* d_Aval, const double* d_t, 
     if (!A) return lso_set_error(nullptr, LSO_ERR_ARG, "A is NULL");
     lso_ctx* ctx = A->ctx;
     LSO_REQUIRE(ctx, d_Aval && d_t, "NULL pointer");
+    LSO_ENTER(ctx);
     synth_csc_jacobian_kernel<<<(unsigned)cdiv64(A->n * 32, 256), 256, 0, ctx->stream>>>(A->n, A->d_colptr, A->d_rowidx, d_Aval, d_t, c, A->d_val);
     LSO_CHECK_LAUNCH(ctx);
     A->csr_dirty = true;
+    A->colsq_valid = false;
+    return LSO_OK;
+}
+// the same g! writing BOTH images (no mirror gather): d_Aval_csr = lso_csc_gather_csr(A, d_Aval), once per pattern
+int lso_synth_csc_jacobian_both(lso_csc* A, const double* d_Aval, const double* d_Aval_csr, const double* d_t, double c) {
+    if (!A) return lso_set_error(nullptr, LSO_ERR_ARG, "A is NULL");
+    lso_ctx* ctx = A->ctx;
+    LSO_REQUIRE(ctx, d_Aval && d_Aval_csr && d_t, "NULL pointer");
+    LSO_ENTER(ctx);
+    LSO_TRY(lso_synth_csc_jacobian(A, d_Aval, d_t, c));
+    if (A->Gr >= 8) synth_csr_jacobian_kernel<8><<<(unsigned)cdiv64(A->m * 8, 256), 256, 0, ctx->stream>>>(A->m, A->d_rowptr, d_Aval_csr, d_t, c, A->d_valr);
+    else synth_csr_jacobian_kernel<2><<<(unsigned)cdiv64(A->m * 2, 256), 256, 0, ctx->stream>>>(A->m, A->d_rowptr, d_Aval_csr, d_t, c, A->d_valr);
+    LSO_CHECK_LAUNCH(ctx);
+    A->csr_dirty = false;
     return LSO_OK;
 }
 
 int lso_bench_fp64_mma_peak(lso_ctx* ctx, int iters, double* tflops_out) {
     LSO_REQUIRE(ctx, ctx && tflops_out && iters > 0, "bad arguments");
+    LSO_ENTER(ctx);
     cudaEvent_t e0, e1;
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e0));
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e1));
@@ -229,6 +268,7 @@ int lso_bench_fp64_mma_peak(lso_ctx* ctx, int iters, double* tflops_out) {
 // mode 1: 8 warps / SM (the trailing-update kernel's occupancy), mode 2: 16 warps / SM, mode 3: 32 warps / SM
 int lso_bench_fp64_mma_pattern(lso_ctx* ctx, int iters, int mode, double* tflops_out) {
     LSO_REQUIRE(ctx, ctx && tflops_out && iters > 0, "bad arguments");
+    LSO_ENTER(ctx);
     cudaEvent_t e0, e1;
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e0));
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e1));
@@ -254,6 +294,7 @@ int lso_bench_fp64_mma_pattern(lso_ctx* ctx, int iters, int mode, double* tflops
 }
 int lso_bench_fp64_fma_peak(lso_ctx* ctx, int iters, double* tflops_out) {
     LSO_REQUIRE(ctx, ctx && tflops_out && iters > 0, "bad arguments");
+    LSO_ENTER(ctx);
     cudaEvent_t e0, e1;
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e0));
     LSO_CHECK_CUDA(ctx, cudaEventCreate(&e1));
@@ -272,6 +313,7 @@ int lso_bench_fp64_fma_peak(lso_ctx* ctx, int iters, double* tflops_out) {
 }
 int lso_bench_hbm_copy(lso_ctx* ctx, size_t nbytes, int iters, double* gbs_out) {
     LSO_REQUIRE(ctx, ctx && gbs_out && iters > 0 && nbytes >= 4096, "bad arguments");
+    LSO_ENTER(ctx);
     nbytes &= ~(size_t)15;
     double2 *a = nullptr, *b = nullptr;
     LSO_CHECK_CUDA(ctx, cudaMalloc(&a, nbytes));

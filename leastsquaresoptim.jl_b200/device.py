@@ -55,6 +55,17 @@ class Context:
         check(lib().lso_ctx_profile_read(self._h, C.byref(ms), C.byref(cnt)), self._h)
         return ms.value, cnt.value
 
+    def stat(self, key: str, reset: bool = False) -> float:
+        out = C.c_double()
+        check(lib().lso_ctx_stat(self._h, key.encode(), C.byref(out), int(reset)), self._h)
+        return out.value
+
+    def profile_read_collective(self):
+        """(total_ms, calls) of the event-bracketed collectives (all-reduce / all-gather) since the last read."""
+        ms, cnt = C.c_double(), C.c_int64()
+        check(lib().lso_ctx_profile_read_collective(self._h, C.byref(ms), C.byref(cnt)), self._h)
+        return ms.value, cnt.value
+
     # -- raw memory --
     def alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -292,11 +303,29 @@ class CSCMatrix:
         assert v.size == self.nnz
         check(lib().lso_csc_set_values_host(self._h, _np_ptr(v)), self.ctx.handle)
 
+    def update_pattern(self, colptr0: np.ndarray, rowidx0: np.ndarray, values=None):
+        """g! changed the sparsity pattern (setindex! into a sparse J, test/nonlinearsolvers.jl:526-530)."""
+        colptr = np.ascontiguousarray(colptr0, dtype=np.int64) + 1
+        rowval = np.ascontiguousarray(rowidx0, dtype=np.int64) + 1
+        self.nnz = int(rowval.size)
+        check(lib().lso_csc_update_pattern(self._h, self.nnz, _np_ptr(colptr), _np_ptr(rowval)), self.ctx.handle)
+        if values is not None:
+            self.set_values(values)
+
     def values_ptr(self) -> int:
         return lib().lso_csc_values(self._h)
 
-    def values_changed(self):
-        check(lib().lso_csc_values_changed(self._h), self.ctx.handle)
+    def values_csr_ptr(self) -> int:
+        return lib().lso_csc_values_csr(self._h)
+
+    def values_changed(self, both: bool = False):
+        """After a device g! wrote `values_ptr()` (and, with both=True, `values_csr_ptr()` as well)."""
+        fn = lib().lso_csc_values_changed_both if both else lib().lso_csc_values_changed
+        check(fn(self._h), self.ctx.handle)
+
+    def gather_csr(self, src: DeviceVector, dst: DeviceVector):
+        """dst (CSR order) = src (CSC order) permuted; once per pattern for constant Jacobian factors."""
+        check(lib().lso_csc_gather_csr(self._h, src.ptr, dst.ptr), self.ctx.handle)
 
     def colsumabs2(self, out: DeviceVector):
         check(lib().lso_csc_colsumabs2(self._h, out.ptr), self.ctx.handle)
@@ -308,10 +337,12 @@ class CSCMatrix:
         check(lib().lso_csc_mul_t(self._h, float(alpha), y.ptr, float(beta), x.ptr), self.ctx.handle)
 
     def colsumabs2_and_grad(self, dtd: DeviceVector, g: DeviceVector, f: DeviceVector):
-        self.colsumabs2(dtd)
-        self.mul_t(g, f, 1.0, 0.0)
+        """colsumabs2!(dtd, J) (LM:82) and mul!(g, J', f) (LM:102) in one pass over the CSC image."""
+        check(lib().lso_csc_colsumabs2_gemv_t(self._h, f.ptr, dtd.ptr, g.ptr), self.ctx.handle)
 
-    def predicted_ssr(self, delta: DeviceVector, f: DeviceVector, fpredict: DeviceVector) -> float:
-        self.mul(fpredict, delta, 1.0, 0.0)      # mul!(fpredict, J, δx, 1, 0)
-        fpredict.axpy(-1.0, f)                   # axpy!(-1, fcur, fpredict)
-        return fpredict.sumabs2()
+    def predicted_ssr(self, delta: DeviceVector, f: DeviceVector, fpredict: DeviceVector | None) -> float:
+        """mul!(fpredict, J, δx, 1, 0); axpy!(-1, fcur, fpredict); sum(abs2, fpredict)  (LM:114-117) in one launch."""
+        out = C.c_double()
+        check(lib().lso_csc_predicted_ssr(self._h, delta.ptr, f.ptr, fpredict.ptr if fpredict is not None else None,
+                                          C.byref(out)), self.ctx.handle)
+        return out.value

@@ -56,31 +56,65 @@ class DenseQRAllocatedSolver(_DenseWorkspace):
 class DenseCholeskyAllocatedSolver(_DenseWorkspace):
     """dense_cholesky.jl:19-21 (one n x n workspace for both optimizers)."""
 
-    def __init__(self, ctx: Context, m: int, n: int, damped: bool):
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool, sharded: bool = False):
         super().__init__(ctx, m, n, LSO_SOLVER_CHOLESKY, damped)
+        self.sharded = sharded      # J, y are this rank's row shard: one all-reduce of the packed [upper(J'J) | J'y]
 
     def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None):
-        check(lib().lso_chol_solve(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr),
+        fn = lib().lso_chol_solve_sharded if self.sharded else lib().lso_chol_solve
+        check(fn(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr),
               self.ctx.handle)
         return x, 1
 
 
+PRECOND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
 class _LSMRWorkspace:
-    def __init__(self, ctx: Context, m: int, n: int, damped: bool):
+    """`preconditioner` mirrors `LSMR(preconditioner!, P)` (types.jl:81-85, README.md:47):
+      None                       the default diagonal preconditioner 1/sqrt(colsumabs2(J) + damp) (iterative_lsmr.jl:130-138)
+      callable(x, J, damp) -> DeviceVector     `preconditioner!` producing the vector of an InverseDiagonal each solve
+      (callable(x, J, damp), apply(out_ptr, in_ptr, n))   a general P: `apply` is `ldiv!(out, P, in)` on device pointers"""
+
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool, preconditioner=None):
         self.ctx, self.m, self.n, self.damped = ctx, m, n, damped
         self._h = C.c_void_p()
         check(lib().lso_lsmr_ws_create(ctx.handle, m, n, int(damped), C.byref(self._h)), ctx.handle)
         self._fin = weakref.finalize(self, lib().lso_lsmr_ws_destroy, self._h)
         self.last_iters = 0
         self.last_istop = 0
+        self.preconditioner = preconditioner
+
+    def stats(self):
+        """(kernel launches, host synchronisations) of the last solve."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().lso_lsmr_ws_stats(self._h, C.byref(a), C.byref(b)), self.ctx.handle)
+        return a.value, b.value
 
     def _solve(self, x, J, y, damp, atol, btol, conlim, maxiter):
         iters, istop = C.c_int64(), C.c_int()
         csc = J.handle if isinstance(J, CSCMatrix) else None
         dj = J.ptr if isinstance(J, DenseMatrix) else None
         ld = J.ld if isinstance(J, DenseMatrix) else 0
-        check(lib().lso_lsmr_solve(self._h, csc, dj, ld, y.ptr, damp.ptr if damp is not None else None, x.ptr,
-                                   atol, btol, conlim, maxiter, C.byref(iters), C.byref(istop)), self.ctx.handle)
+        pdiag, pfn, keep = None, None, None
+        if self.preconditioner is not None:
+            if isinstance(self.preconditioner, tuple):
+                update, apply = self.preconditioner
+                update(x, J, damp)                       # preconditioner!(P, x, J, damp)
+
+                def _cb(user, n, d_in, d_out):
+                    try:
+                        apply(d_out, d_in, n)
+                        return 0
+                    except Exception:
+                        return 1
+                keep = PRECOND_FN(_cb)
+                pfn = C.cast(keep, C.c_void_p)
+            else:
+                pdiag = self.preconditioner(x, J, damp).ptr
+        check(lib().lso_lsmr_solve_ex(self._h, csc, dj, ld, y.ptr, damp.ptr if damp is not None else None, x.ptr,
+                                      atol, btol, conlim, maxiter, pdiag, pfn, None, C.byref(iters), C.byref(istop)),
+              self.ctx.handle)
         self.last_iters, self.last_istop = iters.value, istop.value
         return x, 2 * iters.value      # ch.mvps = 2 * iter (lsmr.jl:236)
 
@@ -88,8 +122,8 @@ class _LSMRWorkspace:
 class LSMRAllocatedSolver(_LSMRWorkspace):
     """iterative_lsmr.jl:161-198 — undamped, lsmr! defaults atol = btol = 1e-6, conlim = 1e8 (lsmr.jl:53-55)."""
 
-    def __init__(self, ctx, m, n):
-        super().__init__(ctx, m, n, False)
+    def __init__(self, ctx, m, n, preconditioner=None):
+        super().__init__(ctx, m, n, False, preconditioner)
 
     def ldiv(self, x, J, y, damp=None):
         assert damp is None
@@ -99,8 +133,8 @@ class LSMRAllocatedSolver(_LSMRWorkspace):
 class LSMRDampenedAllocatedSolver(_LSMRWorkspace):
     """iterative_lsmr.jl:221-259 — damped, btol = 0.5 (:255); `damp` is overwritten by sqrt(damp) (:252)."""
 
-    def __init__(self, ctx, m, n):
-        super().__init__(ctx, m, n, True)
+    def __init__(self, ctx, m, n, preconditioner=None):
+        super().__init__(ctx, m, n, True, preconditioner)
 
     def ldiv(self, x, J, y, damp):
         return self._solve(x, J, y, damp, 1e-6, 0.5, 1e8, 0)

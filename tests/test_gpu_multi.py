@@ -47,8 +47,12 @@ def _worker(rank, world, port, out):
     xr, _ = O.qr_ldiv(Jh, yh, damp.copy())
     L.DenseQRAllocatedSolver(ctx, rows, n, damped=False, sharded=True).ldiv(x, Jk, yk, d)
     res["qr"] = float(np.linalg.norm(x.download() - xr) / np.linalg.norm(xr))
-    L.DenseCholeskyAllocatedSolver(ctx, rows, n, damped=True).ldiv(x, Jk, yk, d)
+    L.DenseCholeskyAllocatedSolver(ctx, rows, n, damped=True, sharded=True).ldiv(x, Jk, yk, d)
     res["chol"] = float(np.linalg.norm(x.download() - xr) / np.linalg.norm(xr))
+    # a REPLICATED (non-sharded) problem on a context that has a communicator stays local: no all-reduce, same answer
+    Jf, yf = L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh)
+    L.DenseCholeskyAllocatedSolver(ctx, m, n, damped=True).ldiv(x, Jf, yf, d)
+    res["chol_local"] = float(np.linalg.norm(x.download() - xr) / np.linalg.norm(xr))
     # ---- sharded LM(QR) and LM(Cholesky) on the synthetic model vs the oracle on the whole problem ----
     m, n, seed = 8000, 64, 31337
     model = S.DenseModel(m, n, seed, c=0.1, noise=1e-3)
@@ -77,7 +81,7 @@ def test_sharded_solves_and_lm(world):
     mp.spawn(_worker, args=(world, 29700 + os.getpid() % 1000, out), nprocs=world, join=True)
     for rank in range(world):
         res = out[rank]
-        assert res["qr"] <= 1e-10 and res["chol"] <= 1e-10, res
+        assert res["qr"] <= 1e-10 and res["chol"] <= 1e-10 and res["chol_local"] <= 1e-10, res
         for k in ("lm_qr", "lm_chol"):
             it, it_ref, err, conv = res[k]
             assert conv and it == it_ref and err <= 1e-9, (k, res[k])

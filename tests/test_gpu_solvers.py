@@ -290,6 +290,38 @@ def test_qr_sharded_algorithm_emulated_on_one_gpu(ctx, P, ms, n, damped):
     assert rel(xg, xr) <= TOL, rel(xg, xr)
 
 
+@pytest.mark.parametrize("P", [2, 3, 8])
+@pytest.mark.parametrize("ms,n,damped", [(700, 64, True), (5000, 257, True), (3000, 96, False), (40, 40, True)])
+def test_cholesky_sharded_algorithm_emulated_on_one_gpu(ctx, P, ms, n, damped):
+    """The multi-GPU Cholesky path of BASELINE.json configs[3] (per-shard syrk + gemv, packed [upper(J'J) | J'y], summed over
+    the shards in rank order = what the single ncclAllReduce does, replicated potrf + solves) with the P shards emulated on
+    one device: same δ as the oracle's dense_cholesky.jl:43-59 on the whole J."""
+    import ctypes as C
+    from lsob200 import DenseCholeskyAllocatedSolver, DenseMatrix, DeviceVector
+    from lsob200._lib import check, lib
+    m = P * ms
+    Jh, yh, rng = make_J(m, n, 13 * m + n + P, scaled=False)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0 if damped else None
+    ws = DenseCholeskyAllocatedSolver(ctx, ms, n, damped=damped)
+    J, y, x = DenseMatrix(ctx, m, n, Jh), DeviceVector(ctx, m, yh), DeviceVector(ctx, n)
+    d = DeviceVector(ctx, n, damp) if damped else None
+    for rep in range(2):
+        check(lib().lso_debug_chol_solve_emulated_shards(ws._h, P, J.ptr, J.ld, y.ptr, d.ptr if d is not None else None, x.ptr),
+              ctx.handle)
+        xg = x.download()
+        if rep == 0:
+            x0 = xg.copy()
+    assert np.array_equal(xg, x0)
+    xr = O.chol_ldiv(Jh, yh, damp.copy() if damped else None)
+    assert rel(xg, xr) <= TOL, rel(xg, xr)
+    # and the un-sharded solve of the same system agrees with it
+    wsf = DenseCholeskyAllocatedSolver(ctx, m, n, damped=damped)
+    wsf.ldiv(x, J, y, d)
+    assert rel(x.download(), xg) <= 1e-11
+
+
+
 def test_qr_and_cholesky_at_the_bench_shape(ctx):
     """BASELINE.json configs[1] at full size (100 000 x 1 000, power-of-two column scales as in the bench's synthetic
     model): the damped QR solve against the oracle's dgelsy (‖δ_gpu − δ_ref‖/‖δ_ref‖ ≤ 1e-10, the north-star tolerance),
