@@ -172,10 +172,22 @@ int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count);
  * the solves are replicated, all ranks get x.  Math of dense_cholesky.jl:43-59 / :29-35 on the whole J. */
 int lso_chol_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                            const double* d_damp, double* d_x);
+/* (f3) re-solve of a rejected step: J'J and J'f of the last lso_chol_solve / lso_chol_solve_sharded (kept packed,
+ * before damping) with a new damping — no pass over J, no collective (levenberg_marquardt.jl:77-87). */
+int lso_chol_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x);
 /* Test hook: the same algorithm (partial products per shard, packed, summed in rank order) with the P shards emulated on
  * one device: d_J is (P * m) x n where m is the workspace's shard row count. */
 int lso_debug_chol_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,
                                          const double* d_damp, double* d_x);
+/* (f3) Re-solves of a rejected trust-region step (levenberg_marquardt.jl:77-87 solves again with the same J and f and a
+ * new damping; the reference refactors everything, dense_qr.jl:64-88).  lso_qr_factor_keep does the QR of [J | y] once
+ * and keeps the n x (n+1) block [R_J | Q'y]; lso_qr_solve_kept solves min ||[J; sqrt(D)] x - [y; 0]|| from it by a QR
+ * of the banded 2n x n stack [R_J; sqrt(D)] (cost independent of m; d_damp == NULL solves the undamped problem).  On a
+ * row-sharded workspace the factors gathered by the last lso_qr_solve_sharded are kept: the re-solve has no collective.
+ * lso_qr_kept_invalidate: J or y changed. */
+int lso_qr_factor_keep(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y);
+int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* rank_out);
+int lso_qr_kept_invalidate(lso_dense_ws* ws);
 /* TSQR over row shards for the QR path: every rank passes its shard of J and y; all ranks get x. */
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                          const double* d_damp, double* d_x, int* rank_out);

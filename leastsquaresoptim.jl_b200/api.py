@@ -378,6 +378,7 @@ class LMRun:
         dx, dtd, ftrial, fpredict = self.dx, self.dtd, self.ftrial, self.fpredict
         self.it += 1
         x.check_finite()
+        same_J = not self.need_jacobian       # a rejected step: J and fcur are what the previous solve saw (:77-87)
         if self.need_jacobian:
             anls.g(x)
             self.g_calls += 1
@@ -389,7 +390,7 @@ class LMRun:
             ctx.allreduce(dtd)
             ctx.allreduce(self.grad)
         _lm_damping(ctx, dtd, 1 / self.Δ)                     # :84-86
-        _, lmiter = anls.solver.ldiv(dx, J, fcur, dtd)        # :87
+        _, lmiter = anls.solver.ldiv(dx, J, fcur, dtd, same_J=same_J)        # :87
         if self.record_steps:
             self.deltas.append(dx.download())
         _box_project(ctx, dx, x, self.dlo, self.dhi)          # :89-98

@@ -503,17 +503,28 @@ static int chol_finish(lso_ctx* ctx, CholPlan* p, const double* d_damp, double* 
     return LSO_OK;
 }
 
-// sharded != 0: J, y are this rank's row shard; ONE all-reduce of the packed [upper(J'J) | J'y]
+// sharded != 0: J, y are this rank's row shard; ONE all-reduce of the packed [upper(J'J) | J'y].
+// The packed [upper(J'J) | J'y] (before damping) stays in p->packed: chol_solve_kept re-solves from it.
 int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
                const double* d_damp, double* d_x, int sharded) {
+    p->kept = false;
     LSO_TRY(chol_local(ctx, p, m, n, d_J, ld, d_y));
+    LSO_TRY(chol_pack(ctx, p, 0, p->packed, nullptr));
     if (sharded && ctx->nranks > 1) {
-        LSO_TRY(chol_pack(ctx, p, 0, p->packed, nullptr));
         lso_prof_mark2(ctx);
         LSO_TRY(lso_comm_allreduce_sum(ctx, p->packed, p->packed_len));
         lso_prof_mark2(ctx);
         LSO_TRY(chol_pack(ctx, p, 1, p->packed, nullptr));
     }
+    p->kept = true;
+    return chol_finish(ctx, p, d_damp, d_x);
+}
+
+// (f3) re-solve of a rejected trust-region step (levenberg_marquardt.jl:77-87: same J and f, new damping): J'J and J'f
+// of the last chol_solve are unpacked again; no pass over J, no collective.
+int chol_solve_kept(lso_ctx* ctx, CholPlan* p, const double* d_damp, double* d_x) {
+    LSO_REQUIRE(ctx, p->kept, "no J'J kept: call lso_chol_solve first");
+    LSO_TRY(chol_pack(ctx, p, 1, p->packed, nullptr));
     return chol_finish(ctx, p, d_damp, d_x);
 }
 
@@ -522,6 +533,7 @@ int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_
 int chol_solve_emulated(lso_ctx* ctx, CholPlan* p, int P, int64_t ms, int64_t n, const double* d_J, int64_t ld,
                         const double* d_y, const double* d_damp, double* d_x) {
     double* sum = p->packed + p->packed_len;
+    p->kept = false;
     for (int k = 0; k < P; ++k) {
         LSO_TRY(chol_local(ctx, p, ms, n, d_J + (size_t)k * ms, ld, d_y + (size_t)k * ms));
         LSO_TRY(chol_pack(ctx, p, 0, k == 0 ? sum : p->packed, nullptr));

@@ -12,12 +12,14 @@ struct CholPlan {
     int* d_info = nullptr;
     double* packed = nullptr; // 2 x packed_len: [upper(J'J) by columns | J'y], the all-reduce buffer (+ the test hook's running sum)
     int64_t packed_len = 0;   // n(n+1)/2 + n
+    bool kept = false;        // packed holds [upper(J'J) | J'y] of the last solve (before damping)
 };
 
 int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p);
 void chol_plan_destroy(CholPlan* p);
 int chol_solve(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_y,
                const double* d_damp, double* d_x, int sharded);
+int chol_solve_kept(lso_ctx* ctx, CholPlan* p, const double* d_damp, double* d_x);
 int chol_solve_emulated(lso_ctx* ctx, CholPlan* p, int P, int64_t ms, int64_t n, const double* d_J, int64_t ld,
                         const double* d_y, const double* d_damp, double* d_x);
 // C (upper tiles) = J'J for the m x n column-major J

@@ -23,6 +23,9 @@ struct lso_dense_ws {
     double* d_damp = nullptr;
     double* d_x = nullptr;
     int last_rank = 0;
+    // (f3) factor kept across the re-solves of a rejected trust-region step: [R_J | Q'y] of the last lso_qr_factor_keep /
+    // sharded solve lives in d_gather; valid until J or y change
+    bool kept = false;
 };
 
 // ---- Q-a: build [J; diag(sqrt(damp)) | y; 0] in the padded workspace (dense_qr.jl:32-36, 64-80) ----
@@ -214,6 +217,15 @@ int lso_chol_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, cons
     return chol_solve(ctx, &ws->chol, ws->m, ws->n, d_J, ld, d_y, d_damp, d_x, 1);
 }
 
+// (f3) re-solve with the J'J and J'f of the last lso_chol_solve / lso_chol_solve_sharded and a new damping
+int lso_chol_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_CHOLESKY && d_x, "bad arguments");
+    LSO_ENTER(ctx);
+    return chol_solve_kept(ctx, &ws->chol, d_damp, d_x);
+}
+
 // Test hook: the sharded Cholesky algorithm with P shards of ws->m rows each emulated on one device (d_J is (P * m) x n).
 int lso_debug_chol_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,
                                          const double* d_damp, double* d_x) {
@@ -299,7 +311,11 @@ static int shard_local_R(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     lso_ctx* ctx = ws->ctx;
     const int64_t n = ws->n;
     LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, n, d_J, ld, d_y, nullptr));
-    LSO_TRY(qr_factor(ctx, &ws->plan));
+    const int64_t M_full = ws->plan.M;
+    ws->plan.M = ws->m;               // a damped workspace has m + n rows: only the m rows of J are in use here
+    const int st = qr_factor(ctx, &ws->plan);
+    ws->plan.M = M_full;
+    LSO_TRY(st);
     dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 64), (unsigned)(n + 1));
     pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, ws->plan.A, ws->plan.ld, ws->plan.Npad, slot);
     LSO_CHECK_LAUNCH(ctx);
@@ -355,7 +371,45 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     lso_prof_mark2(ctx);
     LSO_TRY(lso_comm_allgather(ctx, sendbuf, ws->d_gather, n * (n + 1)));
     lso_prof_mark2(ctx);
+    ws->kept = true;
     return shard_stack_solve(ws, P, d_damp, d_x, rank_out);
+}
+
+// (f3) levenberg_marquardt.jl:77-87: after a REJECTED step the reference solves again with the same J and f and a new
+// damping, and refactors everything.  Here the QR of [J | y] is done once per Jacobian:
+//   lso_qr_factor_keep   J = Q R_J : keeps the n x (n+1) block [R_J | Q'y]  (cost of one undamped factorisation)
+//   lso_qr_solve_kept    QR of the interleaved 2n x n stack [R_J ; sqrt(D) | Q'y ; 0]  (banded: n^3-scale, independent of m)
+// which is the same least-squares problem as QR of [J ; sqrt(D) | y ; 0] (dense_qr.jl:64-88).  On a row-sharded
+// workspace the gathered factors of the last lso_qr_solve_sharded are what is kept: a re-solve needs no local
+// factorisation and NO collective.
+int lso_qr_factor_keep(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR, "workspace was not created for QR");
+    LSO_REQUIRE(ctx, d_J && d_y, "NULL pointer");
+    LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
+    LSO_REQUIRE(ctx, ws->m >= ws->n, "kept-factor path needs rows >= columns");
+    LSO_ENTER(ctx);
+    ws->kept = false;
+    LSO_TRY(shard_ensure_stack(ws, 1));
+    LSO_TRY(shard_local_R(ws, d_J, ld, d_y, ws->d_gather));
+    ws->kept = true;
+    return LSO_OK;
+}
+
+int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* rank_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && d_x, "bad arguments");
+    LSO_REQUIRE(ctx, ws->kept && ws->have_stack, "no factor kept: call lso_qr_factor_keep (or lso_qr_solve_sharded) first");
+    LSO_ENTER(ctx);
+    return shard_stack_solve(ws, ws->stack_P, d_damp, d_x, rank_out);
+}
+
+int lso_qr_kept_invalidate(lso_dense_ws* ws) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    ws->kept = false;
+    return LSO_OK;
 }
 
 // Test hook: the sharded algorithm with the P shards emulated on ONE device (the rows of J are cut into P equal

@@ -37,33 +37,71 @@ class _DenseWorkspace:
 
 
 class DenseQRAllocatedSolver(_DenseWorkspace):
-    """dense_qr.jl: Dogleg{QR} workspace (m x n, :25-28) or LevenbergMarquardt{QR} workspace ((m+n) x n, :50-54)."""
+    """dense_qr.jl: Dogleg{QR} workspace (m x n, :25-28) or LevenbergMarquardt{QR} workspace ((m+n) x n, :50-54).
 
-    def __init__(self, ctx: Context, m: int, n: int, damped: bool, sharded: bool = False):
+    `reuse` (f3; levenberg_marquardt.jl:77-87 re-solves with the same J and f after a rejected step):
+      "lazy"    a fresh J is solved by the direct QR of [J; sqrt(D)]; the FIRST re-solve with the same J factors J once
+                (lso_qr_factor_keep) and every re-solve costs only the banded 2n x n stack QR (lso_qr_solve_kept)
+      "always"  every fresh J is factored undamped and finished through the stack
+      "off"     every solve refactors, like the reference
+    On a row-sharded workspace the gathered R factors are always kept: a re-solve has no local QR and no collective."""
+
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool, sharded: bool = False, reuse: str = "lazy"):
         super().__init__(ctx, m, n, LSO_SOLVER_QR, damped)
         self.last_rank = n
         self.sharded = sharded      # J, y are this rank's row shard: TSQR over the context's communicator
+        self.reuse = reuse if m >= n else "off"
+        self._kept = False
+        self.solves_direct = self.solves_kept = self.factor_keeps = 0
 
-    def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None):
+    def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None, same_J: bool = False):
         rank = C.c_int()
-        fn = lib().lso_qr_solve_sharded if self.sharded else lib().lso_qr_solve
-        check(fn(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr, C.byref(rank)),
-              self.ctx.handle)
+        h = self.ctx.handle
+        dptr = damp.ptr if damp is not None else None
+        use_keep = self.reuse != "off" and damp is not None
+        if use_keep and same_J and self._kept:
+            check(lib().lso_qr_solve_kept(self._h, dptr, x.ptr, C.byref(rank)), h)
+            self.solves_kept += 1
+        elif self.sharded:
+            check(lib().lso_qr_solve_sharded(self._h, J.ptr, J.ld, y.ptr, dptr, x.ptr, C.byref(rank)), h)
+            self._kept = True
+            self.solves_direct += 1
+        elif use_keep and (same_J or self.reuse == "always"):
+            check(lib().lso_qr_factor_keep(self._h, J.ptr, J.ld, y.ptr), h)
+            check(lib().lso_qr_solve_kept(self._h, dptr, x.ptr, C.byref(rank)), h)
+            self._kept = True
+            self.factor_keeps += 1
+            self.solves_kept += 1
+        else:
+            check(lib().lso_qr_solve(self._h, J.ptr, J.ld, y.ptr, dptr, x.ptr, C.byref(rank)), h)
+            self._kept = False
+            self.solves_direct += 1
         self.last_rank = rank.value
         return x, 1
 
 
 class DenseCholeskyAllocatedSolver(_DenseWorkspace):
-    """dense_cholesky.jl:19-21 (one n x n workspace for both optimizers)."""
+    """dense_cholesky.jl:19-21 (one n x n workspace for both optimizers).  After a rejected step (same J and f, new
+    damping) the kept J'J and J'f are re-used: no pass over J, no collective (`reuse=False` refactors like the reference)."""
 
-    def __init__(self, ctx: Context, m: int, n: int, damped: bool, sharded: bool = False):
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool, sharded: bool = False, reuse: bool = True):
         super().__init__(ctx, m, n, LSO_SOLVER_CHOLESKY, damped)
         self.sharded = sharded      # J, y are this rank's row shard: one all-reduce of the packed [upper(J'J) | J'y]
+        self.reuse = reuse
+        self._kept = False
+        self.solves_direct = self.solves_kept = 0
 
-    def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None):
+    def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None, same_J: bool = False):
+        dptr = damp.ptr if damp is not None else None
+        if self.reuse and same_J and self._kept:
+            check(lib().lso_chol_solve_kept(self._h, dptr, x.ptr), self.ctx.handle)
+            self.solves_kept += 1
+            return x, 1
         fn = lib().lso_chol_solve_sharded if self.sharded else lib().lso_chol_solve
-        check(fn(self._h, J.ptr, J.ld, y.ptr, damp.ptr if damp is not None else None, x.ptr),
-              self.ctx.handle)
+        self._kept = False
+        check(fn(self._h, J.ptr, J.ld, y.ptr, dptr, x.ptr), self.ctx.handle)
+        self._kept = True
+        self.solves_direct += 1
         return x, 1
 
 
@@ -111,7 +149,8 @@ class _LSMRWorkspace:
                 keep = PRECOND_FN(_cb)
                 pfn = C.cast(keep, C.c_void_p)
             else:
-                pdiag = self.preconditioner(x, J, damp).ptr
+                keep = self.preconditioner(x, J, damp)   # keep the vector alive until the solve has been enqueued and read back
+                pdiag = keep.ptr
         check(lib().lso_lsmr_solve_ex(self._h, csc, dj, ld, y.ptr, damp.ptr if damp is not None else None, x.ptr,
                                       atol, btol, conlim, maxiter, pdiag, pfn, None, C.byref(iters), C.byref(istop)),
               self.ctx.handle)
@@ -125,7 +164,7 @@ class LSMRAllocatedSolver(_LSMRWorkspace):
     def __init__(self, ctx, m, n, preconditioner=None):
         super().__init__(ctx, m, n, False, preconditioner)
 
-    def ldiv(self, x, J, y, damp=None):
+    def ldiv(self, x, J, y, damp=None, same_J=False):
         assert damp is None
         return self._solve(x, J, y, None, 1e-6, 1e-6, 1e8, 0)
 
@@ -136,5 +175,5 @@ class LSMRDampenedAllocatedSolver(_LSMRWorkspace):
     def __init__(self, ctx, m, n, preconditioner=None):
         super().__init__(ctx, m, n, True, preconditioner)
 
-    def ldiv(self, x, J, y, damp):
+    def ldiv(self, x, J, y, damp, same_J=False):
         return self._solve(x, J, y, damp, 1e-6, 0.5, 1e8, 0)

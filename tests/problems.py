@@ -501,3 +501,105 @@ def bounds_cases():
         ("upper_active", fhi, ghi, np.array([0.0, 1.0]), dict(upper=[2.0, 100.0], x_tol=1e-50, f_tol=1e-50),
          np.array([2.0, 2.0])),
     ]
+
+
+# NIST StRD nonlinear regression (test/nonlinearfitting.jl:6-1472) --------------------------------------
+# Numbers (observations, NIST start columns, NIST certified values) come from tests/golden/nist_strd.json, frozen
+# from the reference's test file by oracle/make_golden_nist.py.  The models below are the `f(x, beta)` lines of
+# that file (cited per entry); the residual is ff!(fcur, x, f, data): fcur[i] = y[i] - f(x[i], beta)
+# (test/nonlinearfitting.jl:1448-1452).  The reference differentiates f with ForwardDiff (exact derivatives up to
+# rounding, types.jl:54-66); here the Jacobian d fcur / d beta = -d f / d beta is written out analytically.
+def _nist_models():
+    e = np.exp
+
+    def misra1a(x, b):          # :28   b1*(1-exp(-b2*x))
+        E = e(-b[1] * x)
+        return b[0] * (1 - E), [1 - E, b[0] * x * E]
+
+    def chwirut(x, b):          # :98, :327   exp(-b1*x)/(b2+b3*x)
+        E, D = e(-b[0] * x), b[1] + b[2] * x
+        return E / D, [-x * E / D, -E / D ** 2, -x * E / D ** 2]
+
+    def lanczos3(x, b):         # :369   b1*exp(-b2*x) + b3*exp(-b4*x) + b5*exp(-b6*x)
+        E1, E2, E3 = e(-b[1] * x), e(-b[3] * x), e(-b[5] * x)
+        return b[0] * E1 + b[2] * E2 + b[4] * E3, [E1, -b[0] * x * E1, E2, -b[2] * x * E2, E3, -b[4] * x * E3]
+
+    def gauss(x, b):            # :658, :928   b1*exp(-b2*x) + b3*exp(-(x-b4)^2/b5^2) + b6*exp(-(x-b7)^2/b8^2)
+        E1 = e(-b[1] * x)
+        d2, d3 = x - b[3], x - b[6]
+        E2, E3 = e(-d2 ** 2 / b[4] ** 2), e(-d3 ** 2 / b[7] ** 2)
+        return (b[0] * E1 + b[2] * E2 + b[5] * E3,
+                [E1, -b[0] * x * E1, E2, b[2] * E2 * 2 * d2 / b[4] ** 2, b[2] * E2 * 2 * d2 ** 2 / b[4] ** 3,
+                 E3, b[5] * E3 * 2 * d3 / b[7] ** 2, b[5] * E3 * 2 * d3 ** 2 / b[7] ** 3])
+
+    def danwood(x, b):          # :958   b1*x^b2
+        p = x ** b[1]
+        return b[0] * p, [p, b[0] * p * np.log(x)]
+
+    def misra1b(x, b):          # :989   b1*(1 - 1/(1+b2*x/2)^2)
+        q = 1 + b[1] * x / 2
+        return b[0] * (1 - 1 / q ** 2), [1 - 1 / q ** 2, b[0] * x / q ** 3]
+
+    def mgh09(x, b):            # :1019  b1*(x^2+x*b2)/(x^2+x*b3+b4)
+        N, D = x ** 2 + x * b[1], x ** 2 + x * b[2] + b[3]
+        return b[0] * N / D, [N / D, b[0] * x / D, -b[0] * N * x / D ** 2, -b[0] * N / D ** 2]
+
+    def thurber(x, b):          # :1081  (b1+b2x+b3x^2+b4x^3)/(1+b5x+b6x^2+b7x^3)
+        N = b[0] + b[1] * x + b[2] * x ** 2 + b[3] * x ** 3
+        D = 1 + b[4] * x + b[5] * x ** 2 + b[6] * x ** 3
+        return N / D, [1 / D, x / D, x ** 2 / D, x ** 3 / D, -N * x / D ** 2, -N * x ** 2 / D ** 2, -N * x ** 3 / D ** 2]
+
+    def rat42(x, b):            # :1140  b1/(1+exp(b2-b3*x))
+        E = e(b[1] - b[2] * x)
+        return b[0] / (1 + E), [1 / (1 + E), -b[0] * E / (1 + E) ** 2, b[0] * x * E / (1 + E) ** 2]
+
+    def mgh10(x, b):            # :1173  b1*exp(b2/(x+b3))
+        E = e(b[1] / (x + b[2]))
+        return b[0] * E, [E, b[0] * E / (x + b[2]), -b[0] * E * b[1] / (x + b[2]) ** 2]
+
+    def eckerle4(x, b):         # :1227  b1/b2*exp(-(x-b3)^2/(2*b2^2))
+        d = x - b[2]
+        E = e(-d ** 2 / (2 * b[1] ** 2))
+        return b[0] / b[1] * E, [E / b[1], b[0] * E * (d ** 2 / b[1] ** 4 - 1 / b[1] ** 2), b[0] / b[1] * E * d / b[1] ** 2]
+
+    def rat43(x, b):            # :1263  b1/(1+exp(b2-b3*x))^(1/b4)
+        E = e(b[1] - b[2] * x)
+        q = 1 + E
+        P = q ** (-1 / b[3])
+        return b[0] * P, [P, -b[0] * P * E / (b[3] * q), b[0] * P * x * E / (b[3] * q), b[0] * P * np.log(q) / b[3] ** 2]
+
+    def bennett5(x, b):         # :1442  b1*(b2+x)^(-1/b3)
+        q = b[1] + x
+        P = q ** (-1 / b[2])
+        return b[0] * P, [P, -b[0] * P / (b[2] * q), b[0] * P * np.log(q) / b[2] ** 2]
+
+    return {"misra1a": misra1a, "Chwirut2": chwirut, "Chwirut1": chwirut, "Lanczos3": lanczos3, "Gauss1": gauss,
+            "Gauss2": gauss, "DanWood": danwood, "Misra1b": misra1b, "MGH09": mgh09, "Thurber": thurber,
+            "BoxBOD": misra1a, "Rat42": rat42, "MGH10": mgh10, "Eckerle4": eckerle4, "Rat43": rat43,
+            "Bennet5": bennett5}        # BoxBOD (:1112) has misra1a's model; "Bennet5" is the file's own spelling (:1278)
+
+
+def nist_strd():
+    """[(name, f_, g_, [start columns], certified, m)] for the 16 datasets the reference's loop runs (:1455)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nist_strd.json")) as fh:
+        blob = json.load(fh)
+    models = _nist_models()
+    out = []
+    for p in blob["problems"]:
+        model = models[p["name"]]
+        xs, ys = np.array(p["x"]), np.array(p["y"])
+
+        def f(fcur, beta, model=model, xs=xs, ys=ys):
+            with np.errstate(all="ignore"):
+                fcur[:] = ys - model(xs, beta)[0]
+
+        def g(J, beta, model=model, xs=xs):
+            with np.errstate(all="ignore"):
+                cols = model(xs, beta)[1]
+            for k, c in enumerate(cols):
+                J[:, k] = -c
+
+        out.append((p["name"], f, g, [np.array(s) for s in p["starts"]], np.array(p["certified"]), len(ys)))
+    return out

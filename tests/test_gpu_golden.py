@@ -60,7 +60,9 @@ def test_runs_match_golden(ctx):
         assert (r.iterations, r.f_calls, r.g_calls, r.mul_calls) == (e["iterations"], e["f_calls"], e["g_calls"], e["mul_calls"])
         assert rel(r.minimizer, e["minimizer"]) <= 1e-9
         checked += 1
-    mism = 0
+    import json as _json
+    allowed = _json.load(open(os.path.join(G, "iteration_allowlist.json")))
+    mism = {}
     for i, (name, f, g, x0) in enumerate(P.minpack_cholesky()):
         for opt in ("dogleg", "lm"):
             e = gold[f"minpack_cholesky/{i:02d}_{name}_{x0.size}/{opt}"]
@@ -68,6 +70,8 @@ def test_runs_match_golden(ctx):
             r = L.optimize_(L.LeastSquaresProblem(x=x0.copy(), y=np.zeros(n), f_=f, g_=g, J=np.zeros((n, n), order="F")),
                             optc[opt](L.Cholesky()))
             assert r.converged == e["converged"] and r.ssr <= 1e-3
-            mism += (r.iterations != e["iterations"])
+            if r.iterations != e["iterations"]:
+                mism[f"{opt}/{name}_{n}"] = (r.iterations, e["iterations"])
             checked += 1
-    assert mism <= checked // 4, mism
+    unexpected = {k: v for k, v in mism.items() if k.split("/", 1)[1] not in allowed.get(f"minpack/{k.split('/')[0]}/cholesky/dense", {})}
+    assert not unexpected, unexpected

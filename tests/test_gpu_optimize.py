@@ -59,23 +59,51 @@ def test_readme_rosenbrock(ctx, opt):
     assert _replay_solves(ctx, ro, "qr", opt == "lm") <= 1e-10
 
 
+def _allowlist():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "iteration_allowlist.json")) as fh:
+        return json.load(fh)
+
+
 @pytest.mark.parametrize("solver,dense", [("qr", True), ("lsmr", True), ("lsmr", False), ("cholesky", True)])
 @pytest.mark.parametrize("opt", ["lm", "dogleg"])
 def test_minpack(opt, solver, dense):
-    """test/nonlinearsolvers.jl:505-537, :573-595 — ssr <= 1e-3 (and converged for Cholesky) on the GPU path;
-    iteration counts compared with the oracle."""
+    """test/nonlinearsolvers.jl:505-537, :573-595 — ssr <= 1e-3 (and converged for Cholesky) on the GPU path, and the
+    SAME outer-iteration count as the oracle on the same (x0, f!, g!).  The only runs allowed to differ are the ones
+    NAMED, each with its reason, in tests/golden/iteration_allowlist.json (problems whose Jacobian is singular or
+    numerically singular at the solution, where the last iterations are decided by rounding in f(x) itself)."""
     probs = P.minpack_cholesky() if solver == "cholesky" else P.minpack_all()
-    mismatched = []
+    allowed = _allowlist().get(f"minpack/{opt}/{solver}/{'dense' if dense else 'csc'}", {})
+    mismatched = {}
     for name, f, g, x0 in probs:
         rg, ro = _run_pair(f, g, x0, x0.size, opt, solver, J_dense=dense)
         assert rg.ssr <= 1e-3, (name, x0.size, rg.ssr)
         if solver == "cholesky":
             assert rg.converged, name
         if rg.iterations != ro.iterations:
-            mismatched.append((name, x0.size, rg.iterations, ro.iterations))
-    # well-conditioned problems must agree exactly; a few MINPACK problems are singular at the solution
-    # (powell_singular, watson, chebyquad, brown) where rounding decides the last iterations
-    assert len(mismatched) <= len(probs) // 3, mismatched
+            mismatched[f"{name}_{x0.size}"] = (rg.iterations, ro.iterations)
+    unexpected = {k: v for k, v in mismatched.items() if k not in allowed}
+    assert not unexpected, f"iteration counts differ from the oracle on runs that are not allow-listed: {unexpected}"
+
+
+@pytest.mark.parametrize("opt", ["lm", "dogleg"])
+def test_nist_strd(opt):
+    """test/nonlinearfitting.jl:1457-1472 through the GPU plugin: the reference's @test (no NaN) holds, the run ends
+    within 1e-3 of NIST's certified values on exactly the (dataset, start) pairs where the oracle does
+    (tests/test_oracle_pins.py pins those to the certified values), and the minimizers of the two paths agree."""
+    import lsob200 as L
+    from test_oracle_pins import NIST_KW, NIST_MISSES
+    optc = {"dogleg": L.Dogleg, "lm": L.LevenbergMarquardt}[opt]
+    for name, f, g, starts, cert, m in P.nist_strd():
+        for j, x0 in enumerate(starts):
+            n = cert.size
+            with np.errstate(all="ignore"):
+                r = L.optimize_(L.LeastSquaresProblem(x=x0.copy(), y=np.zeros(m), f_=f, g_=g, J=np.zeros((m, n), order="F")),
+                                optc(L.QR()), **NIST_KW)
+            assert not np.isnan(np.mean(r.minimizer)), (name, j)
+            ok = np.linalg.norm(r.minimizer - cert) <= 1e-3
+            assert ok == ((opt, name, j) not in NIST_MISSES), (opt, name, j, np.linalg.norm(r.minimizer - cert))
 
 
 @pytest.mark.parametrize("opt", ["lm", "dogleg"])

@@ -1,5 +1,7 @@
 """GPU parity of the three solver plugins (`ldiv!`) against the oracle on identical (J, y, damp):
 ||δ_gpu − δ_ref|| / ||δ_ref|| <= 1e-10 per linear solve (BASELINE.json north_star)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -387,3 +389,68 @@ def test_qr_bit_reproducible_when_all_tree_levels_run_concurrently(ctx):
         assert all(np.array_equal(xs[0], v) for v in xs)
         xr, _ = O.qr_ldiv(Jh, yh, damp)
         assert rel(xs[0], xr) <= TOL
+
+
+# ---- (f3) factor once, re-solve per damping (levenberg_marquardt.jl:77-87) ------------------------------------------
+@pytest.mark.parametrize("m,n", [(4000, 96), (20000, 520), (100000, 1000)])
+def test_qr_kept_factor_resolves(ctx, m, n):
+    """lso_qr_factor_keep + lso_qr_solve_kept (QR of the banded stack [R_J; sqrt(D)]) give the δ of the direct QR of
+    [J; sqrt(D)] for several dampings of the same J, to 1e-10 of the oracle; the undamped re-solve too."""
+    import lsob200 as L
+    from lsob200._lib import check, lib
+    rng = np.random.default_rng(m + n)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)) * (1.0 + 10.0 * rng.random(n)))
+    yh = rng.standard_normal(m)
+    J, y, x = L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh), L.DeviceVector(ctx, n)
+    ws = L.DenseQRAllocatedSolver(ctx, m, n, damped=True)
+    check(lib().lso_qr_factor_keep(ws._h, J.ptr, J.ld, y.ptr), ctx.handle)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    rank = C.c_int()
+    for delta in (10.0, 2.5, 1e-3):
+        damp = dtd / delta
+        d = L.DeviceVector(ctx, n, damp)
+        check(lib().lso_qr_solve_kept(ws._h, d.ptr, x.ptr, C.byref(rank)), ctx.handle)
+        xr, _ = O.qr_ldiv(Jh, yh, damp)
+        assert rank.value == n
+        assert rel(x.download(), xr) <= 1e-10, (delta, rel(x.download(), xr))
+    check(lib().lso_qr_solve_kept(ws._h, None, x.ptr, C.byref(rank)), ctx.handle)
+    xr, _ = O.qr_ldiv(Jh, yh, None)
+    assert rel(x.download(), xr) <= 1e-10
+    # the direct path on the same (damped) workspace is unaffected by the kept factor
+    d = L.DeviceVector(ctx, n, dtd / 10.0)
+    ws.ldiv(x, J, y, d)
+    xr, _ = O.qr_ldiv(Jh, yh, dtd / 10.0)
+    assert rel(x.download(), xr) <= 1e-10
+
+
+def test_chol_kept_resolves(ctx):
+    import lsob200 as L
+    m, n = 6000, 200
+    rng = np.random.default_rng(11)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)))
+    yh = rng.standard_normal(m)
+    J, y, x = L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh), L.DeviceVector(ctx, n)
+    ws = L.DenseCholeskyAllocatedSolver(ctx, m, n, damped=True)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    for k, delta in enumerate((10.0, 3.0, 0.1)):
+        d = L.DeviceVector(ctx, n, dtd / delta)
+        ws.ldiv(x, J, y, d, same_J=(k > 0))
+        assert rel(x.download(), O.chol_ldiv(Jh, yh, dtd / delta)) <= 1e-10
+    assert (ws.solves_direct, ws.solves_kept) == (1, 2)
+
+
+@pytest.mark.parametrize("solver", ["qr", "cholesky"])
+def test_lm_with_rejected_steps_reuses_the_factor(ctx, solver):
+    """An LM run that rejects steps (Δ starts far too large) takes the kept-factor path on every re-solve and still
+    walks the oracle's trajectory: same iteration / call counts, same minimizer."""
+    import lsob200 as L
+    import problems as P
+    name, f, g, x0 = P.rosenbrock()
+    solc = {"qr": L.QR, "cholesky": L.Cholesky}[solver]
+    nls = L.LeastSquaresProblem(x=x0.copy(), y=np.zeros(2), f_=f, g_=g, J=np.zeros((2, 2), order="F"))
+    anls = L.allocate(nls, L.LevenbergMarquardt(solc()))
+    r = L.optimize_(anls, Δ=1e6)
+    ro = O.optimize(f, g, x0.copy(), np.zeros((2, 2), order="F"), 2, optimizer="lm", solver=solver, delta=1e6)
+    assert anls.solver.solves_kept >= 1, "no step was rejected: the test does not exercise the re-solve"
+    assert (r.iterations, r.f_calls, r.g_calls) == (ro.iterations, ro.f_calls, ro.g_calls)
+    assert np.linalg.norm(r.minimizer - ro.minimizer) <= 1e-9

@@ -107,3 +107,51 @@ def test_dense_solvers_agree_with_normal_equations():
     assert np.linalg.norm(x2 - np.linalg.pinv(J2) @ y) <= 1e-10 * np.linalg.norm(x2)
     with pytest.raises(O.RankDeficientException):
         O.chol_ldiv(np.hstack([J[:, :3], np.zeros((300, 1))]), y)
+
+
+# ---- NIST StRD: the per-problem KNOWN ANSWERS the reference's test-suite holds (test/nonlinearfitting.jl) -----------
+# (optimizer, dataset, start column) triples whose run does NOT end within 1e-3 of the certified values.  NIST's
+# "start 1" columns of MGH09 / MGH10 are far from the solution (classed "higher difficulty" by NIST); the reference
+# itself only counts successes there (`println("strd ...")`, :1471) and asserts no NaN (:1468).
+NIST_MISSES = {("dogleg", "MGH09", 0), ("dogleg", "MGH10", 0), ("lm", "MGH10", 0)}
+NIST_KW = dict(x_tol=1e-50, f_tol=1e-36, g_tol=1e-50)        # test/nonlinearfitting.jl:1466
+
+
+@pytest.mark.parametrize("opt", ["dogleg", "lm"])
+def test_nist_strd_certified_values_pin_the_oracle(opt):
+    """The oracle's Dogleg(QR()) / LevenbergMarquardt(QR()) loops land on NIST's certified parameter values
+    (norm(minimizer - solution) <= 1e-3, the reference's own criterion at :1467) from the NIST start columns, on all 16
+    datasets the reference runs — except the three named hard starts.  This is what anchors the restatement to
+    numbers the reference holds rather than to itself."""
+    reached, total = 0, 0
+    for name, f, g, starts, cert, m in P.nist_strd():
+        for j, x0 in enumerate(starts):
+            J = np.zeros((m, cert.size), order="F")
+            with np.errstate(all="ignore"):
+                r = O.optimize(f, g, x0.copy(), J, m, optimizer=opt, solver="qr", **NIST_KW)
+            assert not np.isnan(np.mean(r.minimizer)), (name, j)          # the reference's @test (:1468)
+            ok = np.linalg.norm(r.minimizer - cert) <= 1e-3
+            assert ok == ((opt, name, j) not in NIST_MISSES), (opt, name, j, np.linalg.norm(r.minimizer - cert))
+            reached += ok
+            total += 1
+    assert total == 33 and reached == total - sum(1 for o, _, _ in NIST_MISSES if o == opt)
+
+
+def test_nist_models_have_exact_jacobians():
+    """The reference differentiates `f(x, beta)` with ForwardDiff; the analytic Jacobians of tests/problems.py agree with
+    central differences at every start column and at the certified point."""
+    for name, f, g, starts, cert, m in P.nist_strd():
+        n = cert.size
+        for x0 in starts + [cert]:
+            J, Jn = np.zeros((m, n)), np.zeros((m, n))
+            g(J, x0)
+            for k in range(n):
+                h = 1e-6 * max(abs(x0[k]), 1e-3)
+                xp, xm = x0.copy(), x0.copy()
+                xp[k] += h
+                xm[k] -= h
+                fp, fm = np.zeros(m), np.zeros(m)
+                f(fp, xp)
+                f(fm, xm)
+                Jn[:, k] = (fp - fm) / (2 * h)
+            assert np.abs(J - Jn).max() <= 1e-6 * max(np.abs(Jn).max(), 1e-300), name
