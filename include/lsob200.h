@@ -57,7 +57,7 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *                  4 levels 0 and 1 one launch each and the levels above chained in one launch
  *   "qr_lookahead" 1 = panel trees on a second stream under the previous update (default 0)
  *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default)
- *   "spmv"         0 first-generation warp-per-segment sparse products, 1 stream kernels (default)
+ *   "spmv"         0 first-generation sparse products, 1 stream kernels (shared-memory staging), 2 warp kernels (default)
  *   "lsmr_fused"   0 LSMR with host-side scalars (3 syncs per iteration), 1 fused device-resident LSMR (default)
  *   "profile"      see lso_ctx_profile_read */
 int         lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value);
@@ -253,6 +253,18 @@ int lso_lsmr_solve_ex(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_J, int64_
 /* kernel launches and host synchronisations of the last solve on this workspace (lsmr.jl:116-231 runs on the device:
  * 3 launches per iteration, at most one synchronisation per iteration) */
 int lso_lsmr_ws_stats(lso_lsmr_ws* ws, int64_t* launches_out, int64_t* syncs_out);
+
+/* ---- (f1) the four reductions a trust-region iteration reads, with ONE host synchronisation
+ *      (levenberg_marquardt.jl:104,110,114-117, dogleg.jl:101,168,171-174, utils.jl:21).  lso_lm_gradient_norm_async
+ *      enqueues maxabs_projected_gradient(g, x, lower, upper) (utils.jl:38-55) where the reference computes it (before x
+ *      moves); lso_lm_step_tail enqueues sum(abs2, ftrial), fpredict = J*dx - fcur with sum(abs2, fpredict) and
+ *      maximum(abs, dx), all-reduces the two m-dimension sums over the ranks when `allreduce` != 0 (row-sharded J) and
+ *      returns out4 = {trial ssr, predicted ssr, maxabs dx, maxabs projected gradient}. ---- */
+int lso_lm_gradient_norm_async(lso_ctx* ctx, int64_t n, const double* d_g, const double* d_x, const double* d_lower,
+                               const double* d_upper);
+int lso_lm_step_tail(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld, lso_csc* A_csc,
+                     const double* d_dx, const double* d_fcur, const double* d_ftrial, double* d_fpredict, int allreduce,
+                     double* out4);
 
 /* ---- synthetic workload generators and residual models used by bench.py / tests
  *      (counter-based hash, bit-identical on CPU and GPU).  Harness, not boundary. ---- */

@@ -311,12 +311,35 @@ def _maxabs_projected_gradient(ctx, g, x, dlo, dhi) -> float:
     return out.value
 
 
-def assess_convergence(dx: DeviceVector, maxabs_gr, ssr, trial_ssr, xtol, ftol, grtol, step_accepted):
-    """src/utils/utils.jl:7-31 — an if / elseif chain: at most one flag is set."""
+def _gradient_norm_async(ctx, g, x, dlo, dhi):
+    """maxabs_projected_gradient (utils.jl:38-55) enqueued into the step's device scalars; read back by `_step_tail`."""
+    from ._lib import check, lib
+    check(lib().lso_lm_gradient_norm_async(ctx.handle, len(g), g.ptr, x.ptr, dlo.ptr if dlo else None,
+                                           dhi.ptr if dhi else None), ctx.handle)
+
+
+def _step_tail(ctx, J, dx, fcur, ftrial, fpredict, allreduce):
+    """(f1) sum(abs2, ftrial), fpredict = J*dx - fcur with sum(abs2, fpredict), maximum(abs, dx) and the projected
+    gradient norm with ONE host synchronisation (lso_lm_step_tail)."""
+    import ctypes as C
+    from ._lib import check, lib
+    out = (C.c_double * 4)()
+    if isinstance(J, CSCMatrix):
+        dJ, ld, csc = None, 0, J.handle
+    else:
+        dJ, ld, csc = J.ptr, J.ld, None
+    check(lib().lso_lm_step_tail(ctx.handle, J.m, J.n, dJ, ld, csc, dx.ptr, fcur.ptr, ftrial.ptr, fpredict.ptr,
+                                 int(bool(allreduce)), C.addressof(out)), ctx.handle)
+    return out[0], out[1], out[2], out[3]
+
+
+def assess_convergence(dx, maxabs_gr, ssr, trial_ssr, xtol, ftol, grtol, step_accepted):
+    """src/utils/utils.jl:7-31 — an if / elseif chain: at most one flag is set.  `dx` is the step (DeviceVector) or its
+    max-norm already reduced on the device (float)."""
     x_c = f_c = g_c = False
     if step_accepted and abs(trial_ssr - ssr) <= ftol * (abs(ssr) + ftol):
         f_c = True
-    elif dx.maxabs() <= xtol:
+    elif (dx if isinstance(dx, float) else dx.maxabs()) <= xtol:
         x_c = True
     elif maxabs_gr <= grtol:
         g_c = True
@@ -397,21 +420,20 @@ class LMRun:
         self.mul_calls += lmiter
         dtd.copyto(self.grad)                                 # :102 gradient J'f (computed above)
         self.mul_calls += 1
-        self.maxabs_gr = _maxabs_projected_gradient(ctx, dtd, x, self.dlo, self.dhi)
+        _gradient_norm_async(ctx, dtd, x, self.dlo, self.dhi)  # :104 (read back with the other scalars below)
         x.axpy(-1.0, dx)                                      # :106
         anls.f(ftrial, x)
         self.f_calls += 1
-        trial_ssr = ftrial.sumabs2()
-        predicted_ssr = J.predicted_ssr(dx, fcur, fpredict)   # :114-117 fused
-        if self.sharded:
-            trial_ssr, predicted_ssr = self._allsum(trial_ssr, predicted_ssr)
+        # :110 sum(abs2, ftrial), :114-117 ||J δ - f||², maximum(abs, δx) for utils.jl:21 — one synchronisation; the two
+        # m-dimension sums are all-reduced over the ranks on the device when J is row-sharded
+        trial_ssr, predicted_ssr, maxabs_dx, self.maxabs_gr = _step_tail(ctx, J, dx, fcur, ftrial, fpredict, self.sharded)
         self.mul_calls += 1
         ssr = self.ssr
         predicted_reduction = abs(ssr - predicted_ssr)
         ρ = (ssr - trial_ssr) / predicted_reduction if predicted_reduction > 0 else 0.0
         step_accepted = ρ > MIN_STEP_QUALITY
         self.x_converged, self.f_converged, self.g_converged, self.converged = assess_convergence(
-            dx, self.maxabs_gr, ssr, trial_ssr, self.x_tol, self.f_tol, self.g_tol, step_accepted)
+            maxabs_dx, self.maxabs_gr, ssr, trial_ssr, self.x_tol, self.f_tol, self.g_tol, step_accepted)
         if step_accepted:
             fcur.copyto(ftrial)
             self.ssr = trial_ssr
@@ -493,7 +515,7 @@ class DoglegRun:
                     self.Δ *= wnorm_x
             J.mul_t(dgr, fcur, 1.0, 0.0)                    # :99
             self.mul_calls += 1
-            self.maxabs_gr = _maxabs_projected_gradient(ctx, dgr, x, dlo, dhi)
+            _gradient_norm_async(ctx, dgr, x, dlo, dhi)       # :101 (read back by the step tail; kept across reuse)
             dgr.div_(dgr, dtd)                              # :105  δgr = D⁻¹ g
             self.wnorm_dgr = wnorm(dgr, dtd)
             J.mul(fpredict, dgr, 1.0, 0.0)                  # :109
@@ -516,15 +538,15 @@ class DoglegRun:
         x.axpy(-1.0, dx)                                    # :160
         anls.f(ftrial, x)
         self.f_calls += 1
-        trial_ssr = ftrial.sumabs2()
-        predicted_ssr = J.predicted_ssr(dx, fcur, fpredict)  # :171-174
+        # :168 sum(abs2, ftrial), :171-174 ||J δ - f||², maximum(abs, δx), projected gradient norm: one synchronisation
+        trial_ssr, predicted_ssr, maxabs_dx, self.maxabs_gr = _step_tail(ctx, J, dx, fcur, ftrial, fpredict, False)
         self.mul_calls += 1
         ssr = self.ssr
         predicted_reduction = abs(ssr - predicted_ssr)
         ρ = (ssr - trial_ssr) / predicted_reduction if predicted_reduction > 0 else 0.0
         step_accepted = ρ >= MIN_STEP_QUALITY
         self.x_converged, self.f_converged, self.g_converged, self.converged = assess_convergence(
-            dx, self.maxabs_gr, ssr, trial_ssr, self.x_tol, self.f_tol, self.g_tol, step_accepted)
+            maxabs_dx, self.maxabs_gr, ssr, trial_ssr, self.x_tol, self.f_tol, self.g_tol, step_accepted)
         if step_accepted:
             self.reuse = False
             fcur.copyto(ftrial)

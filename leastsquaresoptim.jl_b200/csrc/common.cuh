@@ -35,7 +35,8 @@ struct lso_ctx {
                                        // latency-bound levels above chained in one launch (saves 0.05 ms per solve at C2)
     int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
     int64_t opt_qr_lookahead = 0;      // 1 = panel trees on a second stream under the previous update (+2% at C2)
-    int64_t opt_spmv = 1;              // 0 = first-generation warp-per-segment sparse products, 1 = stream kernels
+    int64_t opt_spmv = 2;              // 0 = first-generation sparse products, 1 = stream kernels (shared-memory staging),
+                                       // 2 = warp kernels (registers + shuffles, persistent grid; default)
     int64_t opt_lsmr_fused = 1;        // 0 = LSMR scalars on the host, 1 = fused device-resident LSMR (sparse operator)
     int64_t opt_profile = 0;           // 1 = bracket every launch of the dominant kernel with CUDA events
     std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)

@@ -361,6 +361,14 @@ int lso_dev_sumabs2(lso_ctx* ctx, int64_t n, const double* x, double* d_out) {
 int lso_dev_sum(lso_ctx* ctx, int64_t n, const double* x, double* d_out) {
     return rd_launch_dev<RD_SUM>(ctx, n, x, nullptr, nullptr, nullptr, nullptr, d_out);
 }
+int lso_dev_maxabs(lso_ctx* ctx, int64_t n, const double* x, double* d_out) {
+    return rd_launch_dev<RD_MAXABS>(ctx, n, x, nullptr, nullptr, nullptr, nullptr, d_out);
+}
+int lso_dev_maxabs_projected(lso_ctx* ctx, int64_t n, const double* g, const double* x, const double* lo, const double* hi,
+                             double* d_out) {
+    if (!lo && !hi) return rd_launch_dev<RD_MAXABS>(ctx, n, g, nullptr, nullptr, nullptr, nullptr, d_out);
+    return rd_launch_dev<RD_MAXABS_PROJ>(ctx, n, g, x, nullptr, lo, hi, d_out);
+}
 
 // ---- LM damping (levenberg_marquardt.jl:84-86), mean read from a device scalar -------------------
 __global__ void lm_damping_kernel(int64_t n, double* __restrict__ dtd, const double* __restrict__ d_sum,

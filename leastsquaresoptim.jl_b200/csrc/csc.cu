@@ -300,6 +300,14 @@ int csc_colsumabs2_cached(lso_csc* A, double* d_out) {
     return LSO_OK;
 }
 
+// fpredict = J δ - f, *d_out (device scalar) = sum(abs2, fpredict); no synchronisation
+int csc_predicted_ssr_dev(lso_csc* A, const double* d_delta, const double* d_f, double* d_fpredict, double* d_out) {
+    lso_ctx* ctx = A->ctx;
+    LSO_TRY(csc_refresh_csr(A));
+    PredictFunctor f{d_delta, d_f, d_fpredict, d_out, 0};
+    return spmv_stream_launch(ctx, A->Gr, f, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk, A->m);
+}
+
 extern "C" {
 
 int lso_csc_create(lso_ctx* ctx, int64_t m, int64_t n, int64_t nnz, const int64_t* h_colptr, const int64_t* h_rowval,
@@ -392,7 +400,7 @@ int lso_csc_mul_n(lso_csc* A, double alpha, const double* d_x, double beta, doub
     lso_prof_mark(ctx);
     if (ctx->opt_spmv) {
         MulFunctor f{d_x, d_y, alpha, beta, 0};
-        LSO_TRY(spmv_stream_launch(ctx, A->Gr, f, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk));
+        LSO_TRY(spmv_stream_launch(ctx, A->Gr, f, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk, A->m));
     } else {
         const double avg = (double)A->nnz / (double)A->m;
         if (avg <= 6.0) {
@@ -417,7 +425,7 @@ int lso_csc_mul_t(lso_csc* A, double alpha, const double* d_y, double beta, doub
     lso_prof_mark(ctx);
     if (ctx->opt_spmv) {
         MulFunctor f{d_y, d_x, alpha, beta, 0};
-        LSO_TRY(spmv_stream_launch(ctx, A->Gc, f, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk));
+        LSO_TRY(spmv_stream_launch(ctx, A->Gc, f, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk, A->n));
     } else {
         csc_mul_t_kernel<<<(unsigned)cdiv64(A->n * 32, 256), 256, 0, ctx->stream>>>(A->n, A->d_colptr, A->d_rowidx, A->d_val, d_y, alpha, beta, d_x);
         LSO_CHECK_LAUNCH(ctx);
@@ -444,7 +452,7 @@ int lso_csc_colsumabs2_gemv_t(lso_csc* A, const double* d_f, double* d_dtd, doub
         return lso_csc_mul_t(A, 1.0, d_f, 0.0, d_g);
     }
     ColsqGradFunctor f{d_f, A->d_colsq, d_g, 0};
-    LSO_TRY(spmv_stream_launch(ctx, A->Gc, f, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk));
+    LSO_TRY(spmv_stream_launch(ctx, A->Gc, f, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk, A->n));
     A->colsq_valid = true;
     return csc_colsumabs2_cached(A, d_dtd);
 }
@@ -454,9 +462,7 @@ int lso_csc_predicted_ssr(lso_csc* A, const double* d_delta, const double* d_f, 
     lso_ctx* ctx = A->ctx;
     LSO_REQUIRE(ctx, d_delta && d_f && ssr_out, "NULL pointer");
     LSO_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    LSO_TRY(csc_refresh_csr(A));
-    PredictFunctor f{d_delta, d_f, d_fpredict, ctx->d_scalars + 2, 0};
-    LSO_TRY(spmv_stream_launch(ctx, A->Gr, f, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk));
+    LSO_TRY(csc_predicted_ssr_dev(A, d_delta, d_f, d_fpredict, ctx->d_scalars + 2));
     LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *ssr_out = ctx->h_scalars[2];

@@ -42,6 +42,7 @@ int csc_refresh_csr(lso_csc* A);
 #define SP_THREADS 256
 #define SP_CHUNK 2048            /* stored entries per CTA slice: 8 per thread */
 #define SP_SEGMAX 2048           /* segments per CTA (bounds the epilogue loop when there are empty segments) */
+#define SP_WARP_CTAS 6           /* resident CTAs per SM of the warp kernel = its persistent grid per SM */
 #define SP_COUNTER_SLOT 1        /* ctx->d_counters slot of the retirement ticket */
 
 #ifdef __CUDACC__
@@ -157,16 +158,117 @@ spmv_stream_kernel(const F f_in, const int* __restrict__ ptr, const int* __restr
     }
 }
 
-// launch helper: grid = nblk segment CTAs + the CTAs of the elementwise tail
+// "warp" SpMV (ctx option "spmv" = 2, the default): G lanes per segment, everything in registers and shuffles, no shared
+// memory staging and no block barrier on the data path, persistent grid.  A random-pattern product is bound by the
+// gathers, not by the stream: every gathered double costs one L1TEX wavefront and one 32-byte L2 sector (measured:
+// profiles/r2_ncu_spmv.txt), so the kernel is built to keep as many gathers in flight as possible — each lane loads
+// entries in aligned PAIRS (one 128-bit value load + one 64-bit index load), two pairs per loop trip, i.e. up to four
+// independent gathers per lane before the first use — and to spend as few wavefronts as possible on anything else.
+// Same functor interface as the stream kernel; sums are formed in a fixed order (lane-sequential FMA chain, shuffle
+// tree over the G lanes, per-CTA partial in segment order, last CTA adds the partials in index order): bit-reproducible.
+template <int G, class F>
+__global__ void __launch_bounds__(SP_THREADS, SP_WARP_CTAS)
+spmv_warp_kernel(const F f_in, const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+                 long long nseg, double* __restrict__ partials, unsigned int* __restrict__ counter) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    F f = f_in;
+    if (!f.begin()) return;
+    const int tid = threadIdx.x;
+    double contrib = 0.0, contrib_x = 0.0;
+    if (!f.idle()) {
+        constexpr int SPB = SP_THREADS / G;                       // segments per CTA per pass
+        const int sub = tid % G;
+        for (long long base = (long long)blockIdx.x * SPB; base < nseg; base += (long long)gridDim.x * SPB) {
+            const long long s = base + tid / G;
+            const bool live = s < nseg;
+            double a = 0.0, a2 = 0.0;
+            if (live) {
+                const int k0 = ptr[s], k1 = ptr[s + 1];
+                const int ka = k0 & ~1;                          // pairs start on a 16-byte boundary
+                for (int e = ka + 2 * sub; e < k1; e += 4 * G) {
+                    const int e2 = e + 2 * G;
+                    const bool h2 = e2 < k1;
+                    const double2 v0 = __ldg(reinterpret_cast<const double2*>(val + e));
+                    const int2 c0 = __ldg(reinterpret_cast<const int2*>(idx + e));
+                    double2 v1 = make_double2(0.0, 0.0);
+                    int2 c1 = make_int2(0, 0);
+                    if (h2) {
+                        v1 = __ldg(reinterpret_cast<const double2*>(val + e2));
+                        c1 = __ldg(reinterpret_cast<const int2*>(idx + e2));
+                    }
+                    const bool o00 = e >= k0, o01 = e + 1 < k1, o10 = h2, o11 = e2 + 1 < k1;    // e2 >= k0 always
+                    const double g00 = o00 ? f.gather(c0.x) : 0.0, g01 = o01 ? f.gather(c0.y) : 0.0;
+                    const double g10 = o10 ? f.gather(c1.x) : 0.0, g11 = o11 ? f.gather(c1.y) : 0.0;
+                    if (o00) { a = fma(v0.x, g00, a); if (F::DUAL) a2 = fma(v0.x, v0.x, a2); }
+                    if (o01) { a = fma(v0.y, g01, a); if (F::DUAL) a2 = fma(v0.y, v0.y, a2); }
+                    if (o10) { a = fma(v1.x, g10, a); if (F::DUAL) a2 = fma(v1.x, v1.x, a2); }
+                    if (o11) { a = fma(v1.y, g11, a); if (F::DUAL) a2 = fma(v1.y, v1.y, a2); }
+                }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (F::DUAL) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (live && sub == 0) contrib += F::DUAL ? f.epilogue2(s, a, a2) : f.epilogue(s, a);
+        }
+        // elementwise tail (the damping rows of LSMR's augmented operator)
+        for (long long i = (long long)blockIdx.x * SP_THREADS + tid; i < f.n_extra; i += (long long)gridDim.x * SP_THREADS)
+            contrib_x += f.extra(i);
+    }
+    // ---- deterministic grid-wide sums: per-CTA partials, the last CTA to retire adds them in index order ----
+    contrib = block_sum(contrib, red);
+    contrib_x = block_sum(contrib_x, red);
+    if (tid == 0) {
+        partials[blockIdx.x] = contrib;
+        partials[gridDim.x + blockIdx.x] = contrib_x;
+        __threadfence();
+        const unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double sm = 0.0, sx = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += SP_THREADS) {
+            sm += ((volatile double*)partials)[i];
+            sx += ((volatile double*)partials)[gridDim.x + i];
+        }
+        sm = block_sum(sm, red);
+        sx = block_sum(sx, red);
+        if (tid == 0) {
+            *counter = 0;
+            f.finish(sm, sx);
+        }
+    }
+}
+
+// launch helper.  stream kernel: grid = nblk segment CTAs + the CTAs of the elementwise tail; warp kernel: persistent grid
 template <class F>
 static inline int spmv_stream_launch(lso_ctx* ctx, int G, const F& f, const int* ptr, const int* idx, const double* val,
-                                     const int* blk, int nblk) {
+                                     const int* blk, int nblk, long long nseg) {
+    double* part = ctx->d_partials;
+    unsigned int* cnt = ctx->d_counters + SP_COUNTER_SLOT;
+    if (ctx->opt_spmv >= 2) {
+        if (nseg <= 0 && f.n_extra <= 0) return LSO_OK;
+        const long long want = std::max<long long>((nseg * G + SP_THREADS - 1) / SP_THREADS, (f.n_extra + SP_THREADS - 1) / SP_THREADS);
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)ctx->num_sms * SP_WARP_CTAS));
+        switch (G) {
+            case 1: spmv_warp_kernel<1, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, nseg, part, cnt); break;
+            case 2: spmv_warp_kernel<2, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, nseg, part, cnt); break;
+            case 4: spmv_warp_kernel<4, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, nseg, part, cnt); break;
+            case 8: spmv_warp_kernel<8, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, nseg, part, cnt); break;
+            case 16: spmv_warp_kernel<16, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, nseg, part, cnt); break;
+            default: spmv_warp_kernel<32, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, nseg, part, cnt); break;
+        }
+        LSO_CHECK_LAUNCH(ctx);
+        return LSO_OK;
+    }
     const long long extra = (f.n_extra + SP_THREADS - 1) / SP_THREADS;
     const unsigned grid = (unsigned)(nblk + extra);
     if (grid == 0) return LSO_OK;
     if ((size_t)grid > (size_t)LSO_PARTIALS) return lso_set_error(ctx, LSO_ERR_UNSUPPORTED, "sparse product: too many CTAs for the partials buffer");
-    double* part = ctx->d_partials;
-    unsigned int* cnt = ctx->d_counters + SP_COUNTER_SLOT;
     switch (G) {
         case 1: spmv_stream_kernel<1, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, blk, nblk, part, cnt); break;
         case 2: spmv_stream_kernel<2, F><<<grid, SP_THREADS, 0, ctx->stream>>>(f, ptr, idx, val, blk, nblk, part, cnt); break;

@@ -299,13 +299,11 @@ int lso_dense_gemv_n(lso_ctx* ctx, int64_t m, int64_t n, double alpha, const dou
     return LSO_OK;
 }
 
-int lso_dense_predicted_ssr(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld,
-                            const double* d_delta, const double* d_f, double* d_fpredict, double* ssr_out) {
-    LSO_REQUIRE(ctx, ctx && ssr_out, "NULL pointer");
-    LSO_REQUIRE(ctx, m >= 0 && n >= 0 && ld >= m, "bad dimensions");
-    if (m == 0) { *ssr_out = 0.0; return LSO_OK; }
-    LSO_REQUIRE(ctx, d_f && (n == 0 || (d_J && d_delta)), "NULL pointer");
-    LSO_ENTER(ctx);
+}  // extern "C"
+
+// fpredict = J δ - f, *d_out (device scalar) = sum(abs2, fpredict); no synchronisation
+int dense_predicted_ssr_dev(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld, const double* d_delta,
+                            const double* d_f, double* d_fpredict, double* d_out) {
     int64_t g = cdiv64(m, 256);
     LSO_REQUIRE(ctx, g <= LSO_PARTIALS, "m too large");
     const int cs = gemv_n_chunks(ctx, m, n);
@@ -317,14 +315,23 @@ int lso_dense_predicted_ssr(lso_ctx* ctx, int64_t m, int64_t n, const double* d_
         gemv_n_part_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, d_J, ld, d_delta, cpc, part);
         LSO_CHECK_LAUNCH(ctx);
         gemv_n_combine_kernel<true><<<(unsigned)g, 256, 0, ctx->stream>>>(m, (int)grid.y, part, 1.0, 0.0, d_fpredict, d_f,
-                                                                         ctx->d_partials, ctx->d_counters + 1, ctx->d_scalars + 3);
+                                                                         ctx->d_partials, ctx->d_counters + 1, d_out);
         LSO_CHECK_LAUNCH(ctx);
-        return lso_fetch_scalar(ctx, 3, ssr_out);
+        return LSO_OK;
     }
     gemv_n_kernel<true><<<(unsigned)g, 256, 0, ctx->stream>>>(m, n, 1.0, d_J, ld, d_delta, 0.0, d_fpredict, d_f,
-                                                             ctx->d_partials, ctx->d_counters + 1, ctx->d_scalars + 3);
+                                                             ctx->d_partials, ctx->d_counters + 1, d_out);
     LSO_CHECK_LAUNCH(ctx);
-    return lso_fetch_scalar(ctx, 3, ssr_out);
+    return LSO_OK;
 }
 
-}  // extern "C"
+extern "C" int lso_dense_predicted_ssr(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int64_t ld,
+                                       const double* d_delta, const double* d_f, double* d_fpredict, double* ssr_out) {
+    LSO_REQUIRE(ctx, ctx && ssr_out, "NULL pointer");
+    LSO_REQUIRE(ctx, m >= 0 && n >= 0 && ld >= m, "bad dimensions");
+    if (m == 0) { *ssr_out = 0.0; return LSO_OK; }
+    LSO_REQUIRE(ctx, d_f && (n == 0 || (d_J && d_delta)), "NULL pointer");
+    LSO_ENTER(ctx);
+    LSO_TRY(dense_predicted_ssr_dev(ctx, m, n, d_J, ld, d_delta, d_f, d_fpredict, ctx->d_scalars + 3));
+    return lso_fetch_scalar(ctx, 3, ssr_out);
+}

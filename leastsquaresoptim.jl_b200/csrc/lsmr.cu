@@ -336,7 +336,7 @@ static int lsmr_fused_csc(lso_lsmr_ws* ws, lso_csc* A, const double* d_y, double
     {   // v = A'u ; α = ‖v‖ ; recurrences initialised ; v /= α, h = v, hbar = 0, tmp = P∘v
         LsmrAdj fa{st, ws->u, nullptr, d_damp, ws->P, ws->v, 1, 0, 0.0, 1.0, false};
         lso_prof_mark(ctx);
-        LSO_TRY(spmv_stream_launch(ctx, A->Gc, fa, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk));
+        LSO_TRY(spmv_stream_launch(ctx, A->Gc, fa, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk, A->n));
         lso_prof_mark(ctx);
         lsmr_upd_kernel<true><<<ugrid, 256, 0, ctx->stream>>>(st, n, ws->v, ws->h, ws->hbar, d_x, ws->P, ws->tmp, ctx->d_partials, cnt);
         LSO_CHECK_LAUNCH(ctx);
@@ -348,10 +348,10 @@ static int lsmr_fused_csc(lso_lsmr_ws* ws, lso_csc* A, const double* d_y, double
     for (;;) {
         for (int b = 0; b < batch && enq < maxiter; ++b, ++enq) {
             lso_prof_mark(ctx);
-            LSO_TRY(spmv_stream_launch(ctx, A->Gr, ff, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk));
+            LSO_TRY(spmv_stream_launch(ctx, A->Gr, ff, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk, A->m));
             lso_prof_mark(ctx);
             lso_prof_mark(ctx);
-            LSO_TRY(spmv_stream_launch(ctx, A->Gc, fa, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk));
+            LSO_TRY(spmv_stream_launch(ctx, A->Gc, fa, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk, A->n));
             lso_prof_mark(ctx);
             lsmr_upd_kernel<false><<<ugrid, 256, 0, ctx->stream>>>(st, n, ws->v, ws->h, ws->hbar, d_x, ws->P, ws->tmp, ctx->d_partials, cnt);
             LSO_CHECK_LAUNCH(ctx);

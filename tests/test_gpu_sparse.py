@@ -33,7 +33,7 @@ def ragged(m, n, seed):
     return A
 
 
-@pytest.mark.parametrize("spmv", [1, 0])
+@pytest.mark.parametrize("spmv", [2, 1, 0])
 @pytest.mark.parametrize("m,n", [(9, 6), (333, 70), (5000, 2600), (2600, 5000), (40000, 3000)])
 def test_stream_products_on_ragged_patterns(ctx, m, n, spmv):
     from lsob200 import CSCMatrix, DeviceVector

@@ -16,6 +16,9 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 500_000
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 ctx = L.Context.default(0)
+import os
+if os.environ.get('LSO_SPMV'):
+    ctx.set_option('spmv', int(os.environ['LSO_SPMV']))
 t0 = time.perf_counter()
 colptr = np.zeros(n + 1, dtype=np.int64)
 rowval = np.zeros(n * k, dtype=np.int64)
