@@ -56,7 +56,12 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *                  per tree level (default), 3 the same kernel with all tree levels of a panel in one launch,
  *                  4 levels 0 and 1 one launch each and the levels above chained in one launch
  *   "qr_lookahead" 1 = panel trees on a second stream under the previous update (default 0)
- *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default)
+ *   "qr_tune"      1 (default) = QR workspaces whose panel tree fits on a third of the SMs (row shards, the stacked R
+ *                  factors) time four launch schedules once at creation and keep the fastest; setting "qr_apply" or
+ *                  "qr_lookahead" explicitly turns this off
+ *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default), 2 tcgen05 syrk: int8 digit matrices (Ozaki scheme) multiplied by
+ *                  tcgen05.mma.kind::i8 into TMEM, operands fed by TMA, fp64 reconstructed exactly
+ *   "ozaki_slices" 7-bit digits per value for "syrk" = 2 (2..8, default 8: representation error 2^-57)
  *   "spmv"         0 first-generation sparse products, 1 stream kernels (shared-memory staging), 2 warp kernels (default)
  *   "lsmr_fused"   0 LSMR with host-side scalars (3 syncs per iteration), 1 fused device-resident LSMR (default)
  *   "profile"      see lso_ctx_profile_read */

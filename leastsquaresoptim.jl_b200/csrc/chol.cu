@@ -381,6 +381,7 @@ void chol_plan_destroy(CholPlan* p) {
     cudaFree(p->part);
     cudaFree(p->d_info);
     cudaFree(p->packed);
+    oz_plan_destroy(p->oz);
     *p = CholPlan();
 }
 
@@ -393,6 +394,8 @@ int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_
     int64_t rows_per_split = roundup64(cdiv64(m, ksplit), SY_KC);
     ksplit = cdiv64(m, rows_per_split);
     if (ksplit < 1) ksplit = 1;
+    if (ctx->opt_syrk == 2)     // tcgen05 int8 digit products (ozaki.cu)
+        return oz_syrk_upper(ctx, &p->oz, (int)ctx->opt_ozaki_slices, m, n, d_J, ld, p->C, p->ldc, p->part, p->part_cap);
     double* out = (ksplit > 1) ? p->part : p->C;
     if (ctx->opt_syrk) {
         int64_t ntb = cdiv64(n, SY_TS);

@@ -2,6 +2,12 @@
 #pragma once
 #include "common.cuh"
 
+struct OzPlan;
+void oz_plan_destroy(OzPlan* p);
+// C (upper tiles) = J'J through int8 digit matrices on tcgen05 (ozaki.cu)
+int oz_syrk_upper(lso_ctx* ctx, OzPlan** pp, int S, int64_t m, int64_t n, const double* d_J, int64_t ld, double* C,
+                  int64_t ldc, double* part, int64_t part_cap);
+
 struct CholPlan {
     int64_t n = 0;
     int64_t ldc = 0;          // roundup(n, 32)
@@ -12,6 +18,7 @@ struct CholPlan {
     int* d_info = nullptr;
     double* packed = nullptr; // 2 x packed_len: [upper(J'J) by columns | J'y], the all-reduce buffer (+ the test hook's running sum)
     int64_t packed_len = 0;   // n(n+1)/2 + n
+    OzPlan* oz = nullptr;     // digit matrices / tensor maps of the tcgen05 syrk (ctx option "syrk" = 2), created on first use
     bool kept = false;        // packed holds [upper(J'J) | J'y] of the last solve (before damping)
 };
 

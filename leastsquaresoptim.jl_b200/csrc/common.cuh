@@ -33,7 +33,10 @@ struct lso_ctx {
                                        // per tree level), 3 = ping-pong kernel, all tree levels of a panel in one launch
                                        // (correct, but 12 % slower at C2 — per-level tails add up), 4 = levels 0, 1 one launch each + the
                                        // latency-bound levels above chained in one launch (saves 0.05 ms per solve at C2)
-    int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk
+    int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk, 2 = tcgen05 int8 digit products (Ozaki scheme, ozaki.cu)
+    int64_t opt_ozaki_slices = 8;      // 7-bit digits per fp64 value in the tcgen05 syrk (2..8; 8 = below fp64 rounding)
+    int64_t opt_qr_tune = 1;           // 1 = small QR plans time their launch schedules once and keep the fastest (cleared by
+                                       // an explicit "qr_apply" / "qr_lookahead" setting)
     int64_t opt_qr_lookahead = 0;      // 1 = panel trees on a second stream under the previous update (+2% at C2)
     int64_t opt_spmv = 2;              // 0 = first-generation sparse products, 1 = stream kernels (shared-memory staging),
                                        // 2 = warp kernels (registers + shuffles, persistent grid; default)

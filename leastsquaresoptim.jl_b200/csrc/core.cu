@@ -92,10 +92,12 @@ void* lso_ctx_stream(lso_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; 
 
 int lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value) {
     LSO_REQUIRE(ctx, ctx && key, "ctx/key is NULL");
-    if (!strcmp(key, "qr_apply")) ctx->opt_qr_apply = value;
+    if (!strcmp(key, "qr_apply")) { ctx->opt_qr_apply = value; ctx->opt_qr_tune = 0; }
     else if (!strcmp(key, "syrk")) ctx->opt_syrk = value;
-    else if (!strcmp(key, "qr_lookahead")) ctx->opt_qr_lookahead = value;
+    else if (!strcmp(key, "qr_lookahead")) { ctx->opt_qr_lookahead = value; ctx->opt_qr_tune = 0; }
+    else if (!strcmp(key, "qr_tune")) ctx->opt_qr_tune = value;
     else if (!strcmp(key, "spmv")) ctx->opt_spmv = value;
+    else if (!strcmp(key, "ozaki_slices")) { if (value < 2 || value > 8) return lso_set_error(ctx, LSO_ERR_ARG, "ozaki_slices must be 2..8"); ctx->opt_ozaki_slices = value; }
     else if (!strcmp(key, "lsmr_fused")) ctx->opt_lsmr_fused = value;
     else if (!strcmp(key, "profile")) { ctx->opt_profile = value; ctx->prof_used = 0; ctx->prof2_used = 0; }
     else return lso_set_error(ctx, LSO_ERR_ARG, "unknown option '%s'", key);

@@ -334,6 +334,8 @@ static int shard_ensure_stack(lso_dense_ws* ws, int P) {
         LSO_TRY(qr_plan_create(ctx, (int64_t)P * n + n, n, &ws->plan_stack));
         ws->have_stack = true;
         ws->stack_P = P;
+        ws->plan_stack.band = P + 1;       // tune the launch schedule for the banded shape the stack solves have
+        LSO_TRY(qr_plan_tune(ctx, &ws->plan_stack));
         LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_gather, (size_t)(P + 1) * n * (n + 1) * sizeof(double)));
     }
     return LSO_OK;

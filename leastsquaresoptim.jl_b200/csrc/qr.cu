@@ -1427,7 +1427,7 @@ int qr_plan_create(lso_ctx* ctx, int64_t M, int64_t N, QRPlan* plan) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(qr_tree_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TREE_DSMEM_BYTES));
         attr_done = true;
     }
-    return LSO_OK;
+    return qr_plan_tune(ctx, plan);
 }
 
 void qr_plan_destroy(QRPlan* plan) {
@@ -1573,8 +1573,9 @@ static int launch_apply_fused(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl,
 
 // apply the panel's block reflectors (all tree levels) to columns [cfirst, cfirst + ntiles*QCT)
 static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int buf, int64_t cfirst, int ntiles,
-                        cudaStream_t st, bool mark, int lend = QR_MAX_LEVELS) {
+                        cudaStream_t st, bool mark, int lend = QR_MAX_LEVELS, int sm_cap = 0) {
     if (ntiles <= 0) return LSO_OK;
+    const int64_t max_ctas = (sm_cap > 0 && sm_cap < ctx->num_sms) ? sm_cap : ctx->num_sms;
     for (int l = 0; l < pl.L && l < lend; ++l) {
         if (ctx->opt_qr_apply == 0) {
             int64_t chunks = cdiv64((int64_t)ctx->num_sms * 2, pl.nblk[l]);
@@ -1586,7 +1587,7 @@ static int launch_apply(lso_ctx* ctx, QRPlan* plan, const PanelLevels& pl, int b
                                                                  plan->lev[l].V[buf], plan->lev[l].T[buf]);
         } else {
             int64_t jtot = pl.nblk[l] * ntiles;
-            int grid = (int)(jtot < ctx->num_sms ? jtot : ctx->num_sms);
+            int grid = (int)(jtot < max_ctas ? jtot : max_ctas);
             if (mark) lso_prof_mark(ctx);
             if (ctx->opt_qr_apply >= 2) {
                 ApplyLevels L;
@@ -1635,7 +1636,7 @@ static void tl_dump(cudaStream_t U, cudaStream_t P) {
     g_tl_on = false;
 }
 
-int qr_factor(lso_ctx* ctx, QRPlan* plan) {
+static int qr_factor_run(lso_ctx* ctx, QRPlan* plan, int reserve) {
     const int64_t M = plan->M;
     g_tl_on = (getenv("LSO_QR_TIMELINE") != nullptr) && plan->M > 50000;
     const int64_t npanels = std::min<int64_t>(plan->Npad / QB, cdiv64(M, QB));   // no rows left beyond that
@@ -1707,7 +1708,8 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
             tl_mark(P, "leaf(k+1) end", k, 1);
             LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, plan->ev_next[k], 0));
             tl_mark(U, "applyRest begin", k, 0);
-            LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail + LA * QCT, ntiles - LA, U, true));
+            // the next panel's tree runs under this launch: leave `reserve` SMs free for it
+            LSO_TRY(launch_apply(ctx, plan, cur, buf, ctrail + LA * QCT, ntiles - LA, U, true, QR_MAX_LEVELS, ctx->num_sms - reserve));
             tl_mark(U, "applyRest end", k, 0);
         } else {
             LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, plan->ev_leaf[k], 0));
@@ -1717,5 +1719,88 @@ int qr_factor(lso_ctx* ctx, QRPlan* plan) {
         if (has_next) cur = nxt;
     }
     tl_dump(U, P);
+    return LSO_OK;
+}
+
+int qr_factor(lso_ctx* ctx, QRPlan* plan) {
+    if (!plan->sched_tuned || !ctx->opt_qr_tune) return qr_factor_run(ctx, plan, 0);
+    const int64_t sa = ctx->opt_qr_apply, sl = ctx->opt_qr_lookahead;
+    ctx->opt_qr_apply = plan->sched_apply;
+    ctx->opt_qr_lookahead = plan->sched_lookahead;
+    const int st = qr_factor_run(ctx, plan, plan->sched_reserve);
+    ctx->opt_qr_apply = sa;
+    ctx->opt_qr_lookahead = sl;
+    return st;
+}
+
+// synthetic fill for the tuning runs: values in (-1, 1) from a counter hash, every entry of the first M rows
+__global__ void qr_tune_fill_kernel(double* __restrict__ A, long long ld, long long M, long long ncols) {
+    const long long col = blockIdx.y;
+    if (col >= ncols) return;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < ld; r += (long long)gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)(col * 0x9E3779B97F4A7C15ull) ^ (unsigned long long)(r * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull);
+        z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+        const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+        A[col * ld + r] = (r < M) ? 2.0 * u - 1.0 : 0.0;
+    }
+}
+
+int qr_plan_tune(lso_ctx* ctx, QRPlan* plan) {
+    plan->sched_tuned = false;
+    if (!ctx->opt_qr_tune) return LSO_OK;
+    PanelLevels p0;
+    panel_levels(plan, 0, p0);
+    int64_t tree_ctas = 0;
+    for (int l = 0; l < p0.L; ++l) tree_ctas += p0.nblk[l];
+    // only plans whose panel tree is small enough to run beside the update are latency-bound enough to matter
+    if (tree_ctas > ctx->num_sms || plan->Npad / QB < 4) return LSO_OK;
+    struct Cand { int apply, la, reserve; };
+    const int reserve = (int)std::min<int64_t>((tree_ctas + 1) / 2, ctx->num_sms / 2);
+    const Cand cand[4] = {{2, 0, 0}, {3, 0, 0}, {4, 0, 0}, {2, 1, reserve}};
+    cudaEvent_t e0, e1;
+    LSO_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+    LSO_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+    const int64_t sa = ctx->opt_qr_apply, sl = ctx->opt_qr_lookahead;
+    const double sflops = ctx->stat_qr_flops, suflops = ctx->stat_qr_update_flops;
+    const int64_t launches = ctx->launches;
+    const int64_t prof = ctx->opt_profile;
+    ctx->opt_profile = 0;
+    int best = 0;
+    int st = LSO_OK;
+    for (int c = 0; c < 4 && st == LSO_OK; ++c) {
+        float ms_best = 1e30f;
+        for (int rep = 0; rep < 3 && st == LSO_OK; ++rep) {
+            dim3 grid((unsigned)std::min<int64_t>(cdiv64(plan->ld, 256), 64), (unsigned)plan->Nc);
+            qr_tune_fill_kernel<<<grid, 256, 0, ctx->stream>>>(plan->A, plan->ld, plan->M, plan->Nc);
+            ctx->opt_qr_apply = cand[c].apply;
+            ctx->opt_qr_lookahead = cand[c].la;
+            cudaEventRecord(e0, ctx->stream);
+            st = qr_factor_run(ctx, plan, cand[c].reserve);
+            cudaEventRecord(e1, ctx->stream);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { st = lso_set_error(ctx, LSO_ERR_CUDA, "QR schedule tuning run failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < ms_best) ms_best = ms;        // the first run of a schedule warms the instruction caches
+        }
+        plan->tune_ms[c] = ms_best;
+        if (ms_best < plan->tune_ms[best]) best = c;
+    }
+    ctx->opt_qr_apply = sa;
+    ctx->opt_qr_lookahead = sl;
+    ctx->opt_profile = prof;
+    ctx->stat_qr_flops = sflops;
+    ctx->stat_qr_update_flops = suflops;
+    ctx->launches = launches;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    LSO_TRY(st);
+    LSO_CHECK_CUDA(ctx, cudaMemsetAsync(plan->A, 0, (size_t)plan->ld * plan->Nc * sizeof(double), ctx->stream));
+    plan->sched_apply = cand[best].apply;
+    plan->sched_lookahead = cand[best].la;
+    plan->sched_reserve = cand[best].reserve;
+    plan->sched_tuned = true;
+    if (getenv("LSO_QR_TUNE_VERBOSE"))
+        fprintf(stderr, "[lsob200] QR plan %lld x %lld (band %lld): schedule ms {per-level %.3f, fused %.3f, fused-upper %.3f, look-ahead(reserve %d) %.3f} -> %d\n",
+                (long long)plan->M, (long long)plan->N, (long long)plan->band, plan->tune_ms[0], plan->tune_ms[1], plan->tune_ms[2], reserve, plan->tune_ms[3], best);
     return LSO_OK;
 }

@@ -42,6 +42,11 @@ struct QRPlan {
     unsigned ticket_base = 0;
     unsigned prog_base = 0;     // tag base of the current launch (row r carries tag base + r + 1)
     QRLevel lev[QR_MAX_LEVELS];
+    // launch schedule chosen by qr_plan_tune for small (latency-bound) plans: which update mode, whether the next panel's
+    // tree runs under the bulk update on SMs reserved for it
+    int sched_apply = 2, sched_lookahead = 0, sched_reserve = 0;
+    bool sched_tuned = false;
+    float tune_ms[4] = {0.f, 0.f, 0.f, 0.f};
     // look-ahead: panel factorisations run on a second stream, overlapped with the previous trailing update
     cudaStream_t panel_stream = nullptr;
     cudaEvent_t ev_start = nullptr;
@@ -53,5 +58,8 @@ void qr_plan_destroy(QRPlan* plan);
 // Factorise plan->A in place: on return the leading N x N upper triangle holds R and column Npad
 // rows 0..N-1 hold Q'b (the right-hand side that was stored in column Npad on entry).
 int qr_factor(lso_ctx* ctx, QRPlan* plan);
+// Small plans (a panel tree that fits on a third of the SMs) are latency-bound: time the launch schedules on synthetic
+// data once and keep the fastest (results are bit-identical across schedules: every tile job does the same arithmetic).
+int qr_plan_tune(lso_ctx* ctx, QRPlan* plan);
 // x = R^{-1} c  (TRANS=0)  or  x = R^{-T} c (TRANS=1) for the upper-triangular n x n R at d_R (ld).
 int tri_solve(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, const double* d_c, double* d_x, int trans);

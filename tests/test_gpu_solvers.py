@@ -454,3 +454,31 @@ def test_lm_with_rejected_steps_reuses_the_factor(ctx, solver):
     assert anls.solver.solves_kept >= 1, "no step was rejected: the test does not exercise the re-solve"
     assert (r.iterations, r.f_calls, r.g_calls) == (ro.iterations, ro.f_calls, ro.g_calls)
     assert np.linalg.norm(r.minimizer - ro.minimizer) <= 1e-9
+
+
+def test_qr_schedule_tuning_is_bit_identical(ctx):
+    """Small QR workspaces (row shards, stacked R factors) time their launch schedules at creation (ctx option "qr_tune")
+    and keep the fastest: the schedules differ in launch grouping only, so δ must be BIT-identical with and without
+    tuning (replicated stack solves on different ranks may pick different schedules), and within 1e-10 of the oracle."""
+    import lsob200 as L
+    from lsob200._lib import check, lib
+    m, n, P = 12000, 200, 4
+    rng = np.random.default_rng(5)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)))
+    yh = rng.standard_normal(m)
+    damp = np.einsum("ij,ij->j", Jh, Jh) / 10.0
+    xr, _ = O.qr_ldiv(Jh, yh, damp)
+    out = []
+    for tune in (1, 0):
+        c = L.Context(0)                      # a fresh context: options at their defaults
+        c.set_option("qr_tune", tune)
+        J, y, d, x = L.DenseMatrix(c, m, n, Jh), L.DeviceVector(c, m, yh), L.DeviceVector(c, n, damp), L.DeviceVector(c, n)
+        ws = L.DenseQRAllocatedSolver(c, m // P, n, damped=False)
+        rank = C.c_int()
+        check(lib().lso_debug_qr_solve_emulated_shards(ws._h, P, J.ptr, J.ld, y.ptr, d.ptr, x.ptr, C.byref(rank)), c.handle)
+        out.append(x.download().copy())
+        wd = L.DenseQRAllocatedSolver(c, m, n, damped=True)
+        wd.ldiv(x, J, y, d)
+        out.append(x.download().copy())
+    assert rel(out[0], xr) <= 1e-10 and rel(out[1], xr) <= 1e-10
+    assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3])

@@ -30,7 +30,10 @@ def wrap(obj, name, label):
         ctx.sync(); t0 = time.perf_counter(); r = f(*a, **k); ctx.sync(); acc[label] = acc.get(label, 0.0) + time.perf_counter() - t0; return r
     setattr(obj, name, g)
 wrap(anls, "g", "g!"); wrap(anls, "f", "f!"); wrap(J, "colsumabs2_and_grad", "colsumabs2+J'f"); wrap(ctx, "allreduce", "allreduce (n-vectors, scalars)")
-wrap(anls.solver, "ldiv", "ldiv (local QR + allgather + stack QR)"); wrap(J, "predicted_ssr", "predicted ssr"); wrap(run, "_allsum", "_allsum (incl. its allreduce)")
+wrap(anls.solver, "ldiv", "ldiv (local QR + allgather + stack QR)")
+import lsob200.api as _api
+wrap(_api, "_step_tail", "step tail (ssr, predicted ssr, maxabs; 1 allreduce of 2 scalars; 1 sync)")
+wrap(_api, "_box_project", "box projection"); wrap(_api, "_lm_damping", "damping")
 K = 6
 ctx.sync(); t0 = time.perf_counter()
 for _ in range(K): run.iterate()
