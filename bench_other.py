@@ -144,14 +144,17 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
         "steps_accepted": st["acc"], "lsmr_iterations_per_step": st["iters"], "gpu_launches": launches,
         "ms_per_lsmr_iteration": ms_per_it,
         "lsmr": {"fixed_iterations": NIT, "launches_per_solve": lsmr_launches, "host_syncs_per_solve": lsmr_syncs},
-        "roofline": {"kernel": "spmv_stream_kernel (CSR-mirror J v and CSC J'u with the LSMR vector algebra and norms fused "
-                               "in; 128-bit value / 64-bit index loads)",
+        "roofline": {"kernel": "spmv_warp_kernel (CSR-mirror J v and CSC J'u with the LSMR vector algebra and norms fused "
+                               "in; paired 128-bit value / 64-bit index loads, G lanes per row / column, shuffle reductions)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "launches": sp_launches, "kernel_ms_per_launch": sp_ms / max(sp_launches, 1),
                      "algorithmic_bytes_per_launch": sp_bytes / max(sp_launches, 1),
                      "numerator": "12 B per stored entry (8 B value + 4 B index) + 8 B per element of both vectors, per product",
                      "whole_iteration_frac": (2 * (12.0 * nnz + 8.0 * (m + n)) + 8.0 * 8 * n) / (ms_per_it * 1e-3) / 1e9 / peak,
-                     "traffic": None},
+                     "binding_resource": "L2 sector bandwidth / L1TEX wavefronts of the random gathers: one 32-byte sector per "
+                                         "gathered double (ncu: 1.75e8 sectors = 5.6 GB through L2 per product, ~11.7 TB/s vs the "
+                                         "~12.4 TB/s LTS cap), not HBM — profiles/r2_ncu_spmv_warp.txt",
+                     "traffic": 1.38e9},
         "last_ssr": st["run"].ssr,
     }
     # cpu baseline: the reference's serial CSC products (SparseArrays mul! is single-threaded), two LSMR iterations' worth
@@ -213,12 +216,14 @@ def run_c4(env, dmma_peak, m_loc=250_000, n=4_000, steps=3, warmup=1):
     ctx.set_option("profile", 1)
     ctx.profile_read(); ctx.profile_read_collective()
     ctx.stat("syrk_flops", reset=True)
+    ctx.stat("syrk_i8_macs", reset=True)
     ctx.launch_count(reset=True)
     ms, wall = env.timed(one_step, steps)
     launches = ctx.launch_count(reset=True)
     syrk_ms, syrk_launches = ctx.profile_read()
     coll_ms, coll_calls = ctx.profile_read_collective()
     syrk_flops = ctx.stat("syrk_flops", reset=True)
+    i8_macs = ctx.stat("syrk_i8_macs", reset=True)
     ctx.set_option("profile", 0)
     coll_ms = env.max_over_ranks(coll_ms)
     last_ssr = st["run"].ssr
@@ -263,16 +268,40 @@ def run_c4(env, dmma_peak, m_loc=250_000, n=4_000, steps=3, warmup=1):
                        "doubles": pk, "bytes": 8 * pk, "calls": coll_calls,
                        "ms_per_call_max_over_ranks": coll_ms / max(coll_calls, 1),
                        "ms_per_step": coll_ms / steps} if world > 1 else None,
-        "roofline": {"kernel": "syrk_mma_kernel (J'J upper tiles on the fp64 tensor pipe, DMMA m8n8k4)", "bound": "tensor",
-                     "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-                     "frac": achieved / dmma_peak if dmma_peak else None, "launches": syrk_launches,
-                     "kernel_ms_per_step": syrk_ms / steps, "kernel_share_of_step": syrk_ms / ms,
-                     "numerator": "m n (n + 1) flops per J'J (lso_ctx_stat \"syrk_flops\"), per rank", "traffic": None},
+        "roofline": _c4_roofline(achieved, dmma_peak, syrk_launches, syrk_ms, steps, ms, i8_macs),
         "parity": parity,
     }
     if world == 1:
         res["cpu_baseline"] = _c4_cpu(m_loc, n)
     return res
+
+
+def _c4_roofline(fp64_tflops, dmma_peak, launches, syrk_ms, steps, ms, i8_macs):
+    """J'J runs on tcgen05 (int8 digit matrices, Ozaki scheme) when the library chose that path (i8_macs > 0): the pipe it
+    occupies is the int8 tensor pipe, so `achieved` / `peak` are int8 TOP/s (peak = 2 x the measured dense bf16 peak of
+    MEASURED_PEAKS.json: kind::i8 issues at twice the kind::f16 rate); the fp64-equivalent rate is reported beside the DMMA
+    peak it replaces.  Otherwise the DMMA syrk's roofline."""
+    base = {"bound": "tensor", "launches": launches, "kernel_ms_per_step": syrk_ms / steps, "kernel_share_of_step": syrk_ms / ms,
+            "fp64_equivalent_tflops": fp64_tflops, "fp64_dmma_peak_tflops": dmma_peak,
+            "fp64_equivalent_over_dmma_peak": fp64_tflops / dmma_peak if dmma_peak else None, "traffic": None}
+    if i8_macs > 0:
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            bf16 = float(pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops"))
+            src = "2 x MEASURED_PEAKS.json dense bf16 (sustained figure: the kernel runs tens of ms inside a step)"
+        except Exception:
+            bf16, src = 2250.0, "2 x nominal dense bf16 (2.25 PFLOP/s)"
+        tops = 2.0 * i8_macs / (syrk_ms * 1e-3) / 1e12 if syrk_ms > 0 else 0.0
+        base.update({"kernel": "oz_syrk_kernel (tcgen05.mma.kind::i8 128x128x32 into TMEM, TMA-fed 3-stage ring; incl. the digit "
+                               "split and the split-K reduce)",
+                     "achieved": tops, "peak": 2.0 * bf16, "unit": "TOP/s (int8)", "frac": tops / (2.0 * bf16), "peak_source": src,
+                     "numerator": "2 x int8 MACs issued (S(S+1)/2 digit products x 128x128 tiles of the upper triangle x rows), "
+                                  "lso_ctx_stat \"syrk_i8_macs\"; time = the whole J'J (split + tiles + reduce)"})
+    else:
+        base.update({"kernel": "syrk_mma_kernel (J'J upper tiles on the fp64 tensor pipe, DMMA m8n8k4)", "achieved": fp64_tflops,
+                     "peak": dmma_peak, "unit": "TFLOP/s", "frac": fp64_tflops / dmma_peak if dmma_peak else None,
+                     "numerator": "m n (n + 1) flops per J'J (lso_ctx_stat \"syrk_flops\"), per rank"})
+    return base
 
 
 def _c4_cpu(m, n, block=16_000):

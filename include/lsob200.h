@@ -59,7 +59,8 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *   "qr_tune"      1 (default) = QR workspaces whose panel tree fits on a third of the SMs (row shards, the stacked R
  *                  factors) time four launch schedules once at creation and keep the fastest; setting "qr_apply" or
  *                  "qr_lookahead" explicitly turns this off
- *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk (default), 2 tcgen05 syrk: int8 digit matrices (Ozaki scheme) multiplied by
+ *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk, 3 (default) tcgen05 syrk for m >= 8192 and n >= 512 and DMMA otherwise,
+ *                  2 tcgen05 syrk always: int8 digit matrices (Ozaki scheme) multiplied by
  *                  tcgen05.mma.kind::i8 into TMEM, operands fed by TMA, fp64 reconstructed exactly
  *   "ozaki_slices" 7-bit digits per value for "syrk" = 2 (2..8, default 8: representation error 2^-57)
  *   "spmv"         0 first-generation sparse products, 1 stream kernels (shared-memory staging), 2 warp kernels (default)
@@ -73,6 +74,7 @@ int         lso_ctx_profile_read(lso_ctx* ctx, double* total_ms, int64_t* launch
 /* Algorithmic work issued through this context since the last reset (the numerators of bench.py's rooflines):
  *   "qr_update_flops"  trailing-update flops of the QR factorisations (sum over panels of 4*32*active rows*trailing columns)
  *   "qr_flops"         2 M n^2 - 2/3 n^3 per factorisation          "syrk_flops"  m n (n+1) per J'J
+ *   "syrk_i8_macs"     int8 multiply-accumulates issued to tcgen05 by the digit-matrix syrk (S(S+1)/2 digit products per tile)
  *   "spmv_bytes"       12 B per stored entry + 8 B per vector element per sparse product */
 int         lso_ctx_stat(lso_ctx* ctx, const char* key, double* out, int reset);
 /* second channel of the same option: the collective of a sharded solve (ncclAllReduce / ncclAllGather) */

@@ -394,8 +394,14 @@ int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_
     int64_t rows_per_split = roundup64(cdiv64(m, ksplit), SY_KC);
     ksplit = cdiv64(m, rows_per_split);
     if (ksplit < 1) ksplit = 1;
-    if (ctx->opt_syrk == 2)     // tcgen05 int8 digit products (ozaki.cu)
-        return oz_syrk_upper(ctx, &p->oz, (int)ctx->opt_ozaki_slices, m, n, d_J, ld, p->C, p->ldc, p->part, p->part_cap);
+    // tcgen05 int8 digit products (ozaki.cu): always with "syrk" = 2; with the default "syrk" = 3 for shapes where the
+    // 128 x 128 tiles and the digit split pay off, falling back to the DMMA kernel if the digit matrices (as large as J
+    // itself) cannot be allocated
+    if (ctx->opt_syrk == 2 || (ctx->opt_syrk == 3 && m >= 8192 && n >= 512)) {
+        const int st = oz_syrk_upper(ctx, &p->oz, (int)ctx->opt_ozaki_slices, m, n, d_J, ld, p->C, p->ldc, p->part, p->part_cap);
+        if (st == LSO_OK) { ctx->stat_syrk_i8_macs += (double)ctx->opt_ozaki_slices * (double)(ctx->opt_ozaki_slices + 1) / 2.0 * (double)roundup64(m, 128) * 128.0 * 128.0 * (double)(cdiv64(n, 128) * (cdiv64(n, 128) + 1) / 2); return st; }
+        if (ctx->opt_syrk == 2 || st != LSO_ERR_ALLOC) return st;
+    }
     double* out = (ksplit > 1) ? p->part : p->C;
     if (ctx->opt_syrk) {
         int64_t ntb = cdiv64(n, SY_TS);

@@ -26,6 +26,7 @@ struct lso_ctx {
     double stat_qr_update_flops = 0.0;  // trailing-update flops of the QR factorisations: sum over panels of 4*QB*rows*trailing columns
     double stat_qr_flops = 0.0;         // 2 M n^2 - 2/3 n^3 per factorisation
     double stat_syrk_flops = 0.0;       // m n (n + 1) per J'J
+    double stat_syrk_i8_macs = 0.0;     // int8 multiply-accumulates issued to tcgen05 by the digit-matrix syrk
     double stat_spmv_bytes = 0.0;       // 12 B per stored entry + 8 B per vector element, per sparse product
     std::string last_error;
     // options
@@ -33,7 +34,8 @@ struct lso_ctx {
                                        // per tree level), 3 = ping-pong kernel, all tree levels of a panel in one launch
                                        // (correct, but 12 % slower at C2 — per-level tails add up), 4 = levels 0, 1 one launch each + the
                                        // latency-bound levels above chained in one launch (saves 0.05 ms per solve at C2)
-    int64_t opt_syrk = 1;              // 0 = plain syrk, 1 = DMMA syrk, 2 = tcgen05 int8 digit products (Ozaki scheme, ozaki.cu)
+    int64_t opt_syrk = 3;              // 0 = plain syrk, 1 = DMMA syrk, 2 = tcgen05 int8 digit products (Ozaki scheme, ozaki.cu),
+                                       // 3 = tcgen05 for m >= 8192 and n >= 512, DMMA otherwise (default)
     int64_t opt_ozaki_slices = 8;      // 7-bit digits per fp64 value in the tcgen05 syrk (2..8; 8 = below fp64 rounding)
     int64_t opt_qr_tune = 1;           // 1 = small QR plans time their launch schedules once and keep the fastest (cleared by
                                        // an explicit "qr_apply" / "qr_lookahead" setting)

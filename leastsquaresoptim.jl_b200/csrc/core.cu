@@ -132,6 +132,7 @@ int lso_ctx_stat(lso_ctx* ctx, const char* key, double* out, int reset) {
     if (!strcmp(key, "qr_update_flops")) p = &ctx->stat_qr_update_flops;
     else if (!strcmp(key, "qr_flops")) p = &ctx->stat_qr_flops;
     else if (!strcmp(key, "syrk_flops")) p = &ctx->stat_syrk_flops;
+    else if (!strcmp(key, "syrk_i8_macs")) p = &ctx->stat_syrk_i8_macs;
     else if (!strcmp(key, "spmv_bytes")) p = &ctx->stat_spmv_bytes;
     else return lso_set_error(ctx, LSO_ERR_ARG, "unknown statistic '%s'", key);
     *out = *p;

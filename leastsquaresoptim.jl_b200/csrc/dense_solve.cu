@@ -84,9 +84,10 @@ static int qr_assemble(lso_ctx* ctx, QRPlan* p, int64_t m, int64_t n, const doub
 }
 
 int small_qr_finish(lso_ctx* ctx, int64_t n, double* d_R, int64_t ld, double* d_c, double* d_x, int* rank_out);
+int qr_rank_screen(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, double rcond, int* full_rank_out);
 
 // R (n x n upper, in plan->A) and c = Q'y (column Npad) -> x.  Full-rank fast path: back substitution.
-static int qr_finish(lso_dense_ws* ws, QRPlan* p, double* d_x, int* rank_out) {
+static int qr_finish(lso_dense_ws* ws, QRPlan* p, double* d_x, int* rank_out, bool undamped) {
     lso_ctx* ctx = ws->ctx;
     const int64_t n = ws->n;
     double* c = p->A + p->Npad * p->ld;
@@ -100,8 +101,17 @@ static int qr_finish(lso_dense_ws* ws, QRPlan* p, double* d_x, int* rank_out) {
                                         ctx->stream));
     LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double mn = ctx->h_scalars[8], mx = ctx->h_scalars[9];
-    const double rcond = (double)std::min<int64_t>(p->M, n) * 2.220446049250313e-16;
-    const bool suspicious = !(mn > 1e3 * rcond * mx);   // also true for NaN / zero matrix
+    // rcond = min(rows, cols) * eps with the rows of the system the REFERENCE factors (zero padding rows do not count)
+    const int64_t sys_rows = (p == &ws->plan) ? (ws->damped ? ws->m + ws->n : ws->m) : p->M;
+    const double rcond = (double)std::min<int64_t>(sys_rows, n) * 2.220446049250313e-16;
+    bool suspicious = !(mn > 1e3 * rcond * mx);   // also true for NaN / zero matrix
+    if (!suspicious && undamped && n > 1) {
+        // an ill-conditioned J can hide behind a benign diagonal (Kahan-type matrices): for the undamped solves, where
+        // nothing bounds cond(J), run the reference's incremental condition estimate on the unpivoted triangle as well
+        int full = 0;
+        LSO_TRY(qr_rank_screen(ctx, n, p->A, p->ld, rcond, &full));
+        suspicious = !full;
+    }
     if (!suspicious) {
         LSO_TRY(tri_solve(ctx, n, p->A, p->ld, c, d_x, 0));
         ws->last_rank = (int)n;
@@ -129,7 +139,9 @@ int lso_dense_ws_create(lso_ctx* ctx, int64_t m, int64_t n, int solver_kind, int
     int st = LSO_OK;
     if (solver_kind == LSO_SOLVER_QR) {
         // LM: (m+n) x n augmented system (dense_qr.jl:50-54); Dogleg: m x n (dense_qr.jl:25-28)
-        st = qr_plan_create(ctx, damped ? m + n : m, n, &ws->plan);
+        // (m < n: the reference sizes u = zeros(max(m, n)), dense_qr.jl:27; here J is padded with zero rows to n x n, which
+        // has the same Gram matrix, hence the same pivots, R and minimum-norm solution)
+        st = qr_plan_create(ctx, damped ? m + n : std::max(m, n), n, &ws->plan);
     } else {
         st = chol_plan_create(ctx, n, &ws->chol);
     }
@@ -161,11 +173,10 @@ int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* 
     LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
     // dense_qr.jl:61 — the damped form needs the (m+n)-row workspace, the undamped form the m-row one
     LSO_REQUIRE(ctx, (d_damp != nullptr) == (ws->damped != 0), "length(u) should equal length(x) + length(y)");
-    LSO_REQUIRE(ctx, ws->plan.M >= ws->n, "QR path requires rows >= columns (underdetermined systems are not supported)");
     LSO_ENTER(ctx);
     LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, ws->n, d_J, ld, d_y, d_damp));
     LSO_TRY(qr_factor(ctx, &ws->plan));
-    return qr_finish(ws, &ws->plan, d_x, rank_out);
+    return qr_finish(ws, &ws->plan, d_x, rank_out, d_damp == nullptr);
 }
 
 static int ensure_staging(lso_dense_ws* ws, int64_t ld) {
@@ -352,7 +363,7 @@ static int shard_stack_solve(lso_dense_ws* ws, int P, const double* d_damp, doub
     ps->M = (int64_t)Q * n;       // rows in use (the workspace was sized for P + 1 triangles)
     ps->band = Q;
     LSO_TRY(qr_factor(ctx, ps));
-    return qr_finish(ws, ps, d_x, rank_out);
+    return qr_finish(ws, ps, d_x, rank_out, d_damp == nullptr);
 }
 
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,

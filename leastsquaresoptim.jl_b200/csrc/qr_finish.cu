@@ -290,8 +290,262 @@ __global__ void copy_upper_kernel(int n, const double* __restrict__ R, long long
     for (int i = threadIdx.x; i < n; i += blockDim.x) W[(long long)j * ldw + i] = (i <= j) ? R[(long long)j * ld + i] : 0.0;
 }
 
+// =====================================================================================================================
+// Large n (> FIN_SINGLE_CTA_MAX): the same pipeline, one grid per dependent step instead of one CTA for everything.
+// Phase A is 4/3 n^3 BLAS-2 flops on an n x n matrix that no longer fits in L2 (n = 10 000: 800 MB): two launches per
+// column (pivot + reflector by one CTA, then the rank-1 update and the norm downdates by the whole grid).
+// =====================================================================================================================
+#define FIN_SINGLE_CTA_MAX 1024
+
+struct FinVecs { double *vn1, *vn2, *tau, *xmin, *xmax; int* jpvt; int* rank; };
+
+__global__ void __launch_bounds__(FT, 1)
+fin_init_kernel(int n, double* __restrict__ W, long long ldw, FinVecs v) {
+    const int j = blockIdx.x;
+    __shared__ double sm[FT / 32];
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n; i += FT) {
+        if (i > j) W[(long long)j * ldw + i] = 0.0;
+        else { const double a = W[(long long)j * ldw + i]; part = fma(a, a, part); }
+    }
+    const double s = f_block_sum(part, sm);
+    if (threadIdx.x == 0) { v.vn1[j] = v.vn2[j] = sqrt(s); v.jpvt[j] = j; }
+}
+
+// step j, part 1 (one CTA): pivot selection, column swap, Householder reflector of W[j:n, j]  (dlaqp2)
+__global__ void __launch_bounds__(FT, 1)
+fin_pivot_reflect_kernel(int n, int j, double* __restrict__ W, long long ldw, FinVecs v) {
+    __shared__ double sm[FT / 32];
+    __shared__ double s_val[FT / 32];
+    __shared__ int s_idx[FT / 32];
+    __shared__ int s_pvt;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    double bv = -1.0; int bi = n;
+    for (int k = j + tid; k < n; k += FT) { const double a = v.vn1[k]; if (a > bv) { bv = a; bi = k; } }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[wrp] = bv; s_idx[wrp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = s_val[0]; int ix = s_idx[0];
+        for (int w = 1; w < FT / 32; ++w) if (s_val[w] > a || (s_val[w] == a && s_idx[w] < ix)) { a = s_val[w]; ix = s_idx[w]; }
+        if (ix >= n) ix = j;
+        s_pvt = ix;
+        if (ix != j) {
+            const int tj = v.jpvt[ix]; v.jpvt[ix] = v.jpvt[j]; v.jpvt[j] = tj;
+            v.vn1[ix] = v.vn1[j]; v.vn2[ix] = v.vn2[j];
+        }
+    }
+    __syncthreads();
+    const int pvt = s_pvt;
+    double* colj = W + (long long)j * ldw;
+    if (pvt != j) {
+        double* colp = W + (long long)pvt * ldw;
+        for (int i = tid; i < n; i += FT) { const double a = colj[i]; colj[i] = colp[i]; colp[i] = a; }
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int i = j + 1 + tid; i < n; i += FT) { const double a = colj[i]; part = fma(a, a, part); }
+    const double xn2 = f_block_sum(part, sm);
+    const double alpha = colj[j];
+    double beta, tj, scale;
+    if (xn2 == 0.0) { beta = alpha; tj = 0.0; scale = 0.0; }
+    else { beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha); tj = (beta - alpha) / beta; scale = 1.0 / (alpha - beta); }
+    __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += FT) colj[i] *= scale;
+    if (tid == 0) { colj[j] = beta; v.tau[j] = tj; }
+}
+
+// step j, part 2 (whole grid, one warp per trailing column; column n is the right-hand side): apply H_j, then the
+// partial column norm downdate of dlaqp2
+__global__ void __launch_bounds__(256)
+fin_apply_kernel(int n, int j, double* __restrict__ W, long long ldw, double* __restrict__ c, FinVecs v) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const double tol3z = sqrt(1.1102230246251565e-16);
+    const double* colj = W + (long long)j * ldw;
+    const double tj = v.tau[j];
+    for (int k = j + 1 + blockIdx.x * wpb + (threadIdx.x >> 5); k <= n; k += gridDim.x * wpb) {
+        double* colk = (k < n) ? (W + (long long)k * ldw) : c;
+        double w = 0.0;
+        for (int i = j + 1 + lane; i < n; i += 32) w = fma(colj[i], colk[i], w);
+        w = warp_sum(w) + colk[j];
+        const double tw = tj * w;
+        for (int i = j + 1 + lane; i < n; i += 32) colk[i] = fma(-tw, colj[i], colk[i]);
+        __syncwarp();
+        const double head = colk[j] - tw;
+        if (lane == 0) colk[j] = head;
+        if (k < n && v.vn1[k] != 0.0) {
+            double temp = fabs(head) / v.vn1[k];
+            temp = fmax(0.0, 1.0 - temp * temp);
+            const double r = v.vn1[k] / v.vn2[k];
+            if (temp * r * r <= tol3z) {
+                double s = 0.0;
+                for (int i = j + 1 + lane; i < n; i += 32) { const double a = colk[i]; s = fma(a, a, s); }
+                s = warp_sum(s);
+                if (lane == 0) v.vn1[k] = v.vn2[k] = sqrt(s);
+            } else if (lane == 0) {
+                v.vn1[k] *= sqrt(temp);
+            }
+        }
+    }
+}
+
+// numerical rank of the upper-triangular W by incremental condition estimation (dlaic1), as `ldiv!(::QRPivoted)` / dgelsy do
+__global__ void __launch_bounds__(FT, 1)
+fin_rank_kernel(int n, const double* __restrict__ W, long long ldw, FinVecs v, double rcond) {
+    __shared__ double sm[FT / 32];
+    __shared__ double s_lo_s, s_hi_s, s_tmin, s_tmax;
+    __shared__ int s_stop;
+    const int tid = threadIdx.x;
+    int rnk = 0;
+    const double ar = fabs(W[0]);
+    if (ar != 0.0) {
+        rnk = 1;
+        if (tid == 0) { v.xmin[0] = 1.0; v.xmax[0] = 1.0; s_tmin = ar; s_tmax = ar; s_stop = 0; }
+        __syncthreads();
+        while (rnk < n) {
+            const double* wcol = W + (long long)rnk * ldw;
+            double a1 = 0.0, a2 = 0.0;
+            for (int i = tid; i < rnk; i += FT) { const double w = wcol[i]; a1 = fma(v.xmin[i], w, a1); a2 = fma(v.xmax[i], w, a2); }
+            a1 = f_block_sum(a1, sm);
+            a2 = f_block_sum(a2, sm);
+            if (tid == 0) {
+                const double gamma = wcol[rnk];
+                const Laic1Out lo = laic1(2, s_tmin, a1, gamma);
+                const Laic1Out hi = laic1(1, s_tmax, a2, gamma);
+                s_tmin = lo.sestpr; s_tmax = hi.sestpr;
+                s_stop = (hi.sestpr * rcond > lo.sestpr) ? 1 : 0;
+                s_lo_s = lo.s; s_hi_s = hi.s;
+                if (!s_stop) { v.xmin[rnk] = lo.c; v.xmax[rnk] = hi.c; }
+            }
+            __syncthreads();
+            if (s_stop) break;
+            const double ls = s_lo_s, hs = s_hi_s;
+            for (int i = tid; i < rnk; i += FT) { v.xmin[i] *= ls; v.xmax[i] *= hs; }
+            __syncthreads();
+            ++rnk;
+        }
+    }
+    if (tid == 0) *v.rank = rnk;
+}
+
+// RZ step i, part 1 (one CTA): reflector that annihilates W[i, r:n] against W[i, i]   (dlatrz)
+__global__ void __launch_bounds__(FT, 1)
+fin_rz_reflect_kernel(int n, int r, int i, double* __restrict__ W, long long ldw, FinVecs v) {
+    __shared__ double sm[FT / 32];
+    const int tid = threadIdx.x;
+    double part = 0.0;
+    for (int k = r + tid; k < n; k += FT) { const double a = W[(long long)k * ldw + i]; part = fma(a, a, part); }
+    const double xn2 = f_block_sum(part, sm);
+    const double alpha = W[(long long)i * ldw + i];
+    double beta, ti, scale;
+    if (xn2 == 0.0) { beta = alpha; ti = 0.0; scale = 0.0; }
+    else { beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha); ti = (beta - alpha) / beta; scale = 1.0 / (alpha - beta); }
+    __syncthreads();
+    for (int k = r + tid; k < n; k += FT) W[(long long)k * ldw + i] *= scale;
+    if (tid == 0) { W[(long long)i * ldw + i] = beta; v.tau[i] = ti; }
+}
+// RZ step i, part 2 (grid over rows p < i): apply the reflector from the right
+__global__ void __launch_bounds__(256)
+fin_rz_apply_kernel(int n, int r, int i, double* __restrict__ W, long long ldw, FinVecs v) {
+    const double ti = v.tau[i];
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < i; p += gridDim.x * blockDim.x) {
+        double w = W[(long long)i * ldw + p];
+        for (int k = r; k < n; ++k) w = fma(W[(long long)k * ldw + p], W[(long long)k * ldw + i], w);
+        const double tw = ti * w;
+        W[(long long)i * ldw + p] -= tw;
+        for (int k = r; k < n; ++k) W[(long long)k * ldw + p] = fma(-tw, W[(long long)k * ldw + i], W[(long long)k * ldw + p]);
+    }
+}
+// x = P Z' [y; 0]: y (length r, in c) already solved; apply Z(1..r) (dormrz 'L','T') and undo the column permutation
+__global__ void __launch_bounds__(FT, 1)
+fin_backtransform_kernel(int n, int r, const double* __restrict__ W, long long ldw, double* __restrict__ c,
+                         double* __restrict__ xout, FinVecs v) {
+    __shared__ double sm[FT / 32];
+    const int tid = threadIdx.x;
+    for (int i = r + tid; i < n; i += FT) c[i] = 0.0;
+    __syncthreads();
+    if (n > r) {
+        for (int k = 0; k < r; ++k) {
+            double part = 0.0;
+            for (int q = r + tid; q < n; q += FT) part = fma(W[(long long)q * ldw + k], c[q], part);
+            const double w = f_block_sum(part, sm) + c[k];
+            const double tw = v.tau[k] * w;
+            __syncthreads();
+            for (int q = r + tid; q < n; q += FT) c[q] = fma(-tw, W[(long long)q * ldw + k], c[q]);
+            if (tid == 0) c[k] -= tw;
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += FT) xout[v.jpvt[i]] = c[i];
+}
+
+static int large_qr_finish(lso_ctx* ctx, int64_t n64, double* W, double* c, FinVecs v, double* d_x, double rcond, int* rank_out) {
+    const int n = (int)n64;
+    const long long ldw = n;
+    fin_init_kernel<<<(unsigned)n, FT, 0, ctx->stream>>>(n, W, ldw, v);
+    LSO_CHECK_LAUNCH(ctx);
+    const int grid = ctx->num_sms * 4;
+    for (int j = 0; j < n; ++j) {
+        fin_pivot_reflect_kernel<<<1, FT, 0, ctx->stream>>>(n, j, W, ldw, v);
+        fin_apply_kernel<<<grid, 256, 0, ctx->stream>>>(n, j, W, ldw, c, v);
+    }
+    LSO_CHECK_LAUNCH(ctx);
+    fin_rank_kernel<<<1, FT, 0, ctx->stream>>>(n, W, ldw, v, rcond);
+    LSO_CHECK_LAUNCH(ctx);
+    int r = 0;
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(&r, v.rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *rank_out = r;
+    if (r == 0) {
+        LSO_CHECK_CUDA(ctx, cudaMemsetAsync(d_x, 0, (size_t)n * sizeof(double), ctx->stream));
+        return LSO_OK;
+    }
+    if (r < n) {
+        for (int i = r - 1; i >= 0; --i) {
+            fin_rz_reflect_kernel<<<1, FT, 0, ctx->stream>>>(n, r, i, W, ldw, v);
+            if (i > 0) fin_rz_apply_kernel<<<(unsigned)std::min<int>((i + 255) / 256, grid), 256, 0, ctx->stream>>>(n, r, i, W, ldw, v);
+        }
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    LSO_TRY(tri_solve(ctx, r, W, ldw, c, c, 0));                 // y = T11^{-1} c(1:r)
+    fin_backtransform_kernel<<<1, FT, 0, ctx->stream>>>(n, r, W, ldw, c, d_x, v);
+    LSO_CHECK_LAUNCH(ctx);
+    ctx->launches += 2LL * n + 4 + (r < n ? 2LL * r : 0);
+    return LSO_OK;
+}
+
+// screen for the undamped solves: the reference's own rank test (dlaic1 sweep with rcond = min(rows, cols) eps) run on
+// the UNPIVOTED triangle.  *full_rank_out = 1 when even a 1000 x stricter threshold finds full rank: the plain back
+// substitution is then what the reference computes too; anything else takes the pivoted finish.
+int qr_rank_screen(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, double rcond, int* full_rank_out) {
+    const size_t need = 8 * (size_t)n + 64;
+    if (ctx->finish_cap < need) {
+        LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_finish);
+        ctx->d_finish = nullptr;
+        ctx->finish_cap = 0;
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_finish, need * sizeof(double)));
+        ctx->finish_cap = need;
+    }
+    double* base = ctx->d_finish;
+    FinVecs v{base, base + n, base + 2 * n, base + 3 * n, base + 4 * n, (int*)(base + 5 * n), nullptr};
+    v.rank = v.jpvt + n;
+    fin_rank_kernel<<<1, FT, 0, ctx->stream>>>((int)n, d_R, ld, v, rcond * 1e3);
+    LSO_CHECK_LAUNCH(ctx);
+    int r = 0;
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(&r, v.rank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *full_rank_out = (r == (int)n) ? 1 : 0;
+    return LSO_OK;
+}
+
 int small_qr_finish(lso_ctx* ctx, int64_t n, double* d_R, int64_t ld, double* d_c, double* d_x, int* rank_out) {
-    LSO_REQUIRE(ctx, n <= 4096, "rank-deficient QR finish: n > 4096 is not supported yet");
+    LSO_REQUIRE(ctx, n <= 24000, "rank-deficient QR finish: n > 24000 is not supported");
     const size_t need = (size_t)n * n + 8 * (size_t)n + 64;
     if (ctx->finish_cap < need) {
         LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -310,6 +564,10 @@ int small_qr_finish(lso_ctx* ctx, int64_t n, double* d_R, int64_t ld, double* d_
     LSO_CHECK_LAUNCH(ctx);
     LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(c, d_c, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     const double rcond = (double)n * 2.220446049250313e-16;
+    if (n > FIN_SINGLE_CTA_MAX) {
+        FinVecs v{vn1, vn2, tau, xmin, xmax, jpvt, d_rank};
+        return large_qr_finish(ctx, n, W, c, v, d_x, rcond, rank_out);
+    }
     small_qrcp_solve_kernel<<<1, FT, 0, ctx->stream>>>((int)n, W, n, c, d_x, vn1, vn2, tau, xmin, xmax, jpvt, rcond, d_rank);
     LSO_CHECK_LAUNCH(ctx);
     int rk = 0;

@@ -482,3 +482,55 @@ def test_qr_schedule_tuning_is_bit_identical(ctx):
         out.append(x.download().copy())
     assert rel(out[0], xr) <= 1e-10 and rel(out[1], xr) <= 1e-10
     assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3])
+
+
+# ---- Q2 completeness: underdetermined systems, large rank-deficient factors, ill-conditioning behind a benign diagonal ----
+@pytest.mark.parametrize("m,n", [(3, 7), (30, 50), (200, 260)])
+def test_qr_underdetermined_minimum_norm(ctx, m, n):
+    """m < n (dense_qr.jl:25-28 sizes u = zeros(max(m, n))): `ldiv!(::QRPivoted)` returns the MINIMUM-NORM solution of
+    the underdetermined system; here J is padded with zero rows to n x n (same Gram matrix, pivots and R)."""
+    import lsob200 as L
+    rng = np.random.default_rng(m * 31 + n)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)))
+    yh = rng.standard_normal(m)
+    xr, rk = O.qr_ldiv(Jh, yh)
+    ws = L.DenseQRAllocatedSolver(ctx, m, n, damped=False)
+    x = L.DeviceVector(ctx, n)
+    ws.ldiv(x, L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh))
+    assert ws.last_rank == rk == m
+    assert rel(x.download(), xr) <= TOL
+    assert np.linalg.norm(Jh @ x.download() - yh) <= 1e-10 * np.linalg.norm(yh)
+
+
+def test_qr_rank_deficient_large_n(ctx):
+    """n above the single-CTA limit of the pivoted finish (1024): the grid-per-step pipeline (dlaqp2 + dlaic1 + dtzrzf +
+    dormrz on the n x n factor) gives dgelsy's rank and minimum-norm solution."""
+    import lsob200 as L
+    m, n, r = 3000, 1300, 1180
+    rng = np.random.default_rng(77)
+    Jh = np.asfortranarray(rng.standard_normal((m, r)) @ rng.standard_normal((r, n)))
+    yh = rng.standard_normal(m)
+    xr, rk = O.qr_ldiv(Jh, yh)
+    ws = L.DenseQRAllocatedSolver(ctx, m, n, damped=False)
+    x = L.DeviceVector(ctx, n)
+    ws.ldiv(x, L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh))
+    assert ws.last_rank == rk == r
+    assert rel(x.download(), xr) <= 1e-8          # cond(R11) ~ 1e4 here: both answers carry O(cond * eps) of their own
+
+
+def test_qr_hidden_ill_conditioning_takes_the_rank_revealing_path(ctx):
+    """triu(-1) + I has a unit diagonal (max|r_ii| / min|r_ii| = 1) but one singular value of order 2^-n: a diagonal screen
+    would take plain back substitution and return a step of norm ~1e19; the incremental condition estimate on the
+    unpivoted factor sends it to the pivoted finish, which drops that direction like the reference (dgelsy) does."""
+    import lsob200 as L
+    n = 70
+    K = np.triu(-np.ones((n, n)), 1) + np.eye(n)
+    Jh = np.asfortranarray(np.vstack([K, np.zeros((10, n))]))
+    yh = np.random.default_rng(3).standard_normal(n + 10)
+    xr, rk = O.qr_ldiv(Jh, yh)
+    assert rk == n - 1
+    ws = L.DenseQRAllocatedSolver(ctx, n + 10, n, damped=False)
+    x = L.DeviceVector(ctx, n)
+    ws.ldiv(x, L.DenseMatrix(ctx, n + 10, n, Jh), L.DeviceVector(ctx, n + 10, yh))
+    assert ws.last_rank == rk
+    assert rel(x.download(), xr) <= 1e-9
