@@ -273,6 +273,14 @@ int lso_lm_step_tail(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int6
                      const double* d_dx, const double* d_fcur, const double* d_ftrial, double* d_fpredict, int allreduce,
                      double* out4);
 
+/* ---- (f2) device Jacobian producer: `autodiff = :central` of LeastSquaresProblem (src/types.jl:54-58: FiniteDiff's
+ *      finite_difference_jacobian! with step cbrt(eps) * max(1, |x_j|)) for a residual f!(out, x) given as a callback on
+ *      DEVICE pointers that enqueues its work on lso_ctx_stream.  d_x is perturbed in place and restored; d_work holds
+ *      2 m doubles.  2 n residual evaluations, J is written on the device. ---- */
+typedef int (*lso_residual_fn)(void* user, const double* d_x, double* d_out);
+int lso_fd_jacobian_central(lso_ctx* ctx, int64_t m, int64_t n, lso_residual_fn f, void* user, double* d_x,
+                            double* d_J, int64_t ld, double* d_work);
+
 /* ---- synthetic workload generators and residual models used by bench.py / tests
  *      (counter-based hash, bit-identical on CPU and GPU).  Harness, not boundary. ---- */
 int lso_synth_dense_matrix(lso_ctx* ctx, int64_t m, int64_t n, int64_t row_offset, uint64_t seed,

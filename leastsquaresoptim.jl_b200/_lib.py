@@ -38,7 +38,7 @@ def _ctype(decl: str):
         return C.c_void_p if stars == 1 else C.POINTER(C.c_void_p)
     if base == "char" and stars == 1:
         return C.c_char_p
-    if base == "lso_precond_fn":
+    if base in ("lso_precond_fn", "lso_residual_fn"):
         return C.c_void_p          # function pointer: pass a ctypes CFUNCTYPE instance cast to c_void_p, or None
     t = _BASE[base]
     if stars == 0:

@@ -106,8 +106,13 @@ class LeastSquaresProblem:
         self.ctx = ctx or Context.default()
         self.device_callbacks = device_callbacks
         if device_callbacks:
-            assert isinstance(x, DeviceVector) and isinstance(y, DeviceVector) and J is not None and g_ is not None
+            assert isinstance(x, DeviceVector) and isinstance(y, DeviceVector) and J is not None
             self.x, self.y, self.J = x, y, J
+            if g_ is None:
+                # autodiff = :central (types.jl:54-58) with f! on the device: J is produced on the device as well
+                if not isinstance(J, DenseMatrix):
+                    raise TypeError("the finite-difference Jacobian fills a dense J; give g! for a sparse J")
+                g_ = _device_central_difference_jacobian(self.ctx, f_, J.m, J.n)
             self.f_, self.g_ = f_, g_
             m, n = J.shape
         else:
@@ -131,6 +136,34 @@ class LeastSquaresProblem:
             raise ValueError("DimensionMismatch: x must have length size(J, 2)")
         if len(self.y) != m:
             raise ValueError("DimensionMismatch: y must have length size(J, 1)")
+
+
+def _device_central_difference_jacobian(ctx, f_, m, n):
+    """(f2) `finite_difference_jacobian!(J, f!, x, cache)` (types.jl:56-58) for a device f!: lso_fd_jacobian_central calls
+    f! back with device pointers; the Python f_(out: DeviceVector, x: DeviceVector) is wrapped accordingly."""
+    import ctypes as C
+    from ._lib import check, lib
+    RES_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+    work = DeviceVector(ctx, 2 * m)
+    state = {}
+
+    def _cb(user, d_x, d_out):
+        try:
+            f_(DeviceVector.view(ctx, d_out, m), DeviceVector.view(ctx, d_x, n))
+            return 0
+        except Exception as e:       # pragma: no cover
+            state["error"] = e
+            return 1
+    cb = RES_FN(_cb)
+
+    def g_(J, x):
+        state.pop("error", None)
+        st = lib().lso_fd_jacobian_central(ctx.handle, m, n, C.cast(cb, C.c_void_p), None, x.ptr, J.ptr, J.ld, work.ptr)
+        if "error" in state:
+            raise state["error"]
+        check(st, ctx.handle)
+    g_._keepalive = (cb, work)
+    return g_
 
 
 def _central_difference_jacobian(f_, m):

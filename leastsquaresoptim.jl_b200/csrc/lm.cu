@@ -57,3 +57,44 @@ int lso_lm_step_tail(lso_ctx* ctx, int64_t m, int64_t n, const double* d_J, int6
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// (f2) device Jacobian producer: the `autodiff = :central` default of LeastSquaresProblem (types.jl:54-58,
+// FiniteDiff.finite_difference_jacobian! with its default step: eps_j = cbrt(eps) * max(1, |x_j|)) for an f! that is a
+// device callback — J never leaves the GPU.  Column j = (f(x + eps_j e_j) - f(x - eps_j e_j)) / (2 eps_j).
+// =====================================================================================================================
+__global__ void fd_perturb_kernel(double* __restrict__ x, long long j, double xj, double h) { x[j] = xj + h; }
+__global__ void fd_column_kernel(long long m, const double* __restrict__ fp, const double* __restrict__ fm, double inv2h,
+                                 double* __restrict__ col) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x)
+        col[i] = (fp[i] - fm[i]) * inv2h;
+}
+
+extern "C" int lso_fd_jacobian_central(lso_ctx* ctx, int64_t m, int64_t n, lso_residual_fn f, void* user, double* d_x,
+                                       double* d_J, int64_t ld, double* d_work /* 2 m */) {
+    LSO_REQUIRE(ctx, ctx && f && d_x && d_J && d_work, "NULL pointer");
+    LSO_REQUIRE(ctx, m >= 1 && n >= 1 && ld >= m, "bad dimensions");
+    LSO_ENTER(ctx);
+    std::vector<double> hx((size_t)n);
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(hx.data(), d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double relstep = cbrt(2.220446049250313e-16);
+    double* fp = d_work;
+    double* fm = d_work + m;
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv64(m, 256), (int64_t)ctx->num_sms * 8);
+    for (int64_t j = 0; j < n; ++j) {
+        const double xj = hx[(size_t)j];
+        const double h = relstep * fmax(1.0, fabs(xj));
+        fd_perturb_kernel<<<1, 1, 0, ctx->stream>>>(d_x, j, xj, h);
+        int st = f(user, d_x, fp);
+        if (st != 0) return lso_set_error(ctx, LSO_ERR_ARG, "residual callback failed with status %d", st);
+        fd_perturb_kernel<<<1, 1, 0, ctx->stream>>>(d_x, j, xj, -h);
+        st = f(user, d_x, fm);
+        if (st != 0) return lso_set_error(ctx, LSO_ERR_ARG, "residual callback failed with status %d", st);
+        fd_perturb_kernel<<<1, 1, 0, ctx->stream>>>(d_x, j, xj, 0.0);
+        fd_column_kernel<<<grid, 256, 0, ctx->stream>>>(m, fp, fm, 1.0 / (2.0 * h), d_J + (size_t)j * (size_t)ld);
+        ctx->launches += 4;
+    }
+    LSO_CHECK_LAUNCH(ctx);
+    return LSO_OK;
+}

@@ -113,6 +113,13 @@ class DeviceVector:
         else:
             self.fill(0.0)
 
+    @classmethod
+    def view(cls, ctx: Context, ptr: int, n: int) -> "DeviceVector":
+        """A non-owning vector over device memory someone else manages (callback arguments)."""
+        v = cls.__new__(cls)
+        v.ctx, v.n, v.ptr, v._fin = ctx, int(n), int(ptr), None
+        return v
+
     def __len__(self):
         return self.n
 

@@ -156,3 +156,43 @@ def test_csc_products(ctx, m, n, density):
     y1 = y.download().copy()
     J.mul(y, x, 1.0, 0.0)
     assert np.array_equal(y.download(), y1)
+
+
+def test_device_central_difference_jacobian(ctx):
+    """(f2) `autodiff = :central` (types.jl:54-58) with f! on the device: lso_fd_jacobian_central reproduces FiniteDiff's
+    central differences (step cbrt(eps) max(1, |x_j|)) column by column, and an LM(QR) run that uses it converges like
+    the run with the analytic g!."""
+    import lsob200 as L
+    from lsob200._lib import check, lib
+    m, n = 500, 12
+    rng = np.random.default_rng(8)
+    Ah = np.asfortranarray(rng.standard_normal((m, n)))
+    A = L.DenseMatrix(ctx, m, n, Ah)
+    xs = rng.standard_normal(n)
+    th = Ah @ xs
+    b = L.DeviceVector(ctx, m, th + 0.1 * th * th)
+    t = L.DeviceVector(ctx, m)
+
+    def f_(out, x):          # r = t + c t^2 - b, t = A x   (device kernels only)
+        check(lib().lso_synth_residual(ctx.handle, m, n, A.ptr, A.ld, x.ptr, b.ptr, 0.1, t.ptr, out.ptr), ctx.handle)
+
+    x0 = xs + 0.05 * rng.standard_normal(n)
+    x = L.DeviceVector(ctx, n, x0)
+    J = L.DenseMatrix(ctx, m, n)
+    nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m), f_=f_, g_=None, J=J, device_callbacks=True, ctx=ctx)
+    nls.g_(J, x)
+    assert np.array_equal(x.download(), x0)                      # x restored
+    Jfd = J.download()
+    t0 = Ah @ x0
+    Jan = (1.0 + 0.2 * t0)[:, None] * Ah
+    assert np.abs(Jfd - Jan).max() <= 1e-8 * np.abs(Jan).max()
+    # reference recipe on the host, same steps
+    h = np.cbrt(np.finfo(float).eps) * np.maximum(1.0, np.abs(x0))
+    col = 3
+    xp, xm = x0.copy(), x0.copy()
+    xp[col] += h[col]; xm[col] -= h[col]
+    fp = (Ah @ xp) + 0.1 * (Ah @ xp) ** 2
+    fm = (Ah @ xm) + 0.1 * (Ah @ xm) ** 2
+    assert np.abs(Jfd[:, col] - (fp - fm) / (2 * h[col])).max() <= 1e-7 * np.abs(Jan[:, col]).max()
+    r = L.optimize_(nls, L.LevenbergMarquardt(L.QR()))
+    assert r.converged and np.linalg.norm(r.minimizer.download() - xs) <= 1e-6
