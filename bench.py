@@ -312,6 +312,11 @@ def main():
     value = args.steps / (ms * 1e-3)
     last_ssr = state["run"].ssr if state["run"] else None
 
+    # ---- (f3) what a REJECTED step's solve costs: same J and f, larger damping (levenberg_marquardt.jl:77-87,135) ----
+    resolve = None
+    if world == 1:
+        resolve = measure_resolve(env, prob, anls, n)
+
     # ---- e2e: hot-path body from HOST buffers (J + f uploaded each step, δ + scalars downloaded) ----
     e2e = None
     if not args.no_e2e:
@@ -390,7 +395,7 @@ def main():
                    "l2_policy": f"inputs larger than L2: J is {8 * m_loc * n / 1e6:.0f} MB per GPU vs 126 MB L2",
                    "lm_restarts_in_run": state["restarts"], "last_ssr": last_ssr, "steps_accepted": state["accepted"],
                    "steps_rejected": state["rejected"],
-                   "wall_ms_per_step": wall_ms / args.steps},
+                   "wall_ms_per_step": wall_ms / args.steps, "rejected_step_solve": resolve},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "collective": ({"what": "ncclAllGather of the n x (n+1) [R | Q'f] factors, per step", "ms_per_step": coll_ms / args.steps,
                         "calls": coll_calls} if world > 1 else None),
@@ -401,6 +406,42 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_resolve(env, prob, anls, n):
+    """One damped solve on a fresh J (the QR of [J; sqrt(D)]) against the re-solve a rejected step needs (same J and f,
+    Δ halved: lso_qr_solve_redamp factors the 2n x n stack [R; sqrt(D_new - D_last)])."""
+    L, ctx = env.L, env.ctx
+    x = anls.x
+    x.copyto(prob.x0)
+    prob.f_(anls.fcur, x)
+    prob.g_(anls.J, x)
+    dtd, d2, dx = L.DeviceVector(ctx, n), L.DeviceVector(ctx, n), L.DeviceVector(ctx, n)
+    anls.J.colsumabs2(dtd)
+    from lsob200.api import _lm_damping
+    _lm_damping(ctx, dtd, 0.1)
+    state = {"delta": 1.0}
+
+    def fresh():
+        d2.copyto(dtd)
+        anls.solver.ldiv(dx, anls.J, anls.fcur, d2, same_J=False)
+
+    def rejected():
+        state["delta"] *= 2.0
+        d2.copyto(dtd).rmul(state["delta"])
+        anls.solver.ldiv(dx, anls.J, anls.fcur, d2, same_J=True)
+
+    fresh()
+    ms_f, _ = env.timed(fresh, 3)
+    fresh()
+    rejected()                      # first use creates (and tunes) the 2n x n stack workspace
+    before = anls.solver.solves_redamped
+    ms_r, _ = env.timed(rejected, 5)
+    return {"fresh_J_solve_ms": ms_f / 3, "rejected_step_solve_ms": ms_r / 5,
+            "redamped_solves": anls.solver.solves_redamped - before,
+            "note": "a rejected LM step re-solves with the same J, f and a larger damping: the triangular factor of the "
+                    "previous solve is re-damped (QR of [R; sqrt(D_new - D_last)], 2n x n banded) instead of refactoring "
+                    "[J; sqrt(D)]; parity tests/test_gpu_solvers.py::test_qr_redamp_after_rejected_steps"}
 
 
 def run_e2e(env, prob, anls, m_loc, n, args):
@@ -442,16 +483,27 @@ def run_e2e(env, prob, anls, m_loc, n, args):
     C.memmove(Jp.ctypes.data, hJ.value, m_loc * n * 8)
     C.memmove(fp.ctypes.data, hf.value, m_loc * 8)
     ms_p, wall_p, _ = measure(Jp.ctypes.data, fp.ctypes.data)
+    # the same arrays page-locked in place once (lso_host_register): what the glue does with a Julia J at allocation
+    check(lib().lso_host_register(ctx.handle, Jp.ctypes.data, m_loc * n * 8), ctx.handle)
+    check(lib().lso_host_register(ctx.handle, fp.ctypes.data, m_loc * 8), ctx.handle)
+    ms_r, wall_r, _ = measure(Jp.ctypes.data, fp.ctypes.data)
+    lib().lso_host_unregister(ctx.handle, Jp.ctypes.data)
+    lib().lso_host_unregister(ctx.handle, fp.ctypes.data)
     lib().lso_host_free_pinned(ctx.handle, hJ)
     lib().lso_host_free_pinned(ctx.handle, hf)
     res = {"value": K / (ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": (m_loc * n + m_loc) * 8,
            "d2h_bytes_per_step": (n + 4) * 8, "steps": K, "ms_per_step": ms / K, "wall_ms_per_step": wall / K,
-           "note": "per step: H2D of J and f from pinned host memory, colsumabs2 + damping + QR solve + J'f + "
-                   "predicted ssr on the device, D2H of δ and 4 scalars; user f!/g! evaluation excluded",
+           "note": "per step: H2D of J and f from pinned host memory (in row chunks, each chunk factorised while the next is in "
+                   "flight when row_chunks > 1), colsumabs2 + damping + QR solve + J'f + predicted ssr on the device, D2H of δ "
+                   "and 4 scalars; user f!/g! evaluation excluded",
            "pageable": {"value": K / (max(ms_p, wall_p) * 1e-3), "ms_per_step": max(ms_p, wall_p) / K,
                         "note": "same step with J and f in ordinary pageable host memory (numpy / Julia Array); "
                                 "the larger of device and wall time is reported because the driver stages pageable "
                                 "copies synchronously"},
+           "registered": {"value": K / (max(ms_r, wall_r) * 1e-3), "ms_per_step": max(ms_r, wall_r) / K,
+                          "note": "the same pageable arrays after ONE lso_host_register (cudaHostRegister in place): J, x, y "
+                                  "persist over the whole optimize! run, so the glue registers them at allocation"},
+           "row_chunks": hstep.chunks,
            "scalars": scal}
     return res
 

@@ -85,6 +85,10 @@ int lso_dev_alloc(lso_ctx* ctx, size_t nbytes, void** d_out);
 int lso_dev_free(lso_ctx* ctx, void* d_ptr);
 int lso_host_alloc_pinned(lso_ctx* ctx, size_t nbytes, void** h_out);
 int lso_host_free_pinned(lso_ctx* ctx, void* h_ptr);
+/* page-lock / release memory the caller owns (Julia Arrays are pageable; J, x, y live for the whole optimize! run,
+ * types.jl:141-157, so the glue registers them once and every H2D copy of J then runs at pinned-memory speed) */
+int lso_host_register(lso_ctx* ctx, void* h_ptr, size_t nbytes);
+int lso_host_unregister(lso_ctx* ctx, void* h_ptr);
 int lso_upload(lso_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);     /* synchronous */
 int lso_download(lso_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes);   /* synchronous */
 int lso_upload_async(lso_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);
@@ -194,7 +198,20 @@ int lso_debug_chol_solve_emulated_shards(lso_dense_ws* ws, int P, const double* 
  * lso_qr_kept_invalidate: J or y changed. */
 int lso_qr_factor_keep(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y);
 int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* rank_out);
+/* lso_qr_factor_keep fed from HOST memory (what `ldiv!` on plain Julia Arrays needs): J (m_total x n, ld_h) and y are
+ * copied in row chunks of the workspace's m rows on a copy stream and each chunk is factorised as soon as it has landed
+ * (TSQR over the chunks), so the PCIe transfer runs under the factorisation; J and y also end up in d_J (ld_d) / d_y.
+ * Follow with lso_qr_solve_kept (the damping is only needed there, so colsumabs2!(dtd, J) can wait for the whole J). */
+int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J, int64_t ld_h, const double* h_y,
+                            double* d_J, int64_t ld_d, double* d_y);
 int lso_qr_kept_invalidate(lso_dense_ws* ws);
+/* Cheaper still, and from the FIRST rejection on: the last damped solve on the workspace left R with R'R = J'J + D_last.
+ * A rejected LM step re-solves with the same J, f and a LARGER damping (Delta shrinks, levenberg_marquardt.jl:77-87,135),
+ * and J'J + D_new = R'R + (D_new - D_last): lso_qr_solve_redamp factors the banded 2n x n stack
+ * [R; sqrt(D_new - D_last)] (right-hand side [Q'y; 0]) — orthogonal transformations only, the same least-squares problem
+ * the reference refactors from scratch, at a cost independent of m.  Returns LSO_ERR_UNSUPPORTED (x untouched) when no
+ * damped factor is available (J or y changed: call lso_qr_kept_invalidate) or the damping did not grow elementwise. */
+int lso_qr_solve_redamp(lso_dense_ws* ws, const double* d_damp_new, double* d_x, int* rank_out);
 /* TSQR over row shards for the QR path: every rank passes its shard of J and y; all ranks get x. */
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                          const double* d_damp, double* d_x, int* rank_out);

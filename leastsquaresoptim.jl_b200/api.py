@@ -614,7 +614,7 @@ class HostStep:
     what the Julia glue does when `J` / `f` are plain host Arrays): H2D of J and f, colsumabs2! + damping (LM:82-86),
     the damped solve (:87), J'f and its max-norm (:102-104), ||Jδ - f||² (:114-117), then D2H of δ and the scalars."""
 
-    def __init__(self, anls: "_Allocated"):
+    def __init__(self, anls: "_Allocated", chunks: int | None = None):
         from ._lib import check, lib
         self.anls, self.ctx = anls, anls.ctx
         self.lib, self.check = lib(), check
@@ -625,30 +625,38 @@ class HostStep:
         self.dx, self.dtd, self.fpredict, self.red = w["dx"], w["dtd"], w["fpredict"], w["red"]
         self.grad = anls.workspace("lm_grad", lambda: dict(g=DeviceVector(ctx, n)))["g"]
         self.sharded = bool(anls.sharded)
+        # row chunks of the host-fed factorisation: 2 when each half still has many more rows than the per-panel latency
+        # floor is worth (measured at 100 000 x 1 000: 27.6 ms against 29.9 ms unchunked), else the plain path
+        self.chunks = chunks if chunks is not None else (2 if (not self.sharded and isinstance(anls.solver, DenseQRAllocatedSolver)
+                                                                and m >= 40 * n and m >= 50000) else 1)
+        if self.chunks > 1:
+            self.chunk_solver = DenseQRAllocatedSolver(ctx, -(-m // self.chunks), n, damped=False)
 
     def run(self, hJ_ptr: int, hf_ptr: int, Δ: float, dx_host: np.ndarray):
         a, ctx, h = self.anls, self.ctx, self.ctx.handle
         J, fcur, dx, dtd = a.J, a.fcur, self.dx, self.dtd
-        self.check(self.lib.lso_upload_async(h, J.ptr, hJ_ptr, a.m * a.n * 8), h)
-        self.check(self.lib.lso_upload_async(h, fcur.ptr, hf_ptr, a.m * 8), h)
-        ssr = fcur.sumabs2()
-        J.colsumabs2_and_grad(dtd, self.grad, fcur)          # LM:82 and LM:102 in one pass over J
-        if self.sharded:
-            ctx.allreduce(dtd)
-            ctx.allreduce(self.grad)
-        _lm_damping(ctx, dtd, 1 / Δ)
-        a.solver.ldiv(dx, J, fcur, dtd)
+        if self.chunks > 1:
+            # J and f cross PCIe in row chunks, each chunk is factorised (undamped) while the next one is in flight; the
+            # damping joins in the stacked finish, so colsumabs2! can wait for the whole J (levenberg_marquardt.jl:82-87)
+            self.chunk_solver.factor_keep_host(a.m, hJ_ptr, a.m, hf_ptr, J, fcur)
+            J.colsumabs2_and_grad(dtd, self.grad, fcur)
+            _lm_damping(ctx, dtd, 1 / Δ)
+            self.chunk_solver.solve_kept(dx, dtd)
+        else:
+            self.check(self.lib.lso_upload_async(h, J.ptr, hJ_ptr, a.m * a.n * 8), h)
+            self.check(self.lib.lso_upload_async(h, fcur.ptr, hf_ptr, a.m * 8), h)
+            J.colsumabs2_and_grad(dtd, self.grad, fcur)          # LM:82 and LM:102 in one pass over J
+            if self.sharded:
+                ctx.allreduce(dtd)
+                ctx.allreduce(self.grad)
+            _lm_damping(ctx, dtd, 1 / Δ)
+            a.solver.ldiv(dx, J, fcur, dtd)
         dtd.copyto(self.grad)
-        maxabs_gr = dtd.maxabs()
-        predicted_ssr = J.predicted_ssr(dx, fcur, self.fpredict)
-        if self.sharded:
-            buf = np.zeros(8)
-            buf[:2] = (ssr, predicted_ssr)
-            self.red.upload(buf)
-            ctx.allreduce(self.red)
-            ssr, predicted_ssr = (float(v) for v in self.red.download()[:2])
+        _gradient_norm_async(ctx, dtd, a.x, None, None)
+        # ssr = sum(abs2, fcur), ||J δ - f||², max|δ|, max|J'f|: one synchronisation (all-reduced over ranks when sharded)
+        ssr, predicted_ssr, maxabs_dx, maxabs_gr = _step_tail(ctx, J, dx, fcur, fcur, self.fpredict, self.sharded)
         dx.download(dx_host)
-        return {"ssr": ssr, "predicted_ssr": predicted_ssr, "maxabs_gr": maxabs_gr, "maxabs_dx": float(np.abs(dx_host).max())}
+        return {"ssr": ssr, "predicted_ssr": predicted_ssr, "maxabs_gr": maxabs_gr, "maxabs_dx": maxabs_dx}
 
 
 def optimize_(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, **kwargs) -> LeastSquaresResult:

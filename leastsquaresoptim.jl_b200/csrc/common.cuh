@@ -16,6 +16,8 @@ struct lso_ctx {
     int device = 0;
     int num_sms = LSO_NUM_SMS_DEFAULT;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // host-to-device copies that run under the factorisation (lso_qr_factor_keep_host)
+    cudaEvent_t copy_ev[18] = {};          // [0] = compute stream -> copy stream, [1 + k] = chunk k has landed
     // scratch for two-stage deterministic reductions
     double* d_partials = nullptr;      // LSO_PARTIALS doubles
     unsigned int* d_counters = nullptr; // ticket counters for last-block reductions (zeroed)

@@ -26,6 +26,13 @@ struct lso_dense_ws {
     // (f3) factor kept across the re-solves of a rejected trust-region step: [R_J | Q'y] of the last lso_qr_factor_keep /
     // sharded solve lives in d_gather; valid until J or y change
     bool kept = false;
+    // (f3) re-damping: the triangular factor [R | c] of the last DAMPED solve (in last_plan->A) and its damping vector;
+    // a re-solve with a larger damping on the same J, y is the QR of the 2n x n stack [R; sqrt(damp_new - damp_last)]
+    QRPlan* last_plan = nullptr;
+    QRPlan plan_redamp;
+    bool have_redamp = false;
+    double* d_lastdamp = nullptr;
+    double* d_redamp_slot = nullptr;   // n x (n+1) packed [R | c]  +  n doubles for the damping increment
 };
 
 // ---- Q-a: build [J; diag(sqrt(damp)) | y; 0] in the padded workspace (dense_qr.jl:32-36, 64-80) ----
@@ -85,6 +92,17 @@ static int qr_assemble(lso_ctx* ctx, QRPlan* p, int64_t m, int64_t n, const doub
 
 int small_qr_finish(lso_ctx* ctx, int64_t n, double* d_R, int64_t ld, double* d_c, double* d_x, int* rank_out);
 int qr_rank_screen(lso_ctx* ctx, int64_t n, const double* d_R, int64_t ld, double rcond, int* full_rank_out);
+
+// (f3) after a damped solve: plan->A holds [R | c] with R'R = J'J + D; keep D so that a later re-solve with MORE damping
+// on the same J, y (a rejected LM step, levenberg_marquardt.jl:77-87) only has to factor [R; sqrt(D_new - D)].
+static int remember_damped_factor(lso_dense_ws* ws, QRPlan* plan, const double* d_damp) {
+    lso_ctx* ctx = ws->ctx;
+    if (!d_damp) { ws->last_plan = nullptr; return LSO_OK; }
+    if (!ws->d_lastdamp) LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_lastdamp, (size_t)ws->n * sizeof(double)));
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(ws->d_lastdamp, d_damp, (size_t)ws->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    ws->last_plan = plan;
+    return LSO_OK;
+}
 
 // R (n x n upper, in plan->A) and c = Q'y (column Npad) -> x.  Full-rank fast path: back substitution.
 static int qr_finish(lso_dense_ws* ws, QRPlan* p, double* d_x, int* rank_out, bool undamped) {
@@ -157,6 +175,9 @@ int lso_dense_ws_destroy(lso_dense_ws* ws) {
     cudaStreamSynchronize(ctx->stream);
     qr_plan_destroy(&ws->plan);
     if (ws->have_stack) qr_plan_destroy(&ws->plan_stack);
+    if (ws->have_redamp) qr_plan_destroy(&ws->plan_redamp);
+    cudaFree(ws->d_lastdamp);
+    cudaFree(ws->d_redamp_slot);
     chol_plan_destroy(&ws->chol);
     cudaFree(ws->d_gather);
     cudaFree(ws->d_J); cudaFree(ws->d_y); cudaFree(ws->d_damp); cudaFree(ws->d_x);
@@ -174,9 +195,11 @@ int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* 
     // dense_qr.jl:61 — the damped form needs the (m+n)-row workspace, the undamped form the m-row one
     LSO_REQUIRE(ctx, (d_damp != nullptr) == (ws->damped != 0), "length(u) should equal length(x) + length(y)");
     LSO_ENTER(ctx);
+    ws->last_plan = nullptr;
     LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, ws->n, d_J, ld, d_y, d_damp));
     LSO_TRY(qr_factor(ctx, &ws->plan));
-    return qr_finish(ws, &ws->plan, d_x, rank_out, d_damp == nullptr);
+    LSO_TRY(qr_finish(ws, &ws->plan, d_x, rank_out, d_damp == nullptr));
+    return remember_damped_factor(ws, &ws->plan, d_damp);
 }
 
 static int ensure_staging(lso_dense_ws* ws, int64_t ld) {
@@ -318,12 +341,13 @@ __global__ void stack_assemble_kernel(long long n, int P, int Q, const double* _
 }
 
 // local QR of [J_k | y_k] and its n x (n+1) [R | Q'y] packed into `slot`
-static int shard_local_R(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, double* slot) {
+static int shard_local_R(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, double* slot, int64_t rows = -1) {
     lso_ctx* ctx = ws->ctx;
     const int64_t n = ws->n;
-    LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, n, d_J, ld, d_y, nullptr));
+    if (rows < 0) rows = ws->m;
+    LSO_TRY(qr_assemble(ctx, &ws->plan, rows, n, d_J, ld, d_y, nullptr));
     const int64_t M_full = ws->plan.M;
-    ws->plan.M = ws->m;               // a damped workspace has m + n rows: only the m rows of J are in use here
+    ws->plan.M = std::max<int64_t>(rows, n);   // a damped workspace has m + n rows: only the rows of J are in use here
     const int st = qr_factor(ctx, &ws->plan);
     ws->plan.M = M_full;
     LSO_TRY(st);
@@ -362,8 +386,10 @@ static int shard_stack_solve(lso_dense_ws* ws, int P, const double* d_damp, doub
     LSO_CHECK_LAUNCH(ctx);
     ps->M = (int64_t)Q * n;       // rows in use (the workspace was sized for P + 1 triangles)
     ps->band = Q;
+    ws->last_plan = nullptr;
     LSO_TRY(qr_factor(ctx, ps));
-    return qr_finish(ws, ps, d_x, rank_out, d_damp == nullptr);
+    LSO_TRY(qr_finish(ws, ps, d_x, rank_out, d_damp == nullptr));
+    return remember_damped_factor(ws, ps, d_damp);
 }
 
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
@@ -410,6 +436,47 @@ int lso_qr_factor_keep(lso_dense_ws* ws, const double* d_J, int64_t ld, const do
     return LSO_OK;
 }
 
+// The same, fed from HOST memory in P row chunks: chunk k (ws->m rows, the last one possibly shorter) is copied to the
+// device on a copy stream while chunk k-1 is being factorised (TSQR over the chunks), so the H2D transfer of J — 14.5 ms
+// of a 30 ms end-to-end LM step at 100 000 x 1 000 — runs under the factorisation instead of in front of it.  J and y
+// also land in d_J (ld_d) / d_y for the passes of the iteration that need them whole.  Follow with lso_qr_solve_kept.
+int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J, int64_t ld_h, const double* h_y,
+                            double* d_J, int64_t ld_d, double* d_y) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && h_J && h_y && d_J && d_y, "bad arguments");
+    const int64_t mc = ws->m, n = ws->n;
+    const int P = (int)cdiv64(m_total, mc);
+    LSO_REQUIRE(ctx, P >= 1 && P <= 16, "between 1 and 16 row chunks");
+    LSO_REQUIRE(ctx, ld_h >= m_total && ld_d >= m_total, "leading dimension < rows");
+    LSO_REQUIRE(ctx, mc >= n && m_total - (int64_t)(P - 1) * mc >= 1, "every chunk needs rows >= columns (the last one at least 1 row)");
+    LSO_ENTER(ctx);
+    ws->kept = false;
+    ws->last_plan = nullptr;
+    if (!ctx->copy_stream) {
+        LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->copy_ev) LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    LSO_TRY(shard_ensure_stack(ws, P));
+    // the copies may not overtake earlier readers of d_J / d_y on the compute stream
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+    for (int k = 0; k < P; ++k) {
+        const int64_t r0 = (int64_t)k * mc, rows = std::min<int64_t>(mc, m_total - r0);
+        LSO_CHECK_CUDA(ctx, cudaMemcpy2DAsync(d_J + r0, ld_d * sizeof(double), h_J + r0, ld_h * sizeof(double), rows * sizeof(double),
+                                              n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_y + r0, h_y + r0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+        LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1 + k], ctx->copy_stream));
+    }
+    for (int k = 0; k < P; ++k) {
+        const int64_t r0 = (int64_t)k * mc, rows = std::min<int64_t>(mc, m_total - r0);
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1 + k], 0));
+        LSO_TRY(shard_local_R(ws, d_J + r0, ld_d, d_y + r0, ws->d_gather + (size_t)k * n * (n + 1), rows));
+    }
+    ws->kept = true;
+    return LSO_OK;
+}
+
 int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* rank_out) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     lso_ctx* ctx = ws->ctx;
@@ -422,7 +489,70 @@ int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* 
 int lso_qr_kept_invalidate(lso_dense_ws* ws) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     ws->kept = false;
+    ws->last_plan = nullptr;
     return LSO_OK;
+}
+
+// e[i] = new[i] - last[i]; *flag = 1 when some e[i] is negative beyond rounding (the increment must be >= 0)
+__global__ void redamp_increment_kernel(long long n, const double* __restrict__ dnew, const double* __restrict__ dlast,
+                                        double* __restrict__ e, int* __restrict__ flag) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double d = dnew[i] - dlast[i];
+        if (!(d >= -4.0e-16 * fabs(dlast[i]))) *flag = 1;      // also catches NaN
+        e[i] = d > 0.0 ? d : 0.0;
+    }
+}
+
+// (f3) Re-solve after a REJECTED trust-region step (levenberg_marquardt.jl:77-87: same J, same f, Δ shrunk, i.e. a
+// LARGER damping D_new >= D_last elementwise).  The last damped solve on this workspace left R with R'R = J'J + D_last
+// and c = Q'[y; 0]; since J'J + D_new = R'R + (D_new - D_last), the triangular factor of the new system is the R of
+//     [ R ; sqrt(D_new - D_last) ]   (2n x n, banded: cost independent of m),   right-hand side [c ; 0],
+// obtained by orthogonal transformations only — the same least-squares problem min ||[J; sqrt(D_new)] x - [y; 0]|| that the
+// reference refactors from scratch (dense_qr.jl:64-88).  No pass over J, no collective on a sharded workspace.
+// Returns LSO_ERR_UNSUPPORTED (and leaves x untouched) when there is no damped factor to start from or the damping did
+// not grow; the caller then solves the ordinary way.
+int lso_qr_solve_redamp(lso_dense_ws* ws, const double* d_damp_new, double* d_x, int* rank_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && d_damp_new && d_x, "bad arguments");
+    if (!ws->last_plan) return lso_set_error(ctx, LSO_ERR_UNSUPPORTED, "no damped factor to re-damp");
+    LSO_ENTER(ctx);
+    const int64_t n = ws->n;
+    if (!ws->have_redamp) {
+        LSO_TRY(qr_plan_create(ctx, 2 * n, n, &ws->plan_redamp));
+        ws->have_redamp = true;
+        ws->plan_redamp.band = 2;
+        LSO_TRY(qr_plan_tune(ctx, &ws->plan_redamp));
+        LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_redamp_slot, ((size_t)n * (n + 1) + (size_t)n + 2) * sizeof(double)));
+    }
+    double* slot = ws->d_redamp_slot;
+    double* inc = slot + (size_t)n * (n + 1);
+    int* flag = (int*)(inc + n);
+    LSO_CHECK_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    redamp_increment_kernel<<<(unsigned)std::min<int64_t>(cdiv64(n, 256), 1024), 256, 0, ctx->stream>>>(n, d_damp_new, ws->d_lastdamp, inc, flag);
+    LSO_CHECK_LAUNCH(ctx);
+    int h_flag = 0;
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_flag) return lso_set_error(ctx, LSO_ERR_UNSUPPORTED, "re-damping needs damp_new >= damp_last elementwise");
+    QRPlan* src = ws->last_plan;
+    {
+        dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 64), (unsigned)(n + 1));
+        pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, src->A, src->ld, src->Npad, slot);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    QRPlan* ps = &ws->plan_redamp;
+    {
+        dim3 grid((unsigned)std::min<int64_t>(cdiv64(ps->ld, 256), 64), (unsigned)ps->Nc);
+        stack_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(n, 1, 2, slot, inc, ps->A, ps->ld, ps->Npad);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    ps->M = 2 * n;
+    ps->band = 2;
+    ws->last_plan = nullptr;
+    LSO_TRY(qr_factor(ctx, ps));
+    LSO_TRY(qr_finish(ws, ps, d_x, rank_out, false));
+    return remember_damped_factor(ws, ps, d_damp_new);
 }
 
 // Test hook: the sharded algorithm with the P shards emulated on ONE device (the rows of J are cut into P equal

@@ -16,6 +16,8 @@ import weakref
 from ._lib import check, lib
 from .device import Context, CSCMatrix, DenseMatrix, DeviceVector
 
+LSO_ERR_UNSUPPORTED = -5
+
 LSO_SOLVER_QR = 1
 LSO_SOLVER_CHOLESKY = 2
 
@@ -39,7 +41,10 @@ class _DenseWorkspace:
 class DenseQRAllocatedSolver(_DenseWorkspace):
     """dense_qr.jl: Dogleg{QR} workspace (m x n, :25-28) or LevenbergMarquardt{QR} workspace ((m+n) x n, :50-54).
 
-    `reuse` (f3; levenberg_marquardt.jl:77-87 re-solves with the same J and f after a rejected step):
+    `reuse` (f3; levenberg_marquardt.jl:77-87 re-solves with the same J and f after a rejected step).  Unless "off", a
+    re-solve with a LARGER damping (what a rejected LM step is) re-damps the triangular factor of the previous solve
+    (lso_qr_solve_redamp: QR of the banded 2n x n stack [R; sqrt(D_new - D_last)], no pass over J).  When that does not
+    apply (the damping shrank):
       "lazy"    a fresh J is solved by the direct QR of [J; sqrt(D)]; the FIRST re-solve with the same J factors J once
                 (lso_qr_factor_keep) and every re-solve costs only the banded 2n x n stack QR (lso_qr_solve_kept)
       "always"  every fresh J is factored undamped and finished through the stack
@@ -52,13 +57,27 @@ class DenseQRAllocatedSolver(_DenseWorkspace):
         self.sharded = sharded      # J, y are this rank's row shard: TSQR over the context's communicator
         self.reuse = reuse if m >= n else "off"
         self._kept = False
-        self.solves_direct = self.solves_kept = self.factor_keeps = 0
+        self._have_damped = False
+        self.solves_direct = self.solves_kept = self.factor_keeps = self.solves_redamped = 0
 
     def ldiv(self, x: DeviceVector, J: DenseMatrix, y: DeviceVector, damp: DeviceVector | None = None, same_J: bool = False):
         rank = C.c_int()
         h = self.ctx.handle
         dptr = damp.ptr if damp is not None else None
         use_keep = self.reuse != "off" and damp is not None
+        if use_keep and same_J and self._have_damped:
+            # a rejected step: same J and f, larger damping — re-damp the triangular factor of the last solve
+            st = lib().lso_qr_solve_redamp(self._h, dptr, x.ptr, C.byref(rank))
+            if st == 0:
+                self.solves_redamped += 1
+                self.last_rank = rank.value
+                return x, 1
+            if st != LSO_ERR_UNSUPPORTED:
+                check(st, h)
+        if not same_J:
+            check(lib().lso_qr_kept_invalidate(self._h), h)
+            self._kept = False
+        self._have_damped = False
         if use_keep and same_J and self._kept:
             check(lib().lso_qr_solve_kept(self._h, dptr, x.ptr, C.byref(rank)), h)
             self.solves_kept += 1
@@ -76,7 +95,24 @@ class DenseQRAllocatedSolver(_DenseWorkspace):
             check(lib().lso_qr_solve(self._h, J.ptr, J.ld, y.ptr, dptr, x.ptr, C.byref(rank)), h)
             self._kept = False
             self.solves_direct += 1
+        self._have_damped = damp is not None
         self.last_rank = rank.value
+        return x, 1
+
+
+    # ---- host-fed, chunk-pipelined form (the end-to-end path when J lives in host memory) ----
+    def factor_keep_host(self, m_total: int, hJ_ptr: int, ld_h: int, hy_ptr: int, J: DenseMatrix, y: DeviceVector):
+        """QR of [J | y] from HOST memory in row chunks of this workspace's m rows, each chunk factorised while the next
+        one is still crossing PCIe (lso_qr_factor_keep_host); J and y also land in the device arrays given."""
+        check(lib().lso_qr_factor_keep_host(self._h, m_total, hJ_ptr, ld_h, hy_ptr, J.ptr, J.ld, y.ptr), self.ctx.handle)
+        self._kept, self._have_damped = True, False
+
+    def solve_kept(self, x: DeviceVector, damp: DeviceVector | None):
+        rank = C.c_int()
+        check(lib().lso_qr_solve_kept(self._h, damp.ptr if damp is not None else None, x.ptr, C.byref(rank)), self.ctx.handle)
+        self.last_rank = rank.value
+        self._have_damped = damp is not None
+        self.solves_kept += 1
         return x, 1
 
 

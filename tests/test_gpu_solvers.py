@@ -451,7 +451,8 @@ def test_lm_with_rejected_steps_reuses_the_factor(ctx, solver):
     anls = L.allocate(nls, L.LevenbergMarquardt(solc()))
     r = L.optimize_(anls, Δ=1e6)
     ro = O.optimize(f, g, x0.copy(), np.zeros((2, 2), order="F"), 2, optimizer="lm", solver=solver, delta=1e6)
-    assert anls.solver.solves_kept >= 1, "no step was rejected: the test does not exercise the re-solve"
+    resolves = anls.solver.solves_kept + getattr(anls.solver, "solves_redamped", 0)
+    assert resolves >= 1, "no step was rejected: the test does not exercise the re-solve"
     assert (r.iterations, r.f_calls, r.g_calls) == (ro.iterations, ro.f_calls, ro.g_calls)
     assert np.linalg.norm(r.minimizer - ro.minimizer) <= 1e-9
 
@@ -534,3 +535,62 @@ def test_qr_hidden_ill_conditioning_takes_the_rank_revealing_path(ctx):
     ws.ldiv(x, L.DenseMatrix(ctx, n + 10, n, Jh), L.DeviceVector(ctx, n + 10, yh))
     assert ws.last_rank == rk
     assert rel(x.download(), xr) <= 1e-9
+
+
+@pytest.mark.parametrize("m,n", [(4000, 96), (20000, 520), (100000, 1000)])
+def test_qr_redamp_after_rejected_steps(ctx, m, n):
+    """lso_qr_solve_redamp: after a damped solve, the solves with the same J, y and successively LARGER dampings (rejected LM
+    steps: Δ -> Δ/2 -> Δ/8 ..., levenberg_marquardt.jl:135-137) re-factor only [R; sqrt(D_new - D_last)] and still give the
+    reference's δ to 1e-10; a smaller damping is refused (the caller then solves the ordinary way)."""
+    import lsob200 as L
+    from lsob200._lib import lib
+    rng = np.random.default_rng(m + 7 * n)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)) * (1.0 + 10.0 * rng.random(n)))
+    yh = rng.standard_normal(m)
+    J, y, x = L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh), L.DeviceVector(ctx, n)
+    ws = L.DenseQRAllocatedSolver(ctx, m, n, damped=True)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    delta = 10.0
+    ws.ldiv(x, J, y, L.DeviceVector(ctx, n, dtd / delta))
+    for k, factor in enumerate((2.0, 4.0, 8.0, 16.0)):          # decrease_factor doubles at every rejection
+        delta /= factor
+        d = L.DeviceVector(ctx, n, dtd / delta)
+        ws.ldiv(x, J, y, d, same_J=True)
+        xr, _ = O.qr_ldiv(Jh, yh, dtd / delta)
+        assert rel(x.download(), xr) <= 1e-10, (k, rel(x.download(), xr))
+    assert ws.solves_redamped == 4 and ws.solves_direct == 1
+    rank = C.c_int()
+    d = L.DeviceVector(ctx, n, dtd / 100.0)                     # less damping than the last solve: not a re-damping
+    assert lib().lso_qr_solve_redamp(ws._h, d.ptr, x.ptr, C.byref(rank)) == -5
+    ws.ldiv(x, J, y, d, same_J=True)                            # the solver falls back by itself
+    xr, _ = O.qr_ldiv(Jh, yh, dtd / 100.0)
+    assert rel(x.download(), xr) <= 1e-10
+
+
+@pytest.mark.parametrize("chunks", [2, 3])
+def test_host_step_chunked_upload_matches_the_direct_solve(ctx, chunks):
+    """The end-to-end path from HOST memory (HostStep / lso_qr_factor_keep_host): J and f cross PCIe in row chunks that are
+    factorised as they land (TSQR) and the damping joins in the stacked finish — same δ and step scalars as uploading
+    everything and solving [J; sqrt(D)] directly; chunk sizes that do not divide m are covered."""
+    import lsob200 as L
+    m, n = 60001, 300
+    rng = np.random.default_rng(12)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)))
+    fh = rng.standard_normal(m)
+    out = {}
+    for c in (chunks, 1):
+        x = L.DeviceVector(ctx, n)
+        nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m), f_=lambda o, xx: None, g_=lambda JJ, xx: None,
+                                    J=L.DenseMatrix(ctx, m, n), device_callbacks=True, ctx=ctx)
+        anls = L.allocate(nls, L.LevenbergMarquardt(L.QR()))
+        hs = L.HostStep(anls, chunks=c)
+        dx = np.zeros(n)
+        for _ in range(2):                       # twice: the second call re-uses every workspace
+            sc = hs.run(Jh.ctypes.data, fh.ctypes.data, 10.0, dx)
+        out[c] = (dx.copy(), sc)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0
+    xr, _ = O.qr_ldiv(Jh, fh, damp)
+    assert rel(out[chunks][0], xr) <= 1e-10 and rel(out[1][0], xr) <= 1e-10
+    for k in ("ssr", "predicted_ssr", "maxabs_gr", "maxabs_dx"):
+        assert abs(out[chunks][1][k] - out[1][1][k]) <= 1e-9 * abs(out[1][1][k]), k
