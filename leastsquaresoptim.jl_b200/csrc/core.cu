@@ -416,8 +416,9 @@ __global__ void box_project_kernel(int64_t n, double* __restrict__ d, const doub
                                    const double* __restrict__ lo, const double* __restrict__ hi) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double v = d[i];
-        if (lo) v = fmin(v, x[i] - lo[i]);
-        if (hi) v = fmax(v, x[i] - hi[i]);
+        // Julia's min / max propagate NaN (fmin / fmax would silently clamp a NaN step to the bound)
+        if (lo) { const double b = x[i] - lo[i]; v = (v != v || b != b) ? NAN : (b < v ? b : v); }
+        if (hi) { const double b = x[i] - hi[i]; v = (v != v || b != b) ? NAN : (b > v ? b : v); }
         d[i] = v;
     }
 }

@@ -4,8 +4,9 @@ the multi-GPU tests and the CPU (gloo) tests.
   * `row_partition(m, world)`            contiguous row blocks, sizes differ by at most one
   * `init_comm(ctx)`                     NCCL communicator for the C-ABI context; the 128-byte id travels over
                                          torch.distributed (plumbing only)
-  * `stack_layout(n, world)`             row offsets of the R_k factors / sqrt(D) block in the TSQR stack that
+  * `stack_layout(n, world)`             the row-interleaved stack of the R_k factors and the sqrt(D) triangle that
                                          `lso_qr_solve_sharded` factorises on every rank
+  * `packed_upper_layout(n)`             the packed [upper(J'J) | J'y] buffer of the sharded Cholesky path's all-reduce
 """
 from __future__ import annotations
 
@@ -18,11 +19,22 @@ def row_partition(m: int, world: int):
     return [(edges[r], edges[r + 1] - edges[r]) for r in range(world)]
 
 
-def stack_layout(n: int, world: int):
-    """TSQR stack: rows [k*n, (k+1)*n) hold R_k (upper triangular), rows [world*n, world*n + n) hold diag(sqrt(damp)),
-    the right-hand side column holds [Q_0'y_0; ...; Q_{P-1}'y_{P-1}; 0]."""
-    return {"R_rows": [(k * n, (k + 1) * n) for k in range(world)], "damp_rows": (world * n, world * n + n),
-            "rows": world * n + n, "cols": n + 1}
+def stack_layout(n: int, world: int, damped: bool = True):
+    """TSQR stack as `stack_assemble_kernel` (csrc/dense_solve.cu) builds it: the P = world upper-triangular R_k and, when
+    damped, diag(sqrt(damp)) as one more triangle, with their rows INTERLEAVED — stack row Q*r + i is row r of triangle i
+    (Q = P + 1 with damping, else P).  Stack row rho then has no entry left of column rho // Q, which is what lets panel j
+    of the replicated QR stop at row Q*32*(j+1) (`QRPlan::band`).  The right-hand side column is interleaved the same way
+    ([Q_k'y_k] for the R triangles, 0 for the damping triangle).
+    Returns {"Q", "rows", "cols", "row_of": f(triangle, r) -> stack row, "damp_triangle": index or None}."""
+    Q = world + 1 if damped else world
+    return {"Q": Q, "rows": Q * n, "cols": n + 1, "row_of": (lambda tri, r: Q * r + tri),
+            "damp_triangle": world if damped else None}
+
+
+def packed_upper_layout(n: int):
+    """The buffer of the ONE all-reduce of the row-sharded Cholesky path (`chol_pack_kernel`, csrc/chol.cu):
+    [upper(J'J) by columns | J'y]: entry (i, j), i <= j, at j*(j+1)//2 + i; J'y at n*(n+1)//2 + i; n(n+1)/2 + n doubles."""
+    return {"len": n * (n + 1) // 2 + n, "index": (lambda i, j: j * (j + 1) // 2 + i), "rhs0": n * (n + 1) // 2}
 
 
 def init_comm(ctx, dist=None):

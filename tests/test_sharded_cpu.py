@@ -16,7 +16,7 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     import torch
     import lsob200  # noqa: F401
-    from lsob200.sharding import row_partition, stack_layout
+    from lsob200.sharding import packed_upper_layout, row_partition, stack_layout
     from oracle import reference_port as O
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,19 +33,35 @@ def _worker(rank, world, port, out):
     Rk = np.triu(R[:n, :])                                   # n x (n+1): [R_k | Q_k' y_k]
     gathered = [torch.zeros(n, n + 1, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(gathered, torch.from_numpy(Rk.copy()))
-    lay = stack_layout(n, world)
+    lay = stack_layout(n, world)                             # the INTERLEAVED layout the device kernel builds
     S = np.zeros((lay["rows"], lay["cols"]))
-    for k, (a, b) in enumerate(lay["R_rows"]):
-        S[a:b] = gathered[k].numpy()
-    a, b = lay["damp_rows"]
-    S[a:b, :n] = np.diag(np.sqrt(damp))
+    for k in range(world):
+        for r in range(n):
+            S[lay["row_of"](k, r)] = gathered[k].numpy()[r]
+    for r in range(n):
+        S[lay["row_of"](lay["damp_triangle"], r), r] = np.sqrt(damp[r])
+    # the band property the replicated QR relies on: stack row rho has no entry left of column rho // Q
+    for rho in range(lay["rows"]):
+        assert not S[rho, :min(rho // lay["Q"], n)].any()
     x_tsqr = np.linalg.lstsq(S[:, :n], S[:, n], rcond=None)[0]
     x_ref, _ = O.qr_ldiv(J, y, damp.copy())
     # ---- Cholesky: one all-reduce of the packed [J'J | J'y] ----
-    packed = torch.from_numpy(np.concatenate([(Jk.T @ Jk).ravel(), Jk.T @ yk]))
+    pk = packed_upper_layout(n)                              # [upper(J'J) by columns | J'y]: n(n+1)/2 + n doubles
+    G, g = Jk.T @ Jk, Jk.T @ yk
+    buf = np.zeros(pk["len"])
+    for j in range(n):
+        for i in range(j + 1):
+            buf[pk["index"](i, j)] = G[i, j]
+    buf[pk["rhs0"]:] = g
+    packed = torch.from_numpy(buf)
     dist.all_reduce(packed)
-    C = packed.numpy()[:n * n].reshape(n, n) + np.diag(damp)
-    x_chol = np.linalg.solve(C, packed.numpy()[n * n:])
+    tot = packed.numpy()
+    C = np.zeros((n, n))
+    for j in range(n):
+        for i in range(j + 1):
+            C[i, j] = C[j, i] = tot[pk["index"](i, j)]
+    C += np.diag(damp)
+    x_chol = np.linalg.solve(C, tot[pk["rhs0"]:])
     out[rank] = (float(np.linalg.norm(x_tsqr - x_ref) / np.linalg.norm(x_ref)),
                  float(np.linalg.norm(x_chol - x_ref) / np.linalg.norm(x_ref)), rows)
     dist.barrier()
