@@ -1,6 +1,7 @@
 # LeastSquaresOptimB200.jl — Julia-side glue that puts liblsob200.so behind LeastSquaresOptim.jl's own plugin
-# surface.  NOT executable in this repository's image (no Julia here or on the GPU box); it is the binding a
-# maintainer adds, kept next to the C header it binds (include/lsob200.h).  The Python package
+# surface.  NOT executable in this repository's image (no Julia here or on the GPU box): it is a SKETCH of the binding a
+# maintainer adds, kept next to the C header it binds (include/lsob200.h) and never run — treat it as documentation of
+# which ABI entry point each reference call site binds, not as tested code.  The Python package
 # `leastsquaresoptim.jl_b200/` mirrors exactly these types and methods and is what the tests drive.
 #
 # Nothing in LeastSquaresOptim.jl changes: the package dispatches on the solver type
@@ -66,6 +67,12 @@ AbstractAllocatedSolver(nls::LeastSquaresProblem, ::Dogleg{B200Cholesky}) =
 AbstractAllocatedSolver(nls::LeastSquaresProblem, ::LevenbergMarquardt{B200Cholesky}) =
     B200DenseWorkspace(length(nls.y), length(nls.x), 2, 1)
 
+# Julia Arrays are pageable: J, x, y live for the whole optimize! run (types.jl:141-157), so they are page-locked ONCE,
+# when the allocated problem is built; every later H2D copy of J then runs at pinned speed (28 ms instead of 95 ms per
+# step at 100 000 x 1 000).  Call `unpin!` when the problem is dropped.
+pin!(a::Array{Float64}) = (check(ccall((:lso_host_register, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx().h, a, sizeof(a)), ctx().h); a)
+unpin!(a::Array{Float64}) = (ccall((:lso_host_unregister, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx().h, a); a)
+
 # host-Array form: `ldiv!` as called at dogleg.jl:115 and levenberg_marquardt.jl:87.  Returns (x, n_mul) like
 # dense_qr.jl:41,87 / dense_cholesky.jl:34,58.
 function _solve_host(A::B200DenseWorkspace, x, J::StridedMatrix{Float64}, y, damp)
@@ -101,6 +108,22 @@ mutable struct B200Vector <: AbstractVector{Float64}
 end
 Base.size(v::B200Vector) = (v.n,)
 Base.similar(v::B200Vector) = B200Vector(v.n)
+# Scalar indexing: the reference's loops touch single elements only in the box projection (LM:89-98, dogleg:148-157) and
+# in the bounds check `all(x .>= lower)` (LM:51, dogleg:52) — both are overridden below by ONE kernel each, so these two
+# methods exist for completeness (show, tests, user code) and cost a PCIe round trip per element.
+function Base.getindex(v::B200Vector, i::Int)
+    @boundscheck checkbounds(v, i)
+    r = Ref{Float64}(0)
+    check(ccall((:lso_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx().h, r, v.p + 8 * (i - 1), 8), ctx().h)
+    r[]
+end
+function Base.setindex!(v::B200Vector, a, i::Int)
+    @boundscheck checkbounds(v, i)
+    r = Ref{Float64}(a)
+    check(ccall((:lso_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx().h, v.p + 8 * (i - 1), r, 8), ctx().h)
+    a
+end
+Base.IndexStyle(::Type{B200Vector}) = IndexLinear()
 B200Vector(h::Vector{Float64}) = copyto!(B200Vector(length(h)), h)
 Base.copyto!(d::B200Vector, h::Vector{Float64}) =
     (GC.@preserve h check(ccall((:lso_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx().h, d.p, h, 8d.n)); d)
@@ -131,6 +154,28 @@ function wdot(x::B200Vector, y::B200Vector, w::B200Vector)          # src/utils/
     r = Ref{Float64}(0)
     check(ccall((:lso_vec_wdot, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
                 ctx().h, x.n, x.p, y.p, w.p, r)); r[]
+end
+# maxabs_projected_gradient(g, x, lower, upper) (src/utils/utils.jl:38-55) and the box projection of the step
+# (levenberg_marquardt.jl:89-98, dogleg.jl:148-157: δx[i] = min(δx[i], x[i] - lower[i]) / max(…, x[i] - upper[i])), one
+# kernel each instead of an element loop.  `lower` / `upper` are B200Vectors (or empty Vectors = no bound).
+_bptr(b) = (b isa B200Vector && length(b) > 0) ? b.p : Ptr{Float64}(C_NULL)
+function LeastSquaresOptim.maxabs_projected_gradient(g::B200Vector, x::B200Vector, lower, upper)
+    r = Ref{Float64}(0)
+    check(ccall((:lso_vec_maxabs_projected, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                ctx().h, g.n, g.p, x.p, _bptr(lower), _bptr(upper), r), ctx().h); r[]
+end
+box_project!(δx::B200Vector, x::B200Vector, lower, upper) =
+    (check(ccall((:lso_vec_box_project, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                 ctx().h, δx.n, δx.p, x.p, _bptr(lower), _bptr(upper)), ctx().h); δx)
+# the four reductions of an iteration with ONE synchronisation (LM:104,110,114-117; utils.jl:21), see lso_lm_step_tail
+function step_tail(J, δx::B200Vector, fcur::B200Vector, ftrial::B200Vector, fpredict::B200Vector)
+    out = zeros(4)
+    dJ, ld, csc = J isa B200Matrix ? (J.p, J.m, C_NULL) : (Ptr{Float64}(C_NULL), 0, J.h)
+    check(ccall((:lso_lm_step_tail, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}),
+                ctx().h, size(J, 1), size(J, 2), dJ, ld, csc, δx.p, fcur.p, ftrial.p, fpredict.p, 0, out), ctx().h)
+    (trial_ssr = out[1], predicted_ssr = out[2], maxabs_dx = out[3], maxabs_gr = out[4])
 end
 LeastSquaresOptim.check_isfinite(v::B200Vector) = begin                # src/utils/utils.jl:70-78
     bad = Ref{Int64}(-1)
@@ -175,10 +220,12 @@ function LinearAlgebra.ldiv!(x::B200Vector, J::B200Matrix, y::B200Vector, A::B20
 end
 
 # ---- sparse operator + LSMR (src/solver/iterative_lsmr.jl:161-259) ------------------------------------------------
-mutable struct B200SparseMatrixCSC          # device image of a SparseMatrixCSC{Float64,Int64}; pattern fixed, values refreshed
+mutable struct B200SparseMatrixCSC <: AbstractMatrix{Float64}   # device image of a SparseMatrixCSC{Float64,Int64}
     h::Ptr{Cvoid}
     host::SparseMatrixCSC{Float64,Int64}
 end
+Base.size(A::B200SparseMatrixCSC) = size(A.host)
+Base.getindex(A::B200SparseMatrixCSC, i::Int, j::Int) = A.host[i, j]     # host mirror (display only; values as of the last refresh!)
 function B200SparseMatrixCSC(J::SparseMatrixCSC{Float64,Int64})
     r = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve J check(ccall((:lso_csc_create, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
@@ -188,10 +235,18 @@ function B200SparseMatrixCSC(J::SparseMatrixCSC{Float64,Int64})
 end
 # after g!(J, x) rewrote nonzeros(J) (test/nonlinearleastsquares.jl:47-86): values-only refresh
 refresh!(A::B200SparseMatrixCSC) = check(ccall((:lso_csc_set_values_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), A.h, nonzeros(A.host)))
-Base.size(A::B200SparseMatrixCSC, d) = size(A.host, d)
+# g! stored a DIFFERENT pattern (setindex! into a sparse J, test/nonlinearsolvers.jl:526-530): re-import colptr / rowval
+function refresh_pattern!(A::B200SparseMatrixCSC)
+    J = A.host
+    GC.@preserve J check(ccall((:lso_csc_update_pattern, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}),
+                               A.h, nnz(J), J.colptr, J.rowval), ctx().h)
+    refresh!(A)
+end
 colsumabs2!(v::B200Vector, A::B200SparseMatrixCSC) = (check(ccall((:lso_csc_colsumabs2, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), A.h, v.p)); v)
-LinearAlgebra.mul!(y::B200Vector, A::B200SparseMatrixCSC, x::B200Vector, α::Number, β::Number) =
+LinearAlgebra.mul!(y::B200Vector, A::B200SparseMatrixCSC, x::B200Vector, α::Number, β::Number) =      # LM:114, dogleg:109,171
     (check(ccall((:lso_csc_mul_n, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Float64, Ptr{Float64}), A.h, α, x.p, β, y.p)); y)
+LinearAlgebra.mul!(x::B200Vector, At::Adjoint{Float64,B200SparseMatrixCSC}, y::B200Vector, α::Number, β::Number) =   # LM:102, dogleg:99
+    (A = parent(At); check(ccall((:lso_csc_mul_t, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Float64, Ptr{Float64}), A.h, α, y.p, β, x.p)); x)
 
 mutable struct B200LSMRWorkspace <: AbstractAllocatedSolver
     h::Ptr{Cvoid}
@@ -218,5 +273,6 @@ end
 LinearAlgebra.ldiv!(x::B200Vector, J, y::B200Vector, A::B200LSMRWorkspace) = _lsmr(A, x, J, y, nothing, 1e-6)            # :179-198
 LinearAlgebra.ldiv!(x::B200Vector, J, y::B200Vector, damp::B200Vector, A::B200LSMRWorkspace) = _lsmr(A, x, J, y, damp, 0.5)  # :238-259
 
-export B200QR, B200Cholesky, B200LSMR, B200Vector, B200Matrix, B200SparseMatrixCSC, refresh!
+export B200QR, B200Cholesky, B200LSMR, B200Vector, B200Matrix, B200SparseMatrixCSC, refresh!, refresh_pattern!,
+       box_project!, step_tail, pin!, unpin!
 end # module
