@@ -36,7 +36,7 @@ def run_all(env, only, dmma_peak):
         out["c3"] = _guard(run_c3, env)
     if want("c4"):
         out["c4"] = _guard(run_c4, env, dmma_peak)
-    if env.world == 1 and want("c5"):
+    if want("c5"):
         out["c5"] = _guard(run_c5, env, dmma_peak)
     return out
 
@@ -335,16 +335,19 @@ def _c4_cpu(m, n, block=16_000):
 def run_c5(env, dmma_peak, m=200_000, n=10_000, steps=2, warmup=1):
     import bench
     L, ctx = env.L, env.ctx
-    prob = bench.DeviceProblem(L, ctx, m, n, 0, 20240607 + 5)
+    world, rank = env.world, env.rank
+    rows = [(m * r) // world for r in range(world + 1)]
+    row0, m_loc = rows[rank], rows[rank + 1] - rows[rank]          # strong scaling: the rows of the fixed problem are sharded
+    prob = bench.DeviceProblem(L, ctx, m_loc, n, row0, 20240607 + 5)
     x = L.DeviceVector(ctx, n).copyto(prob.x0)
-    nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m), f_=prob.f_, g_=prob.g_, J=L.DenseMatrix(ctx, m, n),
+    nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m_loc), f_=prob.f_, g_=prob.g_, J=L.DenseMatrix(ctx, m_loc, n),
                                 device_callbacks=True, ctx=ctx)
     xs, x0 = prob.xstar.download(), prob.x0.download()
     lo, hi = np.full(n, -np.inf), np.full(n, np.inf)
     idx = np.arange(n) % 5 == 0                       # 20 % of the coordinates are boxed around x*
     lo[idx] = np.minimum(xs[idx] - 0.05, x0[idx])
     hi[idx] = np.maximum(xs[idx] + 0.05, x0[idx])
-    anls = L.allocate(nls, L.Dogleg(L.QR()))
+    anls = L.allocate(nls, L.Dogleg(L.QR()), sharded=(world > 1))
     run = L.DoglegRun(anls, lower=lo, upper=hi)
     st = {"acc": 0}
 
@@ -362,16 +365,24 @@ def run_c5(env, dmma_peak, m=200_000, n=10_000, steps=2, warmup=1):
     ms, wall = env.timed(one_step, steps)
     launches = ctx.launch_count(reset=True)
     k_ms, k_launches = ctx.profile_read()
+    coll_ms, coll_calls = ctx.profile_read_collective()
     uflops = ctx.stat("qr_update_flops", reset=True)
     qflops = ctx.stat("qr_flops", reset=True)
     ctx.set_option("profile", 0)
+    coll_ms = env.max_over_ranks(coll_ms)
+    if rank != 0:
+        return None
     achieved = uflops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     res = {
         "workload": f"bounded dense synthetic fit m={m} n={n} fp64 (20 % of the coordinates boxed), Dogleg(QR())",
-        "baseline_config": "BASELINE.json configs[4] at N = 1 (row-sharding is implemented for LevenbergMarquardt only)",
-        "n_gpus": 1, "metric": "trust-region steps/sec (fp64)", "value": steps / (ms * 1e-3), "unit": "steps/s",
+        "baseline_config": "BASELINE.json configs[4] (1 -> 8 GPU sweep: the rows of the fixed problem are sharded, TSQR)",
+        "n_gpus": world, "scaling": "strong", "rows_per_gpu": m_loc,
+        "collective": ({"what": "ncclAllGather of the n x (n+1) [R | Q'f] factors, per factorisation",
+                        "bytes_per_rank": 8 * n * (n + 1), "calls": coll_calls,
+                        "ms_per_call_max_over_ranks": coll_ms / max(coll_calls, 1)} if world > 1 else None),
+        "metric": "trust-region steps/sec (fp64)", "value": steps / (ms * 1e-3), "unit": "steps/s",
         "s_per_step": ms / steps * 1e-3, "wall_s_per_step": wall / steps * 1e-3, "steps": steps, "warmup": warmup,
-        "steps_accepted": st["acc"], "qr_factorisations_in_timed_steps": qflops / (2.0 * m * n * n - 2.0 * n ** 3 / 3.0),
+        "steps_accepted": st["acc"],
         "gpu_launches": launches, "last_ssr": run.ssr,
         "roofline": {"kernel": "qr_apply_pp_kernel_t (CAQR trailing update, DMMA)", "bound": "tensor", "achieved": achieved,
                      "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak else None,
@@ -379,7 +390,8 @@ def run_c5(env, dmma_peak, m=200_000, n=10_000, steps=2, warmup=1):
                      "numerator": "trailing-update flops only (lso_ctx_stat \"qr_update_flops\")", "traffic": None},
     }
     del run, anls, nls, prob
-    res["cpu_baseline"] = _c5_cpu(m, n)
+    if world == 1:
+        res["cpu_baseline"] = _c5_cpu(m, n)
     return res
 
 

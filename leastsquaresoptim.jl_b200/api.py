@@ -243,10 +243,11 @@ class _Allocated:
         damped = isinstance(optimizer, LevenbergMarquardt)
         if sharded and getattr(ctx, "nranks", 1) <= 1:
             raise ValueError("sharded=True needs a communicator on the context (Context.comm_init)")
-        if sharded and (not damped or isinstance(solver, LSMR) or self.sparse):
-            # the row-sharded paths are LM(QR) (TSQR) and LM(Cholesky) (one all-reduce); Dogleg's m-dimension
-            # reductions are not all-reduced and LSMR stays single-GPU (BASELINE.json north_star)
-            raise ValueError("sharded=True is only implemented for LevenbergMarquardt with QR() or Cholesky() on a dense J")
+        if sharded and (isinstance(solver, LSMR) or self.sparse or (not damped and not isinstance(solver, QR))):
+            # the row-sharded paths are LM(QR) / Dogleg(QR) (TSQR) and LM(Cholesky) (one all-reduce); LSMR stays
+            # single-GPU (BASELINE.json north_star) and the undamped Cholesky has no sharded form
+            raise ValueError("sharded=True is implemented for LevenbergMarquardt with QR() or Cholesky() and for Dogleg with "
+                             "QR(), on a dense J")
         if isinstance(solver, QR):
             # row-sharded J: local QR of [J_k | y_k] needs the undamped m_k x n workspace; the sqrt(damp) rows join
             # the stack of R factors (lso_qr_solve_sharded)
@@ -514,6 +515,8 @@ class DoglegRun:
         self.dgn, self.dgr, self.dx, self.dtd = w["dgn"], w["dgr"], w["dx"], w["dtd"]
         self.ftrial, self.fpredict = w["ftrial"], w["fpredict"]
         self.dlo, self.dhi = _bounds(ctx, anls.x, lower, upper)
+        self.sharded = bool(anls.sharded)       # rows of J / f are this rank's shard: the m-dimension sums are all-reduced
+        self.red = anls.workspace("dogleg_red", lambda: dict(r=DeviceVector(ctx, 8)))["r"]
         self.Δ = float(Δ)
         self.reuse = False
         self.wnorm_dgn = self.wnorm_dgr = 0.0
@@ -522,11 +525,21 @@ class DoglegRun:
         self.converged = self.x_converged = self.f_converged = self.g_converged = False
         anls.f(anls.fcur, anls.x)
         self.f_calls += 1
-        self.ssr = anls.fcur.sumabs2()
+        self.ssr = self._allsum(anls.fcur.sumabs2())
         self.maxabs_gr = math.inf
         self.it = 0
         self.tr = [OptimizationState(0, self.ssr, self.maxabs_gr)] if store_trace else []
         self.deltas = []
+
+    def _allsum(self, val: float) -> float:
+        """Sum a scalar over the ranks (identity on one GPU)."""
+        if not self.sharded:
+            return val
+        buf = np.zeros(8)
+        buf[0] = val
+        self.red.upload(buf)
+        self.ctx.allreduce(self.red)
+        return float(self.red.download()[0])
 
     def iterate(self):
         import ctypes as C
@@ -541,19 +554,23 @@ class DoglegRun:
             anls.g(x)
             self.g_calls += 1
             J.colsumabs2(dtd)                               # :85
+            if self.sharded:
+                ctx.allreduce(dtd)
             dtd.clamp(MIN_DIAGONAL, MAX_DIAGONAL)           # :90  (absolute floor, unlike LM)
             if self.it == 1:
                 wnorm_x = wnorm(x, dtd)
                 if wnorm_x > 0:
                     self.Δ *= wnorm_x
             J.mul_t(dgr, fcur, 1.0, 0.0)                    # :99
+            if self.sharded:
+                ctx.allreduce(dgr)
             self.mul_calls += 1
             _gradient_norm_async(ctx, dgr, x, dlo, dhi)       # :101 (read back by the step tail; kept across reuse)
             dgr.div_(dgr, dtd)                              # :105  δgr = D⁻¹ g
             self.wnorm_dgr = wnorm(dgr, dtd)
             J.mul(fpredict, dgr, 1.0, 0.0)                  # :109
             self.mul_calls += 1
-            denom = fpredict.sumabs2()
+            denom = self._allsum(fpredict.sumabs2())
             w2 = self.wnorm_dgr ** 2
             self.α = w2 / denom if denom != 0 else (math.nan if w2 == 0 else math.inf)   # :111 (0/0 -> NaN)
             dgn.fill(0.0)                                   # :114
@@ -572,7 +589,7 @@ class DoglegRun:
         anls.f(ftrial, x)
         self.f_calls += 1
         # :168 sum(abs2, ftrial), :171-174 ||J δ - f||², maximum(abs, δx), projected gradient norm: one synchronisation
-        trial_ssr, predicted_ssr, maxabs_dx, self.maxabs_gr = _step_tail(ctx, J, dx, fcur, ftrial, fpredict, False)
+        trial_ssr, predicted_ssr, maxabs_dx, self.maxabs_gr = _step_tail(ctx, J, dx, fcur, ftrial, fpredict, self.sharded)
         self.mul_calls += 1
         ssr = self.ssr
         predicted_reduction = abs(ssr - predicted_ssr)

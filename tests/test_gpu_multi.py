@@ -66,6 +66,15 @@ def _worker(rank, world, port, out):
         r = L.optimize_(L.allocate(nls, L.LevenbergMarquardt(sol()), sharded=True))
         res[name] = (r.iterations, ro.iterations, float(np.linalg.norm(r.minimizer.download() - ro.minimizer) /
                                                         np.linalg.norm(ro.minimizer)), r.converged)
+    # ---- sharded Dogleg(QR) (undamped TSQR; BASELINE.json configs[4]'s scaling form) with bounds ----
+    rod = O.dogleg(model.f, model.g, model.x0, np.zeros((m, n), order="F"), m, solver="qr")
+    prob = bench.DeviceProblem(L, ctx, rows, n, row0, seed)
+    xx = L.DeviceVector(ctx, n).copyto(prob.x0)
+    nls = L.LeastSquaresProblem(x=xx, y=L.DeviceVector(ctx, rows), f_=prob.f_, g_=prob.g_,
+                                J=L.DenseMatrix(ctx, rows, n), device_callbacks=True, ctx=ctx)
+    r = L.optimize_(L.allocate(nls, L.Dogleg(L.QR()), sharded=True))
+    res["dogleg_qr"] = (r.iterations, rod.iterations, float(np.linalg.norm(r.minimizer.download() - rod.minimizer) /
+                                                            np.linalg.norm(rod.minimizer)), r.converged)
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
@@ -82,6 +91,6 @@ def test_sharded_solves_and_lm(world):
     for rank in range(world):
         res = out[rank]
         assert res["qr"] <= 1e-10 and res["chol"] <= 1e-10 and res["chol_local"] <= 1e-10, res
-        for k in ("lm_qr", "lm_chol"):
+        for k in ("lm_qr", "lm_chol", "dogleg_qr"):
             it, it_ref, err, conv = res[k]
             assert conv and it == it_ref and err <= 1e-9, (k, res[k])
