@@ -41,6 +41,16 @@ def run_all(env, only, dmma_peak):
     return out
 
 
+def _all_ok(env, ok: bool) -> bool:
+    """True only when EVERY rank reports ok (one all-reduce on the torch process group): a rank that failed to allocate
+    must not leave the others waiting inside a library collective."""
+    if env.world == 1:
+        return ok
+    t = env.torch.tensor([1 if ok else 0], device="cuda", dtype=env.torch.int32)
+    env.dist.all_reduce(t, op=env.dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
 def _guard(fn, *a):
     import gc
     try:
@@ -197,11 +207,20 @@ def run_c4(env, dmma_peak, m_loc=250_000, n=4_000, steps=3, warmup=1):
     L, ctx = env.L, env.ctx
     h = ctx.handle
     world, rank = env.world, env.rank
-    prob = bench.DeviceProblem(L, ctx, m_loc, n, rank * m_loc, 20240607 + 4)
-    x = L.DeviceVector(ctx, n).copyto(prob.x0)
-    J = L.DenseMatrix(ctx, m_loc, n)
-    nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m_loc), f_=prob.f_, g_=prob.g_, J=J, device_callbacks=True, ctx=ctx)
-    anls = L.allocate(nls, L.LevenbergMarquardt(L.Cholesky()), sharded=(world > 1))
+    err = None
+    try:
+        prob = bench.DeviceProblem(L, ctx, m_loc, n, rank * m_loc, 20240607 + 4)
+        x = L.DeviceVector(ctx, n).copyto(prob.x0)
+        J = L.DenseMatrix(ctx, m_loc, n)
+        nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m_loc), f_=prob.f_, g_=prob.g_, J=J, device_callbacks=True, ctx=ctx)
+        anls = L.allocate(nls, L.LevenbergMarquardt(L.Cholesky()), sharded=(world > 1))
+        qr = L.DenseQRAllocatedSolver(ctx, m_loc, n, damped=(world == 1), sharded=(world > 1))      # for the parity cross-check
+        if world > 1:
+            check(lib().lso_qr_prepare_sharded(qr._h), h)
+    except Exception as e:
+        err = f"{type(e).__name__}: {e}"
+    if not _all_ok(env, err is None):
+        return {"error": err or "another rank failed to allocate"} if rank == 0 else None
     st = {"run": None, "acc": 0}
 
     def one_step():
@@ -244,7 +263,6 @@ def run_c4(env, dmma_peak, m_loc=250_000, n=4_000, steps=3, warmup=1):
     anls.solver.ldiv(d_ch, J, fcur, dtd)
     parity = {}
     try:
-        qr = L.DenseQRAllocatedSolver(ctx, m_loc, n, damped=(world == 1), sharded=(world > 1))
         qr.ldiv(d_qr, J, fcur, damp2)
         a, b2 = d_ch.download(), d_qr.download()
         parity = {"vs": "row-sharded TSQR solve of the same damped system (independent algorithm, same shards)",
@@ -284,6 +302,8 @@ def _c4_roofline(fp64_tflops, dmma_peak, launches, syrk_ms, steps, ms, i8_macs):
     base = {"bound": "tensor", "launches": launches, "kernel_ms_per_step": syrk_ms / steps, "kernel_share_of_step": syrk_ms / ms,
             "fp64_equivalent_tflops": fp64_tflops, "fp64_dmma_peak_tflops": dmma_peak,
             "fp64_equivalent_over_dmma_peak": fp64_tflops / dmma_peak if dmma_peak else None, "traffic": None}
+    if i8_macs > 0:      # ncu (profiles/r2_ncu_ozaki_syrk_tcgen05.txt): dram bytes of the tile kernel + split + exponents per J'J
+        base["traffic"] = 89.9e9 + 0.2e9 + 16.0e9 + 8.0e9
     if i8_macs > 0:
         try:
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -338,16 +358,25 @@ def run_c5(env, dmma_peak, m=200_000, n=10_000, steps=2, warmup=1):
     world, rank = env.world, env.rank
     rows = [(m * r) // world for r in range(world + 1)]
     row0, m_loc = rows[rank], rows[rank + 1] - rows[rank]          # strong scaling: the rows of the fixed problem are sharded
-    prob = bench.DeviceProblem(L, ctx, m_loc, n, row0, 20240607 + 5)
-    x = L.DeviceVector(ctx, n).copyto(prob.x0)
-    nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m_loc), f_=prob.f_, g_=prob.g_, J=L.DenseMatrix(ctx, m_loc, n),
-                                device_callbacks=True, ctx=ctx)
+    from lsob200._lib import check, lib
+    err = None
+    try:
+        prob = bench.DeviceProblem(L, ctx, m_loc, n, row0, 20240607 + 5)
+        x = L.DeviceVector(ctx, n).copyto(prob.x0)
+        nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m_loc), f_=prob.f_, g_=prob.g_, J=L.DenseMatrix(ctx, m_loc, n),
+                                    device_callbacks=True, ctx=ctx)
+        anls = L.allocate(nls, L.Dogleg(L.QR()), sharded=(world > 1))
+        if world > 1:
+            check(lib().lso_qr_prepare_sharded(anls.solver._h), ctx.handle)
+    except Exception as e:
+        err = f"{type(e).__name__}: {e}"
+    if not _all_ok(env, err is None):
+        return {"error": err or "another rank failed to allocate"} if rank == 0 else None
     xs, x0 = prob.xstar.download(), prob.x0.download()
     lo, hi = np.full(n, -np.inf), np.full(n, np.inf)
     idx = np.arange(n) % 5 == 0                       # 20 % of the coordinates are boxed around x*
     lo[idx] = np.minimum(xs[idx] - 0.05, x0[idx])
     hi[idx] = np.maximum(xs[idx] + 0.05, x0[idx])
-    anls = L.allocate(nls, L.Dogleg(L.QR()), sharded=(world > 1))
     run = L.DoglegRun(anls, lower=lo, upper=hi)
     st = {"acc": 0}
 

@@ -215,6 +215,9 @@ int lso_qr_solve_redamp(lso_dense_ws* ws, const double* d_damp_new, double* d_x,
 /* TSQR over row shards for the QR path: every rank passes its shard of J and y; all ranks get x. */
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y,
                          const double* d_damp, double* d_x, int* rank_out);
+/* allocates the stack workspace / gather buffer of lso_qr_solve_sharded up front, with no collective, so that the host
+ * program can agree on an allocation failure before any rank enters NCCL */
+int lso_qr_prepare_sharded(lso_dense_ws* ws);
 /* Test hook: the sharded algorithm (local QR per shard, interleaved stack of the R factors, banded QR of the stack)
  * with the P shards emulated on one device: d_J is (P * m) x n where m is the workspace's shard row count. */
 int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,

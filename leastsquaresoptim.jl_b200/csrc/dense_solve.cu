@@ -555,6 +555,17 @@ int lso_qr_solve_redamp(lso_dense_ws* ws, const double* d_damp_new, double* d_x,
     return remember_damped_factor(ws, ps, d_damp_new);
 }
 
+// Allocate everything a row-sharded solve will need (the stack workspace and the gather buffer) WITHOUT any collective, so
+// that an allocation failure on one rank can be detected and agreed on by the host program before the first all-gather
+// (a rank that fails inside lso_qr_solve_sharded would leave the others waiting in NCCL).
+int lso_qr_prepare_sharded(lso_dense_ws* ws) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && ws->damped == 0, "create the workspace for QR with damped = 0");
+    LSO_ENTER(ctx);
+    return shard_ensure_stack(ws, ctx->nranks > 1 ? ctx->nranks : 1);
+}
+
 // Test hook: the sharded algorithm with the P shards emulated on ONE device (the rows of J are cut into P equal
 // chunks of ws->m rows that are factorised one after the other; no communicator needed).  d_J is (P * ws->m) x n.
 int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_J, int64_t ld, const double* d_y,

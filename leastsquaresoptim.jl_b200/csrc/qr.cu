@@ -1753,7 +1753,9 @@ int qr_plan_tune(lso_ctx* ctx, QRPlan* plan) {
     int64_t tree_ctas = 0;
     for (int l = 0; l < p0.L; ++l) tree_ctas += p0.nblk[l];
     // only plans whose panel tree is small enough to run beside the update are latency-bound enough to matter
-    if (tree_ctas > ctx->num_sms || plan->Npad / QB < 4) return LSO_OK;
+    // (and only moderately wide ones: above 2048 columns the twelve trial factorisations cost seconds and the per-panel
+    // latency no longer dominates)
+    if (tree_ctas > ctx->num_sms || plan->Npad / QB < 4 || plan->Npad > 2048) return LSO_OK;
     struct Cand { int apply, la, reserve; };
     const int reserve = (int)std::min<int64_t>((tree_ctas + 1) / 2, ctx->num_sms / 2);
     const Cand cand[4] = {{2, 0, 0}, {3, 0, 0}, {4, 0, 0}, {2, 1, reserve}};
