@@ -647,7 +647,12 @@ class HostStep:
         self.chunks = chunks if chunks is not None else (2 if (not self.sharded and isinstance(anls.solver, DenseQRAllocatedSolver)
                                                                 and m >= 40 * n and m >= 50000) else 1)
         if self.chunks > 1:
-            self.chunk_solver = DenseQRAllocatedSolver(ctx, -(-m // self.chunks), n, damped=False)
+            # chunk rows a little above m / chunks: the short remainder chunk is sent (and factorised) FIRST, so that its QR
+            # ends about when the next, full chunk has arrived (2 chunks: 43 % + 57 %)
+            rows = -(-m // self.chunks)
+            if self.chunks == 2 and chunks is None:
+                rows = max(rows, min(m - n, int(0.57 * m)))
+            self.chunk_solver = DenseQRAllocatedSolver(ctx, rows, n, damped=False)
 
     def run(self, hJ_ptr: int, hf_ptr: int, Δ: float, dx_host: np.ndarray):
         a, ctx, h = self.anls, self.ctx, self.ctx.handle

@@ -461,14 +461,19 @@ int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J
     // the copies may not overtake earlier readers of d_J / d_y on the compute stream
     LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
     LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
-    for (int k = 0; k < P; ++k) {
+    // The SHORT remainder chunk goes first: the factorisation can start as soon as it has landed, and choosing the chunk
+    // size a little above m_total / P (HostStep: 57 % for P = 2) makes its QR end when the next chunk arrives.  TSQR does not
+    // care about the order of the triangles.
+    for (int q = 0; q < P; ++q) {
+        const int k = P - 1 - q;
         const int64_t r0 = (int64_t)k * mc, rows = std::min<int64_t>(mc, m_total - r0);
         LSO_CHECK_CUDA(ctx, cudaMemcpy2DAsync(d_J + r0, ld_d * sizeof(double), h_J + r0, ld_h * sizeof(double), rows * sizeof(double),
                                               n, cudaMemcpyHostToDevice, ctx->copy_stream));
         LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_y + r0, h_y + r0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
         LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1 + k], ctx->copy_stream));
     }
-    for (int k = 0; k < P; ++k) {
+    for (int q = 0; q < P; ++q) {
+        const int k = P - 1 - q;
         const int64_t r0 = (int64_t)k * mc, rows = std::min<int64_t>(mc, m_total - r0);
         LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1 + k], 0));
         LSO_TRY(shard_local_R(ws, d_J + r0, ld_d, d_y + r0, ws->d_gather + (size_t)k * n * (n + 1), rows));
