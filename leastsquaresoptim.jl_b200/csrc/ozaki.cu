@@ -117,7 +117,10 @@ oz_colexp_kernel(long long m, long long n, const double* __restrict__ J, long lo
     }
 }
 
-// each thread converts 16 consecutive rows of one column: one 128-byte read, one 16-byte write per digit matrix
+// each thread converts 16 consecutive rows of one column: one 128-byte read, one 16-byte write per digit matrix.
+// Digit extraction without conversion instructions: adding 1.5 * 2^52 rounds x (|x| <= 64) to the nearest integer (ties to
+// even, like rint) and leaves that integer in two's complement in the low mantissa bits, so the digit byte is the low
+// byte of the sum and the rounded value is recovered by subtracting the constant again — 4 fp64 adds / multiplies per digit.
 template <int S>
 __global__ void __launch_bounds__(256)
 oz_split_kernel(long long m, long long n, long long kpad, const double* __restrict__ J, long long ld,
@@ -127,22 +130,39 @@ oz_split_kernel(long long m, long long n, long long kpad, const double* __restri
     if (k0 >= kpad) return;
     const int e = expo[j];
     const double* col = J + j * ld;
-    union { signed char b[16]; uint4 v; } out[S];
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const bool direct = (e > -1000 && e < 1000);                       // 2^-e is a normal double
+    const double scale = (e == INT_MIN) ? 0.0 : (direct ? scalbn(1.0, -e) : 1.0);
+    uint32_t w[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p) { w[p][0] = 0u; w[p][1] = 0u; w[p][2] = 0u; w[p][3] = 0u; }
+    double xin[16];
+    if (k0 + 16 <= m && ((reinterpret_cast<uintptr_t>(col + k0) & 15) == 0)) {
+#pragma unroll
+        for (int t = 0; t < 16; t += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(col + k0 + t);
+            xin[t] = v.x; xin[t + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) xin[t] = (k0 + t < m) ? col[k0 + t] : 0.0;
+    }
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-        const long long k = k0 + t;
-        double f = (k < m && e != INT_MIN) ? scalbn(col[k], -e) : 0.0;
+        double f = (direct || e == INT_MIN) ? xin[t] * scale : scalbn(xin[t], -e);     // |f| <= 1/2
 #pragma unroll
         for (int p = 0; p < S; ++p) {
             const double x = f * 128.0;                 // exact
-            const double d = rint(x);                   // in [-64, 64]
-            out[p].b[t] = (signed char)(int)d;
+            const double r = x + MAGIC;                 // rounds to the nearest integer in [-64, 64]
+            const double d = r - MAGIC;                 // that integer as a double (exact)
+            w[p][t >> 2] |= ((uint32_t)__double2loint(r) & 0xffu) << (8 * (t & 3));
             f = x - d;                                  // exact, |f| <= 1/2
         }
     }
     const size_t plane = (size_t)kpad * (size_t)n;
 #pragma unroll
-    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(slices + (size_t)p * plane + (size_t)j * kpad + k0) = out[p].v;
+    for (int p = 0; p < S; ++p)
+        *reinterpret_cast<uint4*>(slices + (size_t)p * plane + (size_t)j * kpad + k0) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
 }
 
 // =====================================================================================================================

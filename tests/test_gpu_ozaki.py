@@ -102,3 +102,35 @@ def test_ozaki_nonfinite_input_is_not_silent(ctx):
             ws.ldiv(x, L.DenseMatrix(ctx, 500, 20, Jh), L.DeviceVector(ctx, 500, yh))
     finally:
         ctx.set_option("syrk", 1)
+
+
+def test_ozaki_extreme_column_scales(ctx):
+    """Columns 280 decades apart (their Gram entries still fit the double range) and a J whose odd leading dimension makes
+    every second column 8-byte- but not 16-byte-aligned (the split's scalar-load path)."""
+    import lsob200 as L
+    m, n = 3001, 40
+    rng = np.random.default_rng(9)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)))
+    Jh[:, 3] *= 1e-140
+    Jh[:, 7] *= 1e140
+    Jh[:, 11] *= 1e-100
+    yh = rng.standard_normal(m)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    damp = dtd / 10.0
+    xr = O.chol_ldiv(Jh * 1.0, yh, damp.copy()) if np.all(np.isfinite(dtd)) else None
+    ctx.set_option("syrk", 2)
+    try:
+        ws = L.DenseCholeskyAllocatedSolver(ctx, m, n, damped=True)
+        x = L.DeviceVector(ctx, n)
+        ws.ldiv(x, L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh), L.DeviceVector(ctx, n, damp))
+        xg = x.download()
+    finally:
+        ctx.set_option("syrk", 1)
+    # compare with the DMMA path on the same inputs (the oracle's LAPACK also just multiplies these columns out)
+    ws1 = L.DenseCholeskyAllocatedSolver(ctx, m, n, damped=True)
+    x1 = L.DeviceVector(ctx, n)
+    ws1.ldiv(x1, L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh), L.DeviceVector(ctx, n, damp))
+    scale = np.sqrt(dtd)                       # compare δ in the scaled variables (δ_j ‖J_j‖), where every column counts
+    assert rel(xg * scale, x1.download() * scale) <= 1e-10
+    if xr is not None:
+        assert rel(xg * scale, xr * scale) <= 1e-10
