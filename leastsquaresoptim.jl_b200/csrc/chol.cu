@@ -42,7 +42,9 @@ __device__ __forceinline__ void decode_pair(int p, int& bi, int& bj) {
     bi = p - j * (j + 1) / 2;
 }
 
-template <bool ALIGN16>
+// SUB = false: out = J'J (per split-K slab).  SUB = true: out -= J'J on the upper triangle only — the rank-w update of the
+// blocked Cholesky (J = the w x rest row block of the factor just computed, out = the trailing matrix).
+template <bool ALIGN16, bool SUB = false>
 __global__ void __launch_bounds__(256, 1)
 syrk_mma_kernel(long long m, long long n, const double* __restrict__ J, long long ld, long long rows_per_split,
                 double* __restrict__ out, long long ldc, long long slab_stride) {
@@ -130,8 +132,13 @@ syrk_mma_kernel(long long m, long long n, const double* __restrict__ J, long lon
         for (int ni = 0; ni < 4; ++ni) {
             const long long j = (long long)bj * SY_TS + 32 * wj + 8 * ni + 2 * t;
             if (i < n) {
-                if (j < n) o[j * ldc + i] = acc[mi][ni][0];
-                if (j + 1 < n) o[(j + 1) * ldc + i] = acc[mi][ni][1];
+                if (SUB) {
+                    if (j < n && i <= j) o[j * ldc + i] -= acc[mi][ni][0];
+                    if (j + 1 < n && i <= j + 1) o[(j + 1) * ldc + i] -= acc[mi][ni][1];
+                } else {
+                    if (j < n) o[j * ldc + i] = acc[mi][ni][0];
+                    if (j + 1 < n) o[(j + 1) * ldc + i] = acc[mi][ni][1];
+                }
             }
         }
     }
@@ -370,6 +377,7 @@ int chol_plan_create(lso_ctx* ctx, int64_t n, CholPlan* p) {
     if (!attr_done) {
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(syrk_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
         LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute(syrk_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+        LSO_CHECK_CUDA(ctx, cudaFuncSetAttribute((syrk_mma_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
         attr_done = true;
     }
     return LSO_OK;
@@ -424,19 +432,80 @@ int syrk_upper(lso_ctx* ctx, CholPlan* p, int64_t m, int64_t n, const double* d_
     return LSO_OK;
 }
 
+// rank-w update of the row strip [t0, i_end) x [t0, n) of the trailing matrix only (upper triangle), t0 = k0 + w: inside a
+// 128-column super-block only the rows that the NEXT sub-panels factor need the update right away
+__global__ void __launch_bounds__(256)
+potrf_strip_update_kernel(int n, double* __restrict__ C, long long ldc, int k0, int w, int i_end) {
+    __shared__ double Ri[32][65], Rj[32][65];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int t0 = k0 + w;
+    const int i0 = t0 + blockIdx.y * 64, j0 = t0 + blockIdx.x * 64;
+    if (j0 + 63 < i0) return;                      // tile entirely below the diagonal
+    for (int e = tid; e < 32 * 64; e += 256) {
+        const int k = e & 31, c = e >> 5;
+        Ri[k][c] = (k < w && i0 + c < i_end) ? C[(long long)(i0 + c) * ldc + k0 + k] : 0.0;
+        Rj[k][c] = (k < w && j0 + c < n) ? C[(long long)(j0 + c) * ldc + k0 + k] : 0.0;
+    }
+    __syncthreads();
+    double acc[4][4] = {};
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = Ri[k][4 * ty + u]; b[u] = Rj[k][4 * tx + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + 4 * ty + u, j = j0 + 4 * tx + v;
+            if (i < i_end && j < n && i <= j) C[(long long)j * ldc + i] -= acc[u][v];
+        }
+}
+
 int potrf_upper(lso_ctx* ctx, CholPlan* p, int* info_out) {
     const int n = (int)p->n;
     set_int_kernel<<<1, 1, 0, ctx->stream>>>(p->d_info, INT_MAX);
     LSO_CHECK_LAUNCH(ctx);
-    for (int k0 = 0; k0 < n; k0 += 32) {
-        const int w = (n - k0 < 32) ? (n - k0) : 32;
-        const int rest = n - k0 - w;
-        int g = rest > 0 ? (rest + PP_THREADS - 1) / PP_THREADS : 1;
-        potrf_panel_kernel<<<g, PP_THREADS, 0, ctx->stream>>>(n, p->C, p->ldc, k0, p->d_info);
-        LSO_CHECK_LAUNCH(ctx);
-        if (rest > 0) {
-            int nt = (rest + 63) / 64;
-            potrf_update_kernel<<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(n, p->C, p->ldc, k0, w);
+    // Two-level blocking: 128-column super-blocks of four 32-column panels.  Inside a super-block a panel's rank-32 update
+    // only goes to the row strip the next panels of the block factor; the rest of the trailing matrix gets ONE rank-128
+    // update per super-block on the fp64 tensor pipe (the DMMA syrk kernel in subtract mode: its operand is the
+    // 128 x rest row block just computed, K-major like the rows of J) — a quarter of the trailing-matrix traffic.
+    const int SB = 128;
+    for (int b0 = 0; b0 < n; b0 += SB) {
+        const int bend = (b0 + SB < n) ? b0 + SB : n;
+        const bool big = ctx->opt_syrk && (bend - b0 == SB) && (n - bend >= 256);
+        for (int k0 = b0; k0 < bend; k0 += 32) {
+            const int w = (n - k0 < 32) ? (n - k0) : 32;
+            const int rest = n - k0 - w;
+            int g = rest > 0 ? (rest + PP_THREADS - 1) / PP_THREADS : 1;
+            potrf_panel_kernel<<<g, PP_THREADS, 0, ctx->stream>>>(n, p->C, p->ldc, k0, p->d_info);
+            LSO_CHECK_LAUNCH(ctx);
+            if (rest <= 0) continue;
+            if (big) {
+                const int t0 = k0 + w;
+                if (t0 < bend) {
+                    dim3 grid((unsigned)((n - t0 + 63) / 64), (unsigned)((bend - t0 + 63) / 64));
+                    potrf_strip_update_kernel<<<grid, 256, 0, ctx->stream>>>(n, p->C, p->ldc, k0, w, bend);
+                    LSO_CHECK_LAUNCH(ctx);
+                }
+            } else {
+                int nt = (rest + 63) / 64;
+                potrf_update_kernel<<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(n, p->C, p->ldc, k0, w);
+                LSO_CHECK_LAUNCH(ctx);
+            }
+        }
+        if (big) {
+            const int rest = n - bend;
+            const long long ntb = (rest + SY_TS - 1) / SY_TS;
+            dim3 grid((unsigned)(ntb * (ntb + 1) / 2), 1);
+            const double* P = p->C + (long long)bend * p->ldc + b0;          // SB x rest, ld = ldc
+            double* T = p->C + (long long)bend * p->ldc + bend;
+            syrk_mma_kernel<true, true><<<grid, 256, SY_SMEM_BYTES, ctx->stream>>>(SB, rest, P, p->ldc, SB, T, p->ldc, 0);
             LSO_CHECK_LAUNCH(ctx);
         }
     }
