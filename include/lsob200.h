@@ -314,6 +314,9 @@ int lso_synth_jacobian(lso_ctx* ctx, int64_t m, int64_t n, const double* d_A, in
                        double c, double* d_J, int64_t ldJ);
 int lso_synth_csc_pattern(int64_t m, int64_t n, int64_t nnz_per_col, uint64_t seed,
                           int64_t* h_colptr_1based, int64_t* h_rowval_1based); /* host, deterministic */
+/* the same with the rows of column j confined to a window of `window` rows around j*m/n (a Jacobian with locality) */
+int lso_synth_csc_pattern_banded(int64_t m, int64_t n, int64_t nnz_per_col, int64_t window, uint64_t seed,
+                                 int64_t* h_colptr_1based, int64_t* h_rowval_1based);
 int lso_synth_csc_jacobian(lso_csc* A, const double* d_Aval, const double* d_t, double c); /* nzval = (1+2c t[row]) * Aval */
 /* the same device g! writing both the CSC and the CSR image (d_Aval_csr = lso_csc_gather_csr of d_Aval) */
 int lso_synth_csc_jacobian_both(lso_csc* A, const double* d_Aval, const double* d_Aval_csr, const double* d_t, double c);

@@ -221,6 +221,26 @@ int lso_synth_csc_pattern(int64_t m, int64_t n, int64_t nnz_per_col, uint64_t se
     h_colptr[n] = n * nnz_per_col + 1;
     return LSO_OK;
 }
+// The same construction inside a BAND: the rows of column j are stratified over a window of `window` rows centred on
+// j * m / n (clipped to [0, m)).  A Jacobian with this kind of locality (PDE stencils, bundle adjustment, time series) is
+// what lets the gathers of the sparse products hit L1 / whole L2 sectors; the uniform pattern above has none by design.
+int lso_synth_csc_pattern_banded(int64_t m, int64_t n, int64_t nnz_per_col, int64_t window, uint64_t seed, int64_t* h_colptr,
+                                 int64_t* h_rowval) {
+    if (!h_colptr || !h_rowval || nnz_per_col < 1 || window < nnz_per_col || window > m)
+        return lso_set_error(nullptr, LSO_ERR_ARG, "bad arguments");
+    for (int64_t j = 0; j < n; ++j) {
+        h_colptr[j] = j * nnz_per_col + 1;
+        int64_t w0 = (int64_t)(((__int128)j * m) / n) - window / 2;
+        if (w0 < 0) w0 = 0;
+        if (w0 + window > m) w0 = m - window;
+        for (int64_t k = 0; k < nnz_per_col; ++k) {
+            const int64_t lo = (window * k) / nnz_per_col, hi = (window * (k + 1)) / nnz_per_col;
+            h_rowval[j * nnz_per_col + k] = w0 + lo + (int64_t)(lso_hash(seed + 2, (uint64_t)j, (uint64_t)k) % (uint64_t)(hi - lo)) + 1;
+        }
+    }
+    h_colptr[n] = n * nnz_per_col + 1;
+    return LSO_OK;
+}
 int lso_synth_csc_jacobian(lso_csc* A, const double* d_Aval, const double* d_t, double c) {
     if (!A) return lso_set_error(nullptr, LSO_ERR_ARG, "A is NULL");
     lso_ctx* ctx = A->ctx;
