@@ -59,6 +59,8 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *   "qr_tune"      1 (default) = QR workspaces whose panel tree fits on a third of the SMs (row shards, the stacked R
  *                  factors) time four launch schedules once at creation and keep the fastest; setting "qr_apply" or
  *                  "qr_lookahead" explicitly turns this off
+ *   "qr_twin"      extra workspaces / streams (0..3, default 2) among which lso_qr_factor_keep_host[_chunks] rotates its
+ *                  chunks when there are three or more (the panel trees of one chunk run under the updates of another)
  *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk, 3 (default) tcgen05 syrk for m >= 8192 and n >= 512 and DMMA otherwise,
  *                  2 tcgen05 syrk always: int8 digit matrices (Ozaki scheme) multiplied by
  *                  tcgen05.mma.kind::i8 into TMEM, operands fed by TMA, fp64 reconstructed exactly
@@ -204,6 +206,10 @@ int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* 
  * Follow with lso_qr_solve_kept (the damping is only needed there, so colsumabs2!(dtd, J) can wait for the whole J). */
 int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J, int64_t ld_h, const double* h_y,
                             double* d_J, int64_t ld_d, double* d_y);
+/* the same with an explicit list of chunk sizes (each <= the workspace's m, sum = rows of J), sent in that order; with
+ * three or more chunks they are factorised round-robin in up to "qr_twin" + 1 workspaces on as many streams */
+int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk_rows, const double* h_J, int64_t ld_h,
+                                   const double* h_y, double* d_J, int64_t ld_d, double* d_y);
 int lso_qr_kept_invalidate(lso_dense_ws* ws);
 /* Cheaper still, and from the FIRST rejection on: the last damped solve on the workspace left R with R'R = J'J + D_last.
  * A rejected LM step re-solves with the same J, f and a LARGER damping (Delta shrinks, levenberg_marquardt.jl:77-87,135),

@@ -626,6 +626,9 @@ def _optimize_dogleg(anls: _Allocated, **kw):
     return run.result()
 
 
+AUTO_CHUNK_SHARES = (0.30, 0.30, 0.25, 0.15)
+
+
 class HostStep:
     """Hot-path body of one LevenbergMarquardt iteration driven from HOST buffers (the e2e path of bench.py and
     what the Julia glue does when `J` / `f` are plain host Arrays): H2D of J and f, colsumabs2! + damping (LM:82-86),
@@ -642,17 +645,24 @@ class HostStep:
         self.dx, self.dtd, self.fpredict, self.red = w["dx"], w["dtd"], w["fpredict"], w["red"]
         self.grad = anls.workspace("lm_grad", lambda: dict(g=DeviceVector(ctx, n)))["g"]
         self.sharded = bool(anls.sharded)
-        # row chunks of the host-fed factorisation: 2 when each half still has many more rows than the per-panel latency
-        # floor is worth (measured at 100 000 x 1 000: 27.6 ms against 29.9 ms unchunked), else the plain path
-        self.chunks = chunks if chunks is not None else (2 if (not self.sharded and isinstance(anls.solver, DenseQRAllocatedSolver)
-                                                                and m >= 40 * n and m >= 50000) else 1)
+        # Row chunks of the host-fed factorisation.  `chunks`: None = automatic, an int = that many (near-)equal chunks, a
+        # list of fractions = those shares of the rows, in transfer order.  Automatic: four chunks with shrinking sizes when
+        # J is tall enough that a chunk still has many more rows than the per-panel latency floor is worth — chunks are
+        # factorised round-robin in two workspaces, so a small LAST chunk leaves little work after the last byte has landed
+        # (measured at 100 000 x 1 000: see tools/probe_e2e_chunks.py) — else the plain upload + solve.
+        auto = chunks is None
+        if auto:
+            ok = not self.sharded and isinstance(anls.solver, DenseQRAllocatedSolver) and m >= 40 * n and m >= 50000
+            chunks = list(AUTO_CHUNK_SHARES) if ok else 1
+        if isinstance(chunks, int):
+            self.chunk_rows = [m] if chunks <= 1 else [(m * (k + 1)) // chunks - (m * k) // chunks for k in range(chunks)]
+        else:
+            edges = np.rint(np.cumsum([0.0] + [float(c) for c in chunks]) / float(sum(chunks)) * m).astype(np.int64)
+            edges[-1] = m
+            self.chunk_rows = [int(b - a) for a, b in zip(edges[:-1], edges[1:])]
+        self.chunks = len(self.chunk_rows)
         if self.chunks > 1:
-            # chunk rows a little above m / chunks: the short remainder chunk is sent (and factorised) FIRST, so that its QR
-            # ends about when the next, full chunk has arrived (2 chunks: 43 % + 57 %)
-            rows = -(-m // self.chunks)
-            if self.chunks == 2 and chunks is None:
-                rows = max(rows, min(m - n, int(0.57 * m)))
-            self.chunk_solver = DenseQRAllocatedSolver(ctx, rows, n, damped=False)
+            self.chunk_solver = DenseQRAllocatedSolver(ctx, max(max(self.chunk_rows), n), n, damped=False)
 
     def run(self, hJ_ptr: int, hf_ptr: int, Δ: float, dx_host: np.ndarray):
         a, ctx, h = self.anls, self.ctx, self.ctx.handle
@@ -660,7 +670,7 @@ class HostStep:
         if self.chunks > 1:
             # J and f cross PCIe in row chunks, each chunk is factorised (undamped) while the next one is in flight; the
             # damping joins in the stacked finish, so colsumabs2! can wait for the whole J (levenberg_marquardt.jl:82-87)
-            self.chunk_solver.factor_keep_host(a.m, hJ_ptr, a.m, hf_ptr, J, fcur)
+            self.chunk_solver.factor_keep_host_chunks(self.chunk_rows, hJ_ptr, a.m, hf_ptr, J, fcur)
             J.colsumabs2_and_grad(dtd, self.grad, fcur)
             _lm_damping(ctx, dtd, 1 / Δ)
             self.chunk_solver.solve_kept(dx, dtd)

@@ -29,6 +29,12 @@ struct lso_dense_ws {
     // (f3) re-damping: the triangular factor [R | c] of the last DAMPED solve (in last_plan->A) and its damping vector;
     // a re-solve with a larger damping on the same J, y is the QR of the 2n x n stack [R; sqrt(damp_new - damp_last)]
     QRPlan* last_plan = nullptr;
+    // host-fed chunked factorisation with >= 3 chunks: a second workspace and stream, so that the (latency-bound) panel
+    // trees of one chunk run under the trailing updates of the other
+    QRPlan plan_twin[3];
+    int n_twin = 0;
+    cudaStream_t twin_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t twin_done[3] = {nullptr, nullptr, nullptr};
     QRPlan plan_redamp;
     bool have_redamp = false;
     double* d_lastdamp = nullptr;
@@ -176,6 +182,11 @@ int lso_dense_ws_destroy(lso_dense_ws* ws) {
     qr_plan_destroy(&ws->plan);
     if (ws->have_stack) qr_plan_destroy(&ws->plan_stack);
     if (ws->have_redamp) qr_plan_destroy(&ws->plan_redamp);
+    for (int t = 0; t < ws->n_twin; ++t) {
+        qr_plan_destroy(&ws->plan_twin[t]);
+        if (ws->twin_stream[t]) cudaStreamDestroy(ws->twin_stream[t]);
+        if (ws->twin_done[t]) cudaEventDestroy(ws->twin_done[t]);
+    }
     cudaFree(ws->d_lastdamp);
     cudaFree(ws->d_redamp_slot);
     chol_plan_destroy(&ws->chol);
@@ -341,18 +352,20 @@ __global__ void stack_assemble_kernel(long long n, int P, int Q, const double* _
 }
 
 // local QR of [J_k | y_k] and its n x (n+1) [R | Q'y] packed into `slot`
-static int shard_local_R(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, double* slot, int64_t rows = -1) {
+static int shard_local_R(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, double* slot, int64_t rows = -1,
+                         QRPlan* plan = nullptr) {
     lso_ctx* ctx = ws->ctx;
     const int64_t n = ws->n;
     if (rows < 0) rows = ws->m;
-    LSO_TRY(qr_assemble(ctx, &ws->plan, rows, n, d_J, ld, d_y, nullptr));
-    const int64_t M_full = ws->plan.M;
-    ws->plan.M = std::max<int64_t>(rows, n);   // a damped workspace has m + n rows: only the rows of J are in use here
-    const int st = qr_factor(ctx, &ws->plan);
-    ws->plan.M = M_full;
+    if (!plan) plan = &ws->plan;
+    LSO_TRY(qr_assemble(ctx, plan, rows, n, d_J, ld, d_y, nullptr));
+    const int64_t M_full = plan->M;
+    plan->M = std::max<int64_t>(rows, n);      // a damped workspace has m + n rows: only the rows of J are in use here
+    const int st = qr_factor(ctx, plan);
+    plan->M = M_full;
     LSO_TRY(st);
     dim3 grid((unsigned)std::min<int64_t>(cdiv64(n, 256), 64), (unsigned)(n + 1));
-    pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, ws->plan.A, ws->plan.ld, ws->plan.Npad, slot);
+    pack_R_kernel<<<grid, 256, 0, ctx->stream>>>(n, plan->A, plan->ld, plan->Npad, slot);
     LSO_CHECK_LAUNCH(ctx);
     return LSO_OK;
 }
@@ -440,16 +453,20 @@ int lso_qr_factor_keep(lso_dense_ws* ws, const double* d_J, int64_t ld, const do
 // device on a copy stream while chunk k-1 is being factorised (TSQR over the chunks), so the H2D transfer of J — 14.5 ms
 // of a 30 ms end-to-end LM step at 100 000 x 1 000 — runs under the factorisation instead of in front of it.  J and y
 // also land in d_J (ld_d) / d_y for the passes of the iteration that need them whole.  Follow with lso_qr_solve_kept.
-int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J, int64_t ld_h, const double* h_y,
-                            double* d_J, int64_t ld_d, double* d_y) {
+int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk_rows, const double* h_J, int64_t ld_h,
+                                   const double* h_y, double* d_J, int64_t ld_d, double* d_y) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     lso_ctx* ctx = ws->ctx;
-    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && h_J && h_y && d_J && d_y, "bad arguments");
-    const int64_t mc = ws->m, n = ws->n;
-    const int P = (int)cdiv64(m_total, mc);
+    LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && h_J && h_y && d_J && d_y && chunk_rows, "bad arguments");
     LSO_REQUIRE(ctx, P >= 1 && P <= 16, "between 1 and 16 row chunks");
+    const int64_t n = ws->n;
+    int64_t m_total = 0;
+    for (int k = 0; k < P; ++k) {
+        LSO_REQUIRE(ctx, chunk_rows[k] >= 1 && chunk_rows[k] <= ws->m, "a chunk has no rows or more rows than the workspace");
+        m_total += chunk_rows[k];
+    }
     LSO_REQUIRE(ctx, ld_h >= m_total && ld_d >= m_total, "leading dimension < rows");
-    LSO_REQUIRE(ctx, mc >= n && m_total - (int64_t)(P - 1) * mc >= 1, "every chunk needs rows >= columns (the last one at least 1 row)");
+    LSO_REQUIRE(ctx, ws->m >= n, "the workspace needs rows >= columns");
     LSO_ENTER(ctx);
     ws->kept = false;
     ws->last_plan = nullptr;
@@ -461,25 +478,63 @@ int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J
     // the copies may not overtake earlier readers of d_J / d_y on the compute stream
     LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
     LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
-    // The SHORT remainder chunk goes first: the factorisation can start as soon as it has landed, and choosing the chunk
-    // size a little above m_total / P (HostStep: 57 % for P = 2) makes its QR end when the next chunk arrives.  TSQR does not
-    // care about the order of the triangles.
-    for (int q = 0; q < P; ++q) {
-        const int k = P - 1 - q;
-        const int64_t r0 = (int64_t)k * mc, rows = std::min<int64_t>(mc, m_total - r0);
+    int64_t r0 = 0;
+    for (int k = 0; k < P; ++k) {            // chunks cross PCIe in the order given
+        const int64_t rows = chunk_rows[k];
         LSO_CHECK_CUDA(ctx, cudaMemcpy2DAsync(d_J + r0, ld_d * sizeof(double), h_J + r0, ld_h * sizeof(double), rows * sizeof(double),
                                               n, cudaMemcpyHostToDevice, ctx->copy_stream));
         LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_y + r0, h_y + r0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
         LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1 + k], ctx->copy_stream));
+        r0 += rows;
     }
-    for (int q = 0; q < P; ++q) {
-        const int k = P - 1 - q;
-        const int64_t r0 = (int64_t)k * mc, rows = std::min<int64_t>(mc, m_total - r0);
-        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1 + k], 0));
-        LSO_TRY(shard_local_R(ws, d_J + r0, ld_d, d_y + r0, ws->d_gather + (size_t)k * n * (n + 1), rows));
+    // With three or more chunks they are factorised round-robin in up to `qr_twin` + 1 workspaces on as many streams: a
+    // chunk's QR is mostly latency (32 panel trees) and the next chunk is usually there before it ends, so the panel trees
+    // of one chunk run under the trailing updates of another.  TSQR does not care about the order of the triangles.
+    int K = (P >= 3) ? 1 + (int)std::min<int64_t>(std::max<int64_t>(ctx->opt_qr_twin, 0), 3) : 1;
+    if (K > P) K = P;
+    while (ws->n_twin < K - 1) {
+        const int t = ws->n_twin;
+        LSO_TRY(qr_plan_create(ctx, ws->plan.M, n, &ws->plan_twin[t]));
+        LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ws->twin_stream[t], cudaStreamNonBlocking));
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ws->twin_done[t], cudaEventDisableTiming));
+        ws->n_twin = t + 1;
+    }
+    for (int t = 0; t < K - 1; ++t) LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ws->twin_stream[t], ctx->copy_ev[0], 0));
+    cudaStream_t main_stream = ctx->stream;
+    int st = LSO_OK;
+    r0 = 0;
+    for (int k = 0; k < P && st == LSO_OK; ++k) {
+        const int64_t rows = chunk_rows[k];
+        const int w = k % K;                  // 0 = the workspace's own plan on the context stream
+        ctx->stream = (w == 0) ? main_stream : ws->twin_stream[w - 1];
+        if (cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1 + k], 0) != cudaSuccess) { st = lso_set_error(ctx, LSO_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+        st = shard_local_R(ws, d_J + r0, ld_d, d_y + r0, ws->d_gather + (size_t)k * n * (n + 1), rows, (w == 0) ? &ws->plan : &ws->plan_twin[w - 1]);
+        r0 += rows;
+    }
+    ctx->stream = main_stream;
+    LSO_TRY(st);
+    for (int t = 0; t < K - 1; ++t) {
+        LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->twin_done[t], ws->twin_stream[t]));
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ws->twin_done[t], 0));
     }
     ws->kept = true;
     return LSO_OK;
+}
+
+// uniform chunks of the workspace's m rows, the short remainder chunk first
+int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J, int64_t ld_h, const double* h_y,
+                            double* d_J, int64_t ld_d, double* d_y) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    const int64_t mc = ws->m;
+    LSO_REQUIRE(ctx, mc >= 1 && m_total >= 1, "bad dimensions");
+    const int P = (int)cdiv64(m_total, mc);
+    LSO_REQUIRE(ctx, P >= 1 && P <= 16, "between 1 and 16 row chunks");
+    int64_t rows[16];
+    const int64_t rem = m_total - (int64_t)(P - 1) * mc;
+    rows[0] = rem;
+    for (int k = 1; k < P; ++k) rows[k] = mc;
+    return lso_qr_factor_keep_host_chunks(ws, P, rows, h_J, ld_h, h_y, d_J, ld_d, d_y);
 }
 
 int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* rank_out) {

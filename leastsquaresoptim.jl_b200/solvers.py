@@ -107,6 +107,13 @@ class DenseQRAllocatedSolver(_DenseWorkspace):
         check(lib().lso_qr_factor_keep_host(self._h, m_total, hJ_ptr, ld_h, hy_ptr, J.ptr, J.ld, y.ptr), self.ctx.handle)
         self._kept, self._have_damped = True, False
 
+    def factor_keep_host_chunks(self, chunk_rows, hJ_ptr: int, ld_h: int, hy_ptr: int, J: DenseMatrix, y: DeviceVector):
+        """The same with an explicit list of chunk sizes, sent in that order (lso_qr_factor_keep_host_chunks)."""
+        rows = (C.c_int64 * len(chunk_rows))(*[int(r) for r in chunk_rows])
+        check(lib().lso_qr_factor_keep_host_chunks(self._h, len(chunk_rows), C.addressof(rows), hJ_ptr, ld_h, hy_ptr, J.ptr, J.ld,
+                                                   y.ptr), self.ctx.handle)
+        self._kept, self._have_damped = True, False
+
     def solve_kept(self, x: DeviceVector, damp: DeviceVector | None):
         rank = C.c_int()
         check(lib().lso_qr_solve_kept(self._h, damp.ptr if damp is not None else None, x.ptr, C.byref(rank)), self.ctx.handle)

@@ -567,7 +567,7 @@ def test_qr_redamp_after_rejected_steps(ctx, m, n):
     assert rel(x.download(), xr) <= 1e-10
 
 
-@pytest.mark.parametrize("chunks", [2, 3])
+@pytest.mark.parametrize("chunks", [2, 3, [0.3, 0.3, 0.25, 0.15], 7])
 def test_host_step_chunked_upload_matches_the_direct_solve(ctx, chunks):
     """The end-to-end path from HOST memory (HostStep / lso_qr_factor_keep_host): J and f cross PCIe in row chunks that are
     factorised as they land (TSQR) and the damping joins in the stacked finish — same δ and step scalars as uploading
@@ -587,10 +587,11 @@ def test_host_step_chunked_upload_matches_the_direct_solve(ctx, chunks):
         dx = np.zeros(n)
         for _ in range(2):                       # twice: the second call re-uses every workspace
             sc = hs.run(Jh.ctypes.data, fh.ctypes.data, 10.0, dx)
-        out[c] = (dx.copy(), sc)
+        out[c if isinstance(c, int) else tuple(c)] = (dx.copy(), sc)
     dtd = np.einsum("ij,ij->j", Jh, Jh)
     damp = np.clip(dtd, 1e-6 * dtd.mean(), 1e32 * dtd.mean()) / 10.0
     xr, _ = O.qr_ldiv(Jh, fh, damp)
-    assert rel(out[chunks][0], xr) <= 1e-10 and rel(out[1][0], xr) <= 1e-10
+    key = chunks if isinstance(chunks, int) else tuple(chunks)
+    assert rel(out[key][0], xr) <= 1e-10 and rel(out[1][0], xr) <= 1e-10
     for k in ("ssr", "predicted_ssr", "maxabs_gr", "maxabs_dx"):
-        assert abs(out[chunks][1][k] - out[1][1][k]) <= 1e-9 * abs(out[1][1][k]), k
+        assert abs(out[key][1][k] - out[1][1][k]) <= 1e-9 * abs(out[1][1][k]), k
