@@ -11,7 +11,8 @@
 //      the truncation error of step 1 and are dropped).  Each inner sum is an int8 GEMM accumulated EXACTLY in int32
 //      (|D_p D_q| <= 2^12, at most 8 pairs per d, K chunks of <= 32768 rows: < 2^31).
 //   3. the S integer accumulators are converted to fp64, scaled by powers of two (exact) and added, smallest terms first.
-// With S = 8 the representation error 2^-57 is below fp64 rounding; the result is at least as accurate as a DMMA syrk.
+// With S = 8 the representation error is 2^-57 and the dropped pairs contribute (S-1) 2^(-7S-2) = 2^-55, both relative to
+// 2^(e_i+e_j): below fp64 rounding for columns whose entries are of comparable size, K 2^(5-7S) max|J_i| max|J_j| at worst.
 //
 // Kernel: one CTA per 128 x 128 tile of the upper triangle of J'J and per K chunk.  Warp 0 = TMA producer (3-stage ring,
 // one 32-row K step of all needed digit matrices per stage, 32-byte-swizzled K-major boxes), warp 1 = MMA issuer (one
