@@ -59,6 +59,8 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *   "qr_tune"      1 (default) = QR workspaces whose panel tree fits on a third of the SMs (row shards, the stacked R
  *                  factors) time four launch schedules once at creation and keep the fastest; setting "qr_apply" or
  *                  "qr_lookahead" explicitly turns this off
+ *   "qr_shard_pipeline" 1 (default) = lso_qr_solve_sharded runs the replicated stack QR panel by panel behind the local
+ *                  factorisation, fed by one small all-gather per panel; 0 = local QR, one all-gather, stack QR
  *   "qr_twin"      extra workspaces / streams (0..3, default 2) among which lso_qr_factor_keep_host[_chunks] rotates its
  *                  chunks when there are three or more (the panel trees of one chunk run under the updates of another)
  *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk, 3 (default) tcgen05 syrk for m >= 8192 and n >= 512 and DMMA otherwise,

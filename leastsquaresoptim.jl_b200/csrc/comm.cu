@@ -65,6 +65,12 @@ extern "C" int lso_comm_allgather(lso_ctx* ctx, const double* d_send, double* d_
     return LSO_OK;
 }
 
+extern "C" int lso_comm_allgather_on(lso_ctx* ctx, const double* d_send, double* d_recv, int64_t count, cudaStream_t st) {
+    LSO_REQUIRE(ctx, ctx && ctx->nccl_comm, "no communicator (call lso_comm_init_rank)");
+    LSO_CHECK_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, (size_t)count, LSO_NCCL_FLOAT64, ctx->nccl_comm, st));
+    return LSO_OK;
+}
+
 extern "C" {
 
 int lso_comm_unique_id(void* id128) {

@@ -41,6 +41,8 @@ struct lso_ctx {
     int64_t opt_ozaki_slices = 8;      // 7-bit digits per fp64 value in the tcgen05 syrk (2..8; 8 = below fp64 rounding)
     int64_t opt_qr_tune = 1;           // 1 = small QR plans time their launch schedules once and keep the fastest (cleared by
                                        // an explicit "qr_apply" / "qr_lookahead" setting)
+    int64_t opt_qr_shard_pipeline = 1; // row-sharded QR: 1 = the stack QR runs panel by panel behind the local one (one small
+                                       // all-gather per panel), 0 = local QR, one all-gather, stack QR
     int64_t opt_qr_twin = 2;           // host-fed chunked factorisation: extra workspaces / streams the chunks rotate through
     int64_t opt_qr_lookahead = 0;      // 1 = panel trees on a second stream under the previous update (+2% at C2)
     int64_t opt_spmv = 2;              // 0 = first-generation sparse products, 1 = stream kernels (shared-memory staging),

@@ -101,6 +101,7 @@ int lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "qr_lookahead")) { ctx->opt_qr_lookahead = value; ctx->opt_qr_tune = 0; }
     else if (!strcmp(key, "qr_tune")) ctx->opt_qr_tune = value;
     else if (!strcmp(key, "qr_twin")) ctx->opt_qr_twin = value;
+    else if (!strcmp(key, "qr_shard_pipeline")) ctx->opt_qr_shard_pipeline = value;
     else if (!strcmp(key, "spmv")) ctx->opt_spmv = value;
     else if (!strcmp(key, "ozaki_slices")) { if (value < 2 || value > 8) return lso_set_error(ctx, LSO_ERR_ARG, "ozaki_slices must be 2..8"); ctx->opt_ozaki_slices = value; }
     else if (!strcmp(key, "lsmr_fused")) ctx->opt_lsmr_fused = value;

@@ -35,6 +35,14 @@ struct lso_dense_ws {
     int n_twin = 0;
     cudaStream_t twin_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t twin_done[3] = {nullptr, nullptr, nullptr};
+    // panel-pipelined sharded solve: row blocks of the local R travel (all-gather) and enter the replicated stack QR while
+    // the local factorisation is still running
+    double* d_rowsend = nullptr;      // npanels x [ (n+1) columns x 32 rows ]
+    double* d_rowgath = nullptr;      // npanels x P x [ (n+1) x 32 ]
+    cudaStream_t comm_stream = nullptr, stack_stream = nullptr;
+    std::vector<cudaEvent_t> ev_local, ev_gath;
+    cudaEvent_t ev_stack_done = nullptr, ev_pipe_start = nullptr;
+    int pipe_P = 0;
     QRPlan plan_redamp;
     bool have_redamp = false;
     double* d_lastdamp = nullptr;
@@ -182,6 +190,13 @@ int lso_dense_ws_destroy(lso_dense_ws* ws) {
     qr_plan_destroy(&ws->plan);
     if (ws->have_stack) qr_plan_destroy(&ws->plan_stack);
     if (ws->have_redamp) qr_plan_destroy(&ws->plan_redamp);
+    cudaFree(ws->d_rowsend); cudaFree(ws->d_rowgath);
+    if (ws->comm_stream) cudaStreamDestroy(ws->comm_stream);
+    if (ws->stack_stream) cudaStreamDestroy(ws->stack_stream);
+    for (cudaEvent_t e : ws->ev_local) cudaEventDestroy(e);
+    for (cudaEvent_t e : ws->ev_gath) cudaEventDestroy(e);
+    if (ws->ev_stack_done) cudaEventDestroy(ws->ev_stack_done);
+    if (ws->ev_pipe_start) cudaEventDestroy(ws->ev_pipe_start);
     for (int t = 0; t < ws->n_twin; ++t) {
         qr_plan_destroy(&ws->plan_twin[t]);
         if (ws->twin_stream[t]) cudaStreamDestroy(ws->twin_stream[t]);
@@ -405,6 +420,161 @@ static int shard_stack_solve(lso_dense_ws* ws, int P, const double* d_damp, doub
     return remember_damped_factor(ws, ps, d_damp);
 }
 
+// ---- panel-pipelined TSQR -----------------------------------------------------------------------------------------
+// Row block k (rows 32k .. 32k+31) of a rank's R and of its Q'y is final as soon as the rank's panel k has been factorised
+// and applied, and panel k of the stack QR only involves the row blocks 0..k of every rank (QRPlan::band).  So the stack
+// factorisation runs panel by panel BEHIND the local one, on its own stream, fed by one small all-gather per panel: the
+// two latency-bound chains (32 panel trees each) overlap instead of following each other.
+// out: [(n+1) columns][32 rows] for row block k: columns 0..n-1 of R (zero below the diagonal / beyond row n), column n = Q'y
+__global__ void pack_rowblock_kernel(long long n, const double* __restrict__ A, long long ld, long long Npad, long long k,
+                                     double* __restrict__ out) {
+    const long long total = (n + 1) * QB;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long col = e / QB, r = e - col * QB;
+        const long long row = k * QB + r;
+        double v = 0.0;
+        if (row < n) {
+            if (col == n) v = A[Npad * ld + row];
+            else if (row <= col) v = A[col * ld + row];
+        }
+        out[e] = v;
+    }
+}
+// rows Q*(32k + r) + i of the interleaved stack (all Nc columns) from the P gathered row blocks and the damping triangle
+__global__ void stack_assemble_panel_kernel(long long n, int P, int Q, long long k, const double* __restrict__ gath,
+                                            const double* __restrict__ damp, double* __restrict__ A, long long ld,
+                                            long long Npad, long long Nc) {
+    const long long col = blockIdx.y;                       // 0 .. Nc-1
+    if (col >= Nc) return;
+    const long long scol = (col < n) ? col : ((col == Npad) ? n : -1);
+    for (int e = threadIdx.x; e < Q * QB; e += blockDim.x) {
+        const int r = e / Q, i = e - r * Q;
+        const long long row = k * QB + r;                   // row of the triangles
+        if (row >= n) continue;                             // (the rows past Q n are zeroed by stack_zero_tail_kernel)
+        double v = 0.0;
+        if (scol >= 0) {
+            if (i < P) v = gath[((long long)i * (n + 1) + scol) * QB + r];
+            else if (scol == row) v = sqrt(damp[row]);
+        }
+        A[col * ld + (long long)Q * row + i] = v;
+    }
+}
+// rows [row0, row1) of every column := 0 (what lies past the Q n rows in use: padding, and rows a solve with more triangles left)
+__global__ void stack_zero_tail_kernel(double* __restrict__ A, long long ld, long long row0, long long row1) {
+    const long long col = blockIdx.y;
+    for (long long r = row0 + threadIdx.x; r < row1; r += blockDim.x) A[col * ld + r] = 0.0;
+}
+
+static int pipe_ensure(lso_dense_ws* ws, int P) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    const int64_t np = ws->plan.Npad / QB;
+    if (ws->pipe_P == P && ws->d_rowsend) return LSO_OK;
+    cudaFree(ws->d_rowsend); cudaFree(ws->d_rowgath);
+    ws->d_rowsend = ws->d_rowgath = nullptr;
+    const size_t blk = (size_t)(n + 1) * QB;
+    LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_rowsend, (size_t)np * blk * sizeof(double)));
+    LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->d_rowgath, (size_t)np * (size_t)P * blk * sizeof(double)));
+    if (!ws->comm_stream) {
+        LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ws->comm_stream, cudaStreamNonBlocking));
+        LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ws->stack_stream, cudaStreamNonBlocking));
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ws->ev_stack_done, cudaEventDisableTiming));
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ws->ev_pipe_start, cudaEventDisableTiming));
+    }
+    while ((int64_t)ws->ev_local.size() < np) {
+        cudaEvent_t a, b;
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ws->ev_local.push_back(a);
+        ws->ev_gath.push_back(b);
+    }
+    ws->pipe_P = P;
+    return LSO_OK;
+}
+
+int lso_comm_allgather_on(lso_ctx* ctx, const double* d_send, double* d_recv, int64_t count, cudaStream_t st);
+
+// emulate != 0: the P shards are the row chunks of d_J on THIS device (test hook): they are factorised one after the other and
+// their row blocks copied into place instead of all-gathered; the stack side is the code the ranks run.
+static int qr_solve_sharded_pipelined(lso_dense_ws* ws, int P, bool emulate, const double* d_J, int64_t ld, const double* d_y,
+                                      const double* d_damp, double* d_x, int* rank_out) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    LSO_TRY(shard_ensure_stack(ws, P));
+    LSO_TRY(pipe_ensure(ws, P));
+    QRPlan* pl = &ws->plan;
+    QRPlan* ps = &ws->plan_stack;
+    const int Q = d_damp ? P + 1 : P;
+    ps->M = (int64_t)Q * n;
+    ps->band = Q;
+    const int64_t np = pl->Npad / QB;                        // panels of the local plan (m_loc >= n)
+    const int64_t nps = qr_num_panels(ps);
+    const size_t blk = (size_t)(n + 1) * QB;
+    const unsigned pgrid = (unsigned)std::min<int64_t>(cdiv64((int64_t)blk, 256), 64);
+    cudaStream_t U = ctx->stream, Cs = ws->comm_stream, S = ws->stack_stream;
+    ws->last_plan = nullptr;
+    ws->kept = false;
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_pipe_start, U));
+    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(Cs, ws->ev_pipe_start, 0));
+    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(S, ws->ev_pipe_start, 0));
+    int st = LSO_OK;
+    if (emulate) {
+        for (int i = 0; i < P && st == LSO_OK; ++i) {        // shard i: whole local QR, then its row blocks into slot i of every panel
+            st = qr_assemble(ctx, pl, ws->m, n, d_J + (size_t)i * ws->m, ld, d_y + (size_t)i * ws->m, nullptr);
+            const int64_t M_full = pl->M;
+            pl->M = ws->m;
+            if (st == LSO_OK) st = qr_factor(ctx, pl);
+            pl->M = M_full;
+            for (int64_t k = 0; k < np && st == LSO_OK; ++k) {
+                pack_rowblock_kernel<<<pgrid, 256, 0, U>>>(n, pl->A, pl->ld, pl->Npad, k, ws->d_rowgath + ((size_t)k * P + i) * blk);
+                ctx->launches++;
+            }
+        }
+        LSO_TRY(st);
+        LSO_CHECK_LAUNCH(ctx);
+        for (int64_t k = 0; k < np; ++k) LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_gath[k], U));
+    } else {
+        LSO_TRY(qr_assemble(ctx, pl, ws->m, n, d_J, ld, d_y, nullptr));
+        const int64_t M_full = pl->M;
+        pl->M = ws->m;
+        for (int64_t k = 0; k < np && st == LSO_OK; ++k) {
+            st = qr_factor_range(ctx, pl, k, k + 1);
+            if (st != LSO_OK) break;
+            pack_rowblock_kernel<<<pgrid, 256, 0, U>>>(n, pl->A, pl->ld, pl->Npad, k, ws->d_rowsend + (size_t)k * blk);
+            ctx->launches++;
+            cudaEventRecord(ws->ev_local[k], U);
+            cudaStreamWaitEvent(Cs, ws->ev_local[k], 0);
+            st = lso_comm_allgather_on(ctx, ws->d_rowsend + (size_t)k * blk, ws->d_rowgath + (size_t)k * P * blk, (int64_t)blk, Cs);
+            cudaEventRecord(ws->ev_gath[k], Cs);
+        }
+        pl->M = M_full;
+        LSO_TRY(st);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    // the stack side, one panel behind the data
+    {
+        const long long row0 = (long long)Q * n, row1 = std::min<long long>(ps->ld, row0 + 2 * QH);
+        dim3 grid(1, (unsigned)ps->Nc);
+        stack_zero_tail_kernel<<<grid, 128, 0, S>>>(ps->A, ps->ld, row0, row1);
+        ctx->launches++;
+    }
+    ctx->stream = S;
+    for (int64_t k = 0; k < np && st == LSO_OK; ++k) {
+        cudaStreamWaitEvent(S, ws->ev_gath[k], 0);
+        dim3 grid(1, (unsigned)ps->Nc);
+        stack_assemble_panel_kernel<<<grid, 128, 0, S>>>(n, P, Q, k, ws->d_rowgath + (size_t)k * P * blk, d_damp, ps->A, ps->ld, ps->Npad, ps->Nc);
+        ctx->launches++;
+        if (k < nps) st = qr_factor_range(ctx, ps, k, k + 1);
+    }
+    ctx->stream = U;
+    LSO_TRY(st);
+    LSO_CHECK_LAUNCH(ctx);
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_stack_done, S));
+    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, ws->ev_stack_done, 0));
+    LSO_TRY(qr_finish(ws, ps, d_x, rank_out, d_damp == nullptr));
+    return remember_damped_factor(ws, ps, d_damp);
+}
+
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
                          double* d_x, int* rank_out) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
@@ -417,6 +587,8 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     LSO_ENTER(ctx);
     const int64_t n = ws->n;
     const int P = ctx->nranks;
+    if (ctx->opt_qr_shard_pipeline && ws->plan.Npad / QB >= 2)
+        return qr_solve_sharded_pipelined(ws, P, false, d_J, ld, d_y, d_damp, d_x, rank_out);
     LSO_TRY(shard_ensure_stack(ws, P));
     double* sendbuf = ws->d_gather + (size_t)P * n * (n + 1);
     LSO_TRY(shard_local_R(ws, d_J, ld, d_y, sendbuf));
@@ -541,7 +713,8 @@ int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* 
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     lso_ctx* ctx = ws->ctx;
     LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && d_x, "bad arguments");
-    LSO_REQUIRE(ctx, ws->kept && ws->have_stack, "no factor kept: call lso_qr_factor_keep (or lso_qr_solve_sharded) first");
+    if (!(ws->kept && ws->have_stack))
+        return lso_set_error(ctx, LSO_ERR_UNSUPPORTED, "no factor kept: call lso_qr_factor_keep (or a non-pipelined lso_qr_solve_sharded) first");
     LSO_ENTER(ctx);
     return shard_stack_solve(ws, ws->stack_P, d_damp, d_x, rank_out);
 }
@@ -637,6 +810,8 @@ int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_
     LSO_REQUIRE(ctx, ws->m >= ws->n, "each shard needs rows >= columns");
     LSO_ENTER(ctx);
     const int64_t n = ws->n;
+    if (ctx->opt_qr_shard_pipeline && ws->plan.Npad / QB >= 2)
+        return qr_solve_sharded_pipelined(ws, P, true, d_J, ld, d_y, d_damp, d_x, rank_out);
     LSO_TRY(shard_ensure_stack(ws, P));
     for (int k = 0; k < P; ++k)
         LSO_TRY(shard_local_R(ws, d_J + (size_t)k * ws->m, ld, d_y + (size_t)k * ws->m, ws->d_gather + (size_t)k * n * (n + 1)));

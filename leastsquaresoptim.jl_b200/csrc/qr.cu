@@ -1636,27 +1636,28 @@ static void tl_dump(cudaStream_t U, cudaStream_t P) {
     g_tl_on = false;
 }
 
-static int qr_factor_run(lso_ctx* ctx, QRPlan* plan, int reserve) {
+static int qr_factor_run(lso_ctx* ctx, QRPlan* plan, int reserve, int64_t k_begin = 0, int64_t k_end = -1) {
     const int64_t M = plan->M;
     g_tl_on = (getenv("LSO_QR_TIMELINE") != nullptr) && plan->M > 50000;
     const int64_t npanels = std::min<int64_t>(plan->Npad / QB, cdiv64(M, QB));   // no rows left beyond that
     if (npanels <= 0) return LSO_OK;
+    if (k_end < 0 || k_end > npanels) k_end = npanels;
     {   // algorithmic flops of this factorisation (bench.py roofline): the level-0 update of every panel, real columns only
         PanelLevels pl;
-        for (int64_t k = 0; k < npanels; ++k) {
+        for (int64_t k = k_begin; k < k_end; ++k) {
             panel_levels(plan, k * QB, pl);
             const int64_t trailing = plan->N + 1 - (k + 1) * QB;
             if (trailing > 0) ctx->stat_qr_update_flops += 4.0 * QB * (double)pl.tm[0].rows * (double)trailing;
         }
         const double Mq = (double)M, Nq = (double)plan->N;
-        ctx->stat_qr_flops += 2.0 * Mq * Nq * Nq - 2.0 * Nq * Nq * Nq / 3.0;
+        if (k_begin == 0) ctx->stat_qr_flops += 2.0 * Mq * Nq * Nq - 2.0 * Nq * Nq * Nq / 3.0;
     }
     cudaStream_t U = ctx->stream, P = plan->panel_stream;
     const int LA = QB / QCT;      // tiles that make up the next panel's columns
     PanelLevels cur, nxt;
-    if (!ctx->opt_qr_lookahead) {
+    if (!ctx->opt_qr_lookahead || k_begin > 0 || k_end < npanels) {
         tl_mark(U, "start", 0, 0);
-        for (int64_t k = 0; k < npanels; ++k) {
+        for (int64_t k = k_begin; k < k_end; ++k) {
             const int64_t c0 = k * QB, ctrail = c0 + QB;
             panel_levels(plan, c0, cur);
             // qr_apply = 3: all levels in one launch; 4: levels 0 and 1 one launch each, the (tiny, latency-bound) levels
@@ -1721,6 +1722,18 @@ static int qr_factor_run(lso_ctx* ctx, QRPlan* plan, int reserve) {
     tl_dump(U, P);
     return LSO_OK;
 }
+
+// panels [k_begin, k_end) only (the caller runs the ranges in order; used to interleave two factorisations panel by panel)
+int qr_factor_range(lso_ctx* ctx, QRPlan* plan, int64_t k_begin, int64_t k_end) {
+    const int64_t sa = ctx->opt_qr_apply, sl = ctx->opt_qr_lookahead;
+    if (plan->sched_tuned && ctx->opt_qr_tune && !plan->sched_lookahead) ctx->opt_qr_apply = plan->sched_apply;
+    ctx->opt_qr_lookahead = 0;
+    const int st = qr_factor_run(ctx, plan, 0, k_begin, k_end);
+    ctx->opt_qr_apply = sa;
+    ctx->opt_qr_lookahead = sl;
+    return st;
+}
+int64_t qr_num_panels(const QRPlan* plan) { return std::min<int64_t>(plan->Npad / QB, cdiv64(plan->M, QB)); }
 
 int qr_factor(lso_ctx* ctx, QRPlan* plan) {
     if (!plan->sched_tuned || !ctx->opt_qr_tune) return qr_factor_run(ctx, plan, 0);

@@ -58,6 +58,9 @@ void qr_plan_destroy(QRPlan* plan);
 // Factorise plan->A in place: on return the leading N x N upper triangle holds R and column Npad
 // rows 0..N-1 hold Q'b (the right-hand side that was stored in column Npad on entry).
 int qr_factor(lso_ctx* ctx, QRPlan* plan);
+// panels [k_begin, k_end) only, on ctx->stream; ranges must be run in order and cover [0, qr_num_panels)
+int qr_factor_range(lso_ctx* ctx, QRPlan* plan, int64_t k_begin, int64_t k_end);
+int64_t qr_num_panels(const QRPlan* plan);
 // Small plans (a panel tree that fits on a third of the SMs) are latency-bound: time the launch schedules on synthetic
 // data once and keep the fastest (results are bit-identical across schedules: every tile job does the same arithmetic).
 int qr_plan_tune(lso_ctx* ctx, QRPlan* plan);

@@ -78,9 +78,16 @@ class DenseQRAllocatedSolver(_DenseWorkspace):
             check(lib().lso_qr_kept_invalidate(self._h), h)
             self._kept = False
         self._have_damped = False
+        done = False
         if use_keep and same_J and self._kept:
-            check(lib().lso_qr_solve_kept(self._h, dptr, x.ptr, C.byref(rank)), h)
-            self.solves_kept += 1
+            st = lib().lso_qr_solve_kept(self._h, dptr, x.ptr, C.byref(rank))
+            if st == 0:
+                self.solves_kept += 1
+                done = True
+            elif st != LSO_ERR_UNSUPPORTED:      # (the panel-pipelined sharded solve keeps no gathered factors)
+                check(st, h)
+        if done:
+            pass
         elif self.sharded:
             check(lib().lso_qr_solve_sharded(self._h, J.ptr, J.ld, y.ptr, dptr, x.ptr, C.byref(rank)), h)
             self._kept = True

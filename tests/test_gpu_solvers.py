@@ -290,6 +290,20 @@ def test_qr_sharded_algorithm_emulated_on_one_gpu(ctx, P, ms, n, damped):
     xr, _ = O.qr_ldiv(Jh, yh, damp)
     assert rank.value == n
     assert rel(xg, xr) <= TOL, rel(xg, xr)
+    # the panel-pipelined form (the stack QR runs panel by panel behind the local one; default) does the same arithmetic
+    # as "local QR, gather, stack QR": bit-identical δ; and a workspace that last solved WITH the damping triangle gives the
+    # right undamped answer afterwards (the stack then has one triangle less)
+    ctx.set_option("qr_shard_pipeline", 0)
+    try:
+        check(lib().lso_debug_qr_solve_emulated_shards(ws._h, P, J.ptr, J.ld, y.ptr, d.ptr if d is not None else None, x.ptr,
+                                                       C.byref(rank)), ctx.handle)
+        assert np.array_equal(x.download(), xg)
+    finally:
+        ctx.set_option("qr_shard_pipeline", 1)
+    if damped and ms >= n:
+        check(lib().lso_debug_qr_solve_emulated_shards(ws._h, P, J.ptr, J.ld, y.ptr, None, x.ptr, C.byref(rank)), ctx.handle)
+        xu, _ = O.qr_ldiv(Jh, yh, None)
+        assert rel(x.download(), xu) <= 1e-9
 
 
 @pytest.mark.parametrize("P", [2, 3, 8])
