@@ -43,11 +43,27 @@ struct lso_dense_ws {
     std::vector<cudaEvent_t> ev_local, ev_gath;
     cudaEvent_t ev_stack_done = nullptr, ev_pipe_start = nullptr;
     int pipe_P = 0;
+    // host-fed chunks, pipelined: chunk c's panel k is followed by its row block and the event ev_chunk[c * np + k]; the
+    // stack QR of lso_qr_solve_kept follows panel by panel.  chunk_done[w]: the last work queued on chunk stream w.
+    std::vector<cudaEvent_t> ev_chunk;
+    cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    int chunks_pending = 0;           // chunk streams (0 = none) the context stream has not been joined with yet
+    bool kept_pipe = false;           // d_rowgath holds the row blocks of all chunks (the kept factor of the pipelined form)
     QRPlan plan_redamp;
     bool have_redamp = false;
     double* d_lastdamp = nullptr;
     double* d_redamp_slot = nullptr;   // n x (n+1) packed [R | c]  +  n doubles for the damping increment
 };
+
+// The pipelined host-fed factorisation leaves work on the chunk streams that the context stream has not waited for (that is
+// its point: colsumabs2! and the damping run meanwhile).  Every other entry that touches the plans joins first.
+static int ws_join_chunks(lso_dense_ws* ws) {
+    lso_ctx* ctx = ws->ctx;
+    for (int w = 0; w < ws->chunks_pending; ++w)
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ws->chunk_done[w], 0));
+    ws->chunks_pending = 0;
+    return LSO_OK;
+}
 
 // ---- Q-a: build [J; diag(sqrt(damp)) | y; 0] in the padded workspace (dense_qr.jl:32-36, 64-80) ----
 __global__ void qr_assemble_kernel(long long m, long long n, long long M, const double* __restrict__ J, long long ldJ,
@@ -187,6 +203,9 @@ int lso_dense_ws_destroy(lso_dense_ws* ws) {
     lso_ctx* ctx = ws->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ws->comm_stream) cudaStreamSynchronize(ws->comm_stream);
+    if (ws->stack_stream) cudaStreamSynchronize(ws->stack_stream);
+    for (int t = 0; t < ws->n_twin; ++t) if (ws->twin_stream[t]) cudaStreamSynchronize(ws->twin_stream[t]);
     qr_plan_destroy(&ws->plan);
     if (ws->have_stack) qr_plan_destroy(&ws->plan_stack);
     if (ws->have_redamp) qr_plan_destroy(&ws->plan_redamp);
@@ -195,6 +214,8 @@ int lso_dense_ws_destroy(lso_dense_ws* ws) {
     if (ws->stack_stream) cudaStreamDestroy(ws->stack_stream);
     for (cudaEvent_t e : ws->ev_local) cudaEventDestroy(e);
     for (cudaEvent_t e : ws->ev_gath) cudaEventDestroy(e);
+    for (cudaEvent_t e : ws->ev_chunk) cudaEventDestroy(e);
+    for (cudaEvent_t e : ws->chunk_done) if (e) cudaEventDestroy(e);
     if (ws->ev_stack_done) cudaEventDestroy(ws->ev_stack_done);
     if (ws->ev_pipe_start) cudaEventDestroy(ws->ev_pipe_start);
     for (int t = 0; t < ws->n_twin; ++t) {
@@ -221,6 +242,7 @@ int lso_qr_solve(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* 
     // dense_qr.jl:61 — the damped form needs the (m+n)-row workspace, the undamped form the m-row one
     LSO_REQUIRE(ctx, (d_damp != nullptr) == (ws->damped != 0), "length(u) should equal length(x) + length(y)");
     LSO_ENTER(ctx);
+    LSO_TRY(ws_join_chunks(ws));
     ws->last_plan = nullptr;
     LSO_TRY(qr_assemble(ctx, &ws->plan, ws->m, ws->n, d_J, ld, d_y, d_damp));
     LSO_TRY(qr_factor(ctx, &ws->plan));
@@ -492,6 +514,51 @@ static int pipe_ensure(lso_dense_ws* ws, int P) {
     return LSO_OK;
 }
 
+// The stack side of the pipelined forms: on the stack stream, panel k of the replicated stack QR follows the arrival of row
+// block k of every triangle.  n_chunk_events == 0: the blocks of panel k are signalled by ev_gath[k] (all-gather / emulation);
+// > 0: by ev_chunk[c * np + k] for each of that many host-fed chunks.  Ends with the finish on the context stream.
+static int stack_solve_from_rowblocks(lso_dense_ws* ws, int P, int n_chunk_events, const double* d_damp, double* d_x, int* rank_out) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t n = ws->n;
+    QRPlan* ps = &ws->plan_stack;
+    const int Q = d_damp ? P + 1 : P;
+    ps->M = (int64_t)Q * n;
+    ps->band = Q;
+    const int64_t np = ws->plan.Npad / QB;
+    const int64_t nps = qr_num_panels(ps);
+    const size_t blk = (size_t)(n + 1) * QB;
+    cudaStream_t U = ctx->stream, S = ws->stack_stream;
+    ws->last_plan = nullptr;
+    if (n_chunk_events > 0) {                               // the damping was computed on the context stream after the chunks were queued
+        LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_pipe_start, U));
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(S, ws->ev_pipe_start, 0));
+    }
+    {
+        const long long row0 = (long long)Q * n, row1 = std::min<long long>(ps->ld, row0 + 2 * QH);
+        dim3 grid(1, (unsigned)ps->Nc);
+        stack_zero_tail_kernel<<<grid, 128, 0, S>>>(ps->A, ps->ld, row0, row1);
+        ctx->launches++;
+    }
+    int st = LSO_OK;
+    ctx->stream = S;
+    for (int64_t k = 0; k < np && st == LSO_OK; ++k) {
+        if (n_chunk_events > 0) for (int c = 0; c < n_chunk_events; ++c) cudaStreamWaitEvent(S, ws->ev_chunk[(size_t)c * np + k], 0);
+        else cudaStreamWaitEvent(S, ws->ev_gath[k], 0);
+        dim3 grid(1, (unsigned)ps->Nc);
+        stack_assemble_panel_kernel<<<grid, 128, 0, S>>>(n, P, Q, k, ws->d_rowgath + (size_t)k * P * blk, d_damp, ps->A, ps->ld, ps->Npad, ps->Nc);
+        ctx->launches++;
+        if (k < nps) st = qr_factor_range(ctx, ps, k, k + 1);
+    }
+    ctx->stream = U;
+    LSO_TRY(st);
+    LSO_CHECK_LAUNCH(ctx);
+    LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_stack_done, S));
+    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, ws->ev_stack_done, 0));
+    if (n_chunk_events > 0) ws->chunks_pending = 0;         // the stack followed every chunk's last panel
+    LSO_TRY(qr_finish(ws, ps, d_x, rank_out, d_damp == nullptr));
+    return remember_damped_factor(ws, ps, d_damp);
+}
+
 int lso_comm_allgather_on(lso_ctx* ctx, const double* d_send, double* d_recv, int64_t count, cudaStream_t st);
 
 // emulate != 0: the P shards are the row chunks of d_J on THIS device (test hook): they are factorised one after the other and
@@ -513,7 +580,7 @@ static int qr_solve_sharded_pipelined(lso_dense_ws* ws, int P, bool emulate, con
     const unsigned pgrid = (unsigned)std::min<int64_t>(cdiv64((int64_t)blk, 256), 64);
     cudaStream_t U = ctx->stream, Cs = ws->comm_stream, S = ws->stack_stream;
     ws->last_plan = nullptr;
-    ws->kept = false;
+    ws->kept = false; ws->kept_pipe = false;
     LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_pipe_start, U));
     LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(Cs, ws->ev_pipe_start, 0));
     LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(S, ws->ev_pipe_start, 0));
@@ -551,28 +618,7 @@ static int qr_solve_sharded_pipelined(lso_dense_ws* ws, int P, bool emulate, con
         LSO_TRY(st);
         LSO_CHECK_LAUNCH(ctx);
     }
-    // the stack side, one panel behind the data
-    {
-        const long long row0 = (long long)Q * n, row1 = std::min<long long>(ps->ld, row0 + 2 * QH);
-        dim3 grid(1, (unsigned)ps->Nc);
-        stack_zero_tail_kernel<<<grid, 128, 0, S>>>(ps->A, ps->ld, row0, row1);
-        ctx->launches++;
-    }
-    ctx->stream = S;
-    for (int64_t k = 0; k < np && st == LSO_OK; ++k) {
-        cudaStreamWaitEvent(S, ws->ev_gath[k], 0);
-        dim3 grid(1, (unsigned)ps->Nc);
-        stack_assemble_panel_kernel<<<grid, 128, 0, S>>>(n, P, Q, k, ws->d_rowgath + (size_t)k * P * blk, d_damp, ps->A, ps->ld, ps->Npad, ps->Nc);
-        ctx->launches++;
-        if (k < nps) st = qr_factor_range(ctx, ps, k, k + 1);
-    }
-    ctx->stream = U;
-    LSO_TRY(st);
-    LSO_CHECK_LAUNCH(ctx);
-    LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->ev_stack_done, S));
-    LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(U, ws->ev_stack_done, 0));
-    LSO_TRY(qr_finish(ws, ps, d_x, rank_out, d_damp == nullptr));
-    return remember_damped_factor(ws, ps, d_damp);
+    return stack_solve_from_rowblocks(ws, P, 0, d_damp, d_x, rank_out);
 }
 
 int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const double* d_y, const double* d_damp,
@@ -585,6 +631,7 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     LSO_REQUIRE(ctx, d_J && d_y && d_x, "NULL pointer");
     LSO_REQUIRE(ctx, ws->m >= ws->n, "sharded QR: each shard needs rows >= columns");
     LSO_ENTER(ctx);
+    LSO_TRY(ws_join_chunks(ws));
     const int64_t n = ws->n;
     const int P = ctx->nranks;
     if (ctx->opt_qr_shard_pipeline && ws->plan.Npad / QB >= 2)
@@ -595,7 +642,7 @@ int lso_qr_solve_sharded(lso_dense_ws* ws, const double* d_J, int64_t ld, const 
     lso_prof_mark2(ctx);
     LSO_TRY(lso_comm_allgather(ctx, sendbuf, ws->d_gather, n * (n + 1)));
     lso_prof_mark2(ctx);
-    ws->kept = true;
+    ws->kept = true; ws->kept_pipe = false;
     return shard_stack_solve(ws, P, d_damp, d_x, rank_out);
 }
 
@@ -614,10 +661,11 @@ int lso_qr_factor_keep(lso_dense_ws* ws, const double* d_J, int64_t ld, const do
     LSO_REQUIRE(ctx, ld >= ws->m, "leading dimension < m");
     LSO_REQUIRE(ctx, ws->m >= ws->n, "kept-factor path needs rows >= columns");
     LSO_ENTER(ctx);
-    ws->kept = false;
+    LSO_TRY(ws_join_chunks(ws));
+    ws->kept = false; ws->kept_pipe = false;
     LSO_TRY(shard_ensure_stack(ws, 1));
     LSO_TRY(shard_local_R(ws, d_J, ld, d_y, ws->d_gather));
-    ws->kept = true;
+    ws->kept = true; ws->kept_pipe = false;
     return LSO_OK;
 }
 
@@ -640,7 +688,8 @@ int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk
     LSO_REQUIRE(ctx, ld_h >= m_total && ld_d >= m_total, "leading dimension < rows");
     LSO_REQUIRE(ctx, ws->m >= n, "the workspace needs rows >= columns");
     LSO_ENTER(ctx);
-    ws->kept = false;
+    LSO_TRY(ws_join_chunks(ws));
+    ws->kept = false; ws->kept_pipe = false;
     ws->last_plan = nullptr;
     if (!ctx->copy_stream) {
         LSO_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -675,6 +724,53 @@ int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk
     cudaStream_t main_stream = ctx->stream;
     int st = LSO_OK;
     r0 = 0;
+    if (ctx->opt_qr_shard_pipeline && P >= 2 && ws->plan.Npad / QB >= 2) {
+        // Pipelined form: every chunk is factorised panel by panel on a stream of its own (never the context stream), its row
+        // block k packed and signalled after panel k; the context stream only waits for the LAST COPY, so the caller's
+        // passes over the whole J (colsumabs2!, J'f) and the damping run while the last chunk is still being factorised,
+        // and lso_qr_solve_kept's stack QR then follows that factorisation one panel behind (qr_solve_sharded_pipelined).
+        LSO_TRY(pipe_ensure(ws, P));
+        const int64_t np = ws->plan.Npad / QB;
+        while ((int64_t)ws->ev_chunk.size() < (int64_t)P * np) {
+            cudaEvent_t e;
+            LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ws->ev_chunk.push_back(e);
+        }
+        for (int w = 0; w < K; ++w)
+            if (!ws->chunk_done[w]) LSO_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ws->chunk_done[w], cudaEventDisableTiming));
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ws->comm_stream, ctx->copy_ev[0], 0));
+        const size_t blk = (size_t)(n + 1) * QB;
+        const unsigned pgrid = (unsigned)std::min<int64_t>(cdiv64((int64_t)blk, 256), 64);
+        for (int c = 0; c < P && st == LSO_OK; ++c) {
+            const int64_t rows = chunk_rows[c];
+            const int w = c % K;
+            QRPlan* pl = (w == 0) ? &ws->plan : &ws->plan_twin[w - 1];
+            cudaStream_t cs = (w == 0) ? ws->comm_stream : ws->twin_stream[w - 1];
+            ctx->stream = cs;
+            if (cudaStreamWaitEvent(cs, ctx->copy_ev[1 + c], 0) != cudaSuccess) { st = lso_set_error(ctx, LSO_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+            st = qr_assemble(ctx, pl, rows, n, d_J + r0, ld_d, d_y + r0, nullptr);
+            const int64_t M_full = pl->M;
+            pl->M = std::max<int64_t>(rows, n);
+            for (int64_t k = 0; k < np && st == LSO_OK; ++k) {
+                st = qr_factor_range(ctx, pl, k, k + 1);
+                if (st != LSO_OK) break;
+                pack_rowblock_kernel<<<pgrid, 256, 0, cs>>>(n, pl->A, pl->ld, pl->Npad, k, ws->d_rowgath + ((size_t)k * P + c) * blk);
+                ctx->launches++;
+                cudaEventRecord(ws->ev_chunk[(size_t)c * np + k], cs);
+            }
+            pl->M = M_full;
+            r0 += rows;
+        }
+        ctx->stream = main_stream;
+        LSO_TRY(st);
+        LSO_CHECK_LAUNCH(ctx);
+        LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->chunk_done[0], ws->comm_stream));
+        for (int w = 1; w < K; ++w) LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->chunk_done[w], ws->twin_stream[w - 1]));
+        ws->chunks_pending = K;
+        LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->copy_ev[P], 0));   // J and y are whole on the device
+        ws->kept_pipe = true;
+        return LSO_OK;
+    }
     for (int k = 0; k < P && st == LSO_OK; ++k) {
         const int64_t rows = chunk_rows[k];
         const int w = k % K;                  // 0 = the workspace's own plan on the context stream
@@ -689,7 +785,7 @@ int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk
         LSO_CHECK_CUDA(ctx, cudaEventRecord(ws->twin_done[t], ws->twin_stream[t]));
         LSO_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ws->twin_done[t], 0));
     }
-    ws->kept = true;
+    ws->kept = true; ws->kept_pipe = false;
     return LSO_OK;
 }
 
@@ -713,6 +809,10 @@ int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* 
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
     lso_ctx* ctx = ws->ctx;
     LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && d_x, "bad arguments");
+    if (ws->kept_pipe && ws->have_stack) {
+        LSO_ENTER(ctx);
+        return stack_solve_from_rowblocks(ws, ws->stack_P, /*n_chunk_events=*/ws->stack_P, d_damp, d_x, rank_out);
+    }
     if (!(ws->kept && ws->have_stack))
         return lso_set_error(ctx, LSO_ERR_UNSUPPORTED, "no factor kept: call lso_qr_factor_keep (or a non-pipelined lso_qr_solve_sharded) first");
     LSO_ENTER(ctx);
@@ -721,7 +821,7 @@ int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* 
 
 int lso_qr_kept_invalidate(lso_dense_ws* ws) {
     if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
-    ws->kept = false;
+    ws->kept = false; ws->kept_pipe = false;
     ws->last_plan = nullptr;
     return LSO_OK;
 }
@@ -750,6 +850,7 @@ int lso_qr_solve_redamp(lso_dense_ws* ws, const double* d_damp_new, double* d_x,
     LSO_REQUIRE(ctx, ws->kind == LSO_SOLVER_QR && d_damp_new && d_x, "bad arguments");
     if (!ws->last_plan) return lso_set_error(ctx, LSO_ERR_UNSUPPORTED, "no damped factor to re-damp");
     LSO_ENTER(ctx);
+    LSO_TRY(ws_join_chunks(ws));
     const int64_t n = ws->n;
     if (!ws->have_redamp) {
         LSO_TRY(qr_plan_create(ctx, 2 * n, n, &ws->plan_redamp));
@@ -809,6 +910,7 @@ int lso_debug_qr_solve_emulated_shards(lso_dense_ws* ws, int P, const double* d_
     LSO_REQUIRE(ctx, P >= 1 && P <= 64 && d_J && d_y && d_x, "bad arguments");
     LSO_REQUIRE(ctx, ws->m >= ws->n, "each shard needs rows >= columns");
     LSO_ENTER(ctx);
+    LSO_TRY(ws_join_chunks(ws));
     const int64_t n = ws->n;
     if (ctx->opt_qr_shard_pipeline && ws->plan.Npad / QB >= 2)
         return qr_solve_sharded_pipelined(ws, P, true, d_J, ld, d_y, d_damp, d_x, rank_out);

@@ -609,3 +609,41 @@ def test_host_step_chunked_upload_matches_the_direct_solve(ctx, chunks):
     assert rel(out[key][0], xr) <= 1e-10 and rel(out[1][0], xr) <= 1e-10
     for k in ("ssr", "predicted_ssr", "maxabs_gr", "maxabs_dx"):
         assert abs(out[key][1][k] - out[1][1][k]) <= 1e-9 * abs(out[1][1][k]), k
+
+
+@pytest.mark.parametrize("chunks", [2, [0.3, 0.3, 0.25, 0.15], 5])
+def test_host_chunks_pipelined_stack_is_bit_identical_and_keeps_its_factor(ctx, chunks):
+    """The pipelined host-fed form (chunks factorised panel by panel on their own streams, stack QR of lso_qr_solve_kept one
+    panel behind, context option "qr_shard_pipeline") does the arithmetic of the unpipelined form in the same order: δ is
+    bit-identical; the kept row blocks serve a second damping (solve_kept again) and a re-damping."""
+    import lsob200 as L
+    m, n = 30011, 200
+    rng = np.random.default_rng(21)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)))
+    fh = rng.standard_normal(m)
+    dtd = np.einsum("ij,ij->j", Jh, Jh)
+    got = {}
+    try:
+        for pipe in (1, 0):
+            ctx.set_option("qr_shard_pipeline", pipe)
+            x = L.DeviceVector(ctx, n)
+            nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m), f_=lambda o, xx: None, g_=lambda JJ, xx: None,
+                                        J=L.DenseMatrix(ctx, m, n), device_callbacks=True, ctx=ctx)
+            anls = L.allocate(nls, L.LevenbergMarquardt(L.QR()))
+            hs = L.HostStep(anls, chunks=chunks)
+            dx = np.zeros(n)
+            for _ in range(2):
+                hs.run(Jh.ctypes.data, fh.ctypes.data, 10.0, dx)
+            d2 = L.DeviceVector(ctx, n, dtd / 3.0)
+            x2 = L.DeviceVector(ctx, n)
+            hs.chunk_solver.solve_kept(x2, d2)                 # a second damping on the kept factor
+            d3 = L.DeviceVector(ctx, n, dtd * 2.0)
+            x3 = L.DeviceVector(ctx, n)
+            hs.chunk_solver.ldiv(x3, anls.J, anls.fcur, d3, same_J=True)   # a larger one: re-damping of the last factor
+            got[pipe] = (dx.copy(), x2.download(), x3.download())
+    finally:
+        ctx.set_option("qr_shard_pipeline", 1)
+    assert np.array_equal(got[1][0], got[0][0]) and np.array_equal(got[1][1], got[0][1])
+    xr2, _ = O.qr_ldiv(Jh, fh, dtd / 3.0)
+    xr3, _ = O.qr_ldiv(Jh, fh, dtd * 2.0)
+    assert rel(got[1][1], xr2) <= 1e-10 and rel(got[1][2], xr3) <= 1e-10 and rel(got[0][2], xr3) <= 1e-10
