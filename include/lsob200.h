@@ -60,7 +60,9 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *                  factors) time four launch schedules once at creation and keep the fastest; setting "qr_apply" or
  *                  "qr_lookahead" explicitly turns this off
  *   "qr_shard_pipeline" 1 (default) = lso_qr_solve_sharded runs the replicated stack QR panel by panel behind the local
- *                  factorisation, fed by one small all-gather per panel; 0 = local QR, one all-gather, stack QR
+ *                  factorisation, fed by one small all-gather per panel; 0 = local QR, one all-gather, stack QR.
+ *                  The same switch pipelines lso_qr_factor_keep_host[_chunks] + lso_qr_solve_kept: the chunks are
+ *                  factorised panel by panel on streams of their own and the stack QR follows the last one.
  *   "qr_twin"      extra workspaces / streams (0..3, default 2) among which lso_qr_factor_keep_host[_chunks] rotates its
  *                  chunks when there are three or more (the panel trees of one chunk run under the updates of another)
  *   "syrk"         0 plain-FMA syrk, 1 DMMA syrk, 3 (default) tcgen05 syrk for m >= 8192 and n >= 512 and DMMA otherwise,
@@ -209,7 +211,10 @@ int lso_qr_solve_kept(lso_dense_ws* ws, const double* d_damp, double* d_x, int* 
 int lso_qr_factor_keep_host(lso_dense_ws* ws, int64_t m_total, const double* h_J, int64_t ld_h, const double* h_y,
                             double* d_J, int64_t ld_d, double* d_y);
 /* the same with an explicit list of chunk sizes (each <= the workspace's m, sum = rows of J), sent in that order; with
- * three or more chunks they are factorised round-robin in up to "qr_twin" + 1 workspaces on as many streams */
+ * three or more chunks they are factorised round-robin in up to "qr_twin" + 1 workspaces on as many streams.
+ * With "qr_shard_pipeline" (default) the call returns with the context stream ordered after the COPIES only: d_J and
+ * d_y are whole for the caller's passes (colsumabs2!, J'f), the factorisations are still running on their own streams,
+ * and lso_qr_solve_kept joins them panel by panel.  Any other call on the workspace joins them first. */
 int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk_rows, const double* h_J, int64_t ld_h,
                                    const double* h_y, double* d_J, int64_t ld_d, double* d_y);
 int lso_qr_kept_invalidate(lso_dense_ws* ws);

@@ -19,9 +19,11 @@ check(lib().lso_download(ctx.handle, hJ, anls.J.ptr, m * n * 8), ctx.handle)
 check(lib().lso_download(ctx.handle, hf, anls.fcur.ptr, m * 8), ctx.handle)
 dx = np.zeros(n)
 ref = None
-cases = [(1, 1), (2, 1), ([0.43, 0.57], 1), (3, 1), (4, 1), (4, 2), (4, 3), ([0.3, 0.3, 0.25, 0.15], 1), ([0.3, 0.3, 0.25, 0.15], 2),
-         ([0.35, 0.3, 0.2, 0.15], 1), ([0.28, 0.28, 0.22, 0.14, 0.08], 1), ([0.28, 0.28, 0.22, 0.14, 0.08], 2), ([0.25, 0.25, 0.2, 0.15, 0.1, 0.05], 2),
-         ([0.4, 0.3, 0.2, 0.1], 1), (5, 2), (6, 2), (None, 1)]
+cases = [(1, 2), ([0.3, 0.3, 0.25, 0.15], 2), ([0.2, 0.3, 0.3, 0.2], 2), ([0.25, 0.3, 0.25, 0.2], 2), ([0.2, 0.3, 0.3, 0.2], 3),
+         ([0.15, 0.25, 0.25, 0.2, 0.15], 2), ([0.15, 0.25, 0.25, 0.2, 0.15], 3), ([0.2, 0.25, 0.25, 0.18, 0.12], 3), ([0.25, 0.25, 0.25, 0.25], 3),
+         ([0.1, 0.2, 0.25, 0.25, 0.2], 3), ([0.28, 0.28, 0.26, 0.18], 2), ([0.3, 0.28, 0.24, 0.18], 2), ([0.32, 0.3, 0.24, 0.14], 2),
+         ([0.3, 0.3, 0.27, 0.13], 2), ([0.33, 0.33, 0.34], 2), ([0.4, 0.35, 0.25], 2), ([0.38, 0.36, 0.26], 2), (None, 2)]
+if len(sys.argv) > 1 and sys.argv[1] == "nopipe": ctx.set_option("qr_shard_pipeline", 0)
 for chunks, twin in cases:
     ctx.set_option("qr_twin", twin)
     hs = L.HostStep(anls, chunks=chunks)
