@@ -290,6 +290,17 @@ int lso_lsmr_solve_ex(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_J, int64_
                       double atol, double btol, double conlim, int64_t maxiter,
                       const double* d_P_diag, lso_precond_fn precond_apply, void* precond_user,
                       int64_t* iters_out, int* istop_out);
+/* (f4) LSMR on a row-sharded J, one process per GPU (needs lso_comm_init_rank): A_csc / d_y are THIS rank's rows of J
+ * and y (the workspace's m = the rank's row count), d_damp / d_x / d_P_diag are replicated.  u is sharded like the rows;
+ * v, h, hbar, x and the damping part of u are replicated.  Per iteration (iterative_lsmr.jl:30-51, lsmr.jl:116-156):
+ * local J_k (P.v), local J_k'u_k with u not yet normalised, ONE ncclAllReduce of [J'u (n) | ||u||^2 (1)], then beta,
+ * the new v, alpha, the rotations and the stopping tests replicated on every rank: 4 launches + 1 collective per
+ * iteration, the same <= 1 host synchronisation as the single-GPU form.  m_total = rows of the whole J (default maxiter,
+ * lsmr.jl:55; 0 = unknown).  Same answer as lso_lsmr_solve on the whole J up to the order of the row sums.  On a context
+ * without a communicator this IS lso_lsmr_solve_ex. */
+int lso_lsmr_solve_sharded(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_y, double* d_damp, double* d_x,
+                           double atol, double btol, double conlim, int64_t maxiter, int64_t m_total,
+                           const double* d_P_diag, int64_t* iters_out, int* istop_out);
 /* kernel launches and host synchronisations of the last solve on this workspace (lsmr.jl:116-231 runs on the device:
  * 3 launches per iteration, at most one synchronisation per iteration) */
 int lso_lsmr_ws_stats(lso_lsmr_ws* ws, int64_t* launches_out, int64_t* syncs_out);

@@ -243,11 +243,13 @@ class _Allocated:
         damped = isinstance(optimizer, LevenbergMarquardt)
         if sharded and getattr(ctx, "nranks", 1) <= 1:
             raise ValueError("sharded=True needs a communicator on the context (Context.comm_init)")
-        if sharded and (isinstance(solver, LSMR) or self.sparse or (not damped and not isinstance(solver, QR))):
-            # the row-sharded paths are LM(QR) / Dogleg(QR) (TSQR) and LM(Cholesky) (one all-reduce); LSMR stays
-            # single-GPU (BASELINE.json north_star) and the undamped Cholesky has no sharded form
+        sharded_lsmr = sharded and isinstance(solver, LSMR) and self.sparse
+        if sharded and not sharded_lsmr and (isinstance(solver, LSMR) or self.sparse or
+                                             (not damped and not isinstance(solver, QR))):
+            # the row-sharded paths are LM(QR) / Dogleg(QR) (TSQR), LM(Cholesky) (one all-reduce of [J'J | J'f]) and LSMR on a
+            # sparse J (one all-reduce of [J'u | ||u||²] per iteration); the undamped Cholesky has no sharded form
             raise ValueError("sharded=True is implemented for LevenbergMarquardt with QR() or Cholesky() and for Dogleg with "
-                             "QR(), on a dense J")
+                             "QR() on a dense J, and for LSMR() on a sparse (CSC) J")
         if isinstance(solver, QR):
             # row-sharded J: local QR of [J_k | y_k] needs the undamped m_k x n workspace; the sqrt(damp) rows join
             # the stack of R factors (lso_qr_solve_sharded)
@@ -258,7 +260,15 @@ class _Allocated:
             self.solver = DenseCholeskyAllocatedSolver(ctx, m, n, damped, sharded=sharded)
         elif isinstance(solver, LSMR):
             pc = getattr(solver, "preconditioner", None)
-            self.solver = (LSMRDampenedAllocatedSolver(ctx, m, n, pc) if damped else LSMRAllocatedSolver(ctx, m, n, pc))
+            m_total = 0
+            if sharded_lsmr:
+                if isinstance(pc, tuple):
+                    raise ValueError("the row-sharded LSMR takes the default or a diagonal preconditioner")
+                cnt = DeviceVector(ctx, 1, np.array([float(m)]))        # rows of the whole J: lsmr.jl:55 default maxiter
+                ctx.allreduce(cnt)
+                m_total = int(round(float(cnt.download()[0])))
+            cls = LSMRDampenedAllocatedSolver if damped else LSMRAllocatedSolver
+            self.solver = cls(ctx, m, n, pc, sharded=sharded_lsmr, m_total=m_total)
         else:
             raise TypeError(f"unknown solver {solver!r}")
 

@@ -32,6 +32,7 @@ struct LsmrState {
     double atol, btol, ctol;
     long long iter, maxiter;
     int istop, done, v_fresh, pad;                    // v_fresh: this iteration produced a new (unnormalised) v
+    double ux_sumsq;                                  // row-sharded form: ‖b.x‖² of the (replicated) damping part of u
 };
 struct LsmrTail { long long iter; int istop, done; };
 
@@ -43,6 +44,7 @@ struct lso_lsmr_ws {
            *zerosvector = nullptr, *u = nullptr;
     LsmrState* d_state = nullptr;
     LsmrTail* h_tail = nullptr;      // pinned
+    double* packed = nullptr;        // row-sharded form: [ J_k'u_k (n) | ‖u_k‖² ], all-reduced once per iteration
     int64_t last_syncs = 0, last_launches = 0;
 };
 
@@ -133,6 +135,77 @@ struct LsmrFwd {
     }
 };
 
+// α = ‖v‖ (unless the step was skipped), then lsmr.jl:80-113 (init) or one iteration of the rotations / norm estimates
+// (lsmr.jl:128-200); runs in ONE thread (the last CTA to retire of the kernel that produced ‖v‖²)
+__device__ void lsmr_recurrences(LsmrState& s, double sv, bool skip, int init) {
+    double alpha = s.alpha;
+    if (!skip) {
+        alpha = sqrt(sv);
+        s.alpha = alpha;
+        s.inv_alpha = alpha > 0.0 ? 1.0 / alpha : 1.0;
+        s.v_fresh = 1;
+    } else {
+        s.v_fresh = 0;
+    }
+    const double beta = s.beta;
+    if (init) {                                      // lsmr.jl:80-113
+        s.zetabar = alpha * beta; s.alphabar = alpha; s.rho = 1.0; s.rhobar = 1.0; s.cbar = 1.0; s.sbar = 0.0;
+        s.betadd = beta; s.betad = 0.0; s.rhodold = 1.0; s.tautildeold = 0.0; s.thetatilde = 0.0; s.zeta = 0.0; s.d = 0.0;
+        s.normA2 = alpha * alpha; s.maxrbar = 0.0; s.minrbar = 1e100;
+        s.normb = beta; s.normr = beta; s.normAr = alpha * beta;
+        s.normA = -1.0; s.condA = -1.0;
+        s.c1 = 0.0; s.c2 = 0.0; s.c3 = 0.0;
+        if (!(s.normAr != 0.0)) s.done = 1;          // lsmr.jl:115: exit if b = 0 or A'b = 0
+        return;
+    }
+    s.iter += 1;
+    const double lambda = 0.0;                       // damping lives in the augmented operator
+    // rotation Qhat_{k,2k+1}
+    const double alphahat = sqrt(sqd(s.alphabar) + sqd(lambda));
+    const double chat = s.alphabar / alphahat, shat = lambda / alphahat;
+    // rotation Q_i turning B_i into R_i
+    const double rhoold = s.rho;
+    const double rho = sqrt(sqd(alphahat) + sqd(beta));
+    const double c = alphahat / rho, sn = beta / rho;
+    const double thetanew = sn * alpha;
+    s.alphabar = c * alpha;
+    // rotation Qbar_i turning R_i' into R_i^bar
+    const double rhobarold = s.rhobar, zetaold = s.zeta;
+    const double thetabar = s.sbar * rho, rhotemp = s.cbar * rho;
+    const double rhobar = sqrt(sqd(s.cbar * rho) + sqd(thetanew));
+    s.cbar = s.cbar * rho / rhobar;
+    s.sbar = thetanew / rhobar;
+    const double zeta = s.cbar * s.zetabar;
+    s.zetabar = -s.sbar * s.zetabar;
+    s.rho = rho; s.rhobar = rhobar; s.zeta = zeta;
+    s.c1 = -thetabar * rho / (rhoold * rhobarold);
+    s.c2 = zeta / (rho * rhobar);
+    s.c3 = -thetanew / rho;
+    // estimate of ‖r‖
+    const double betaacute = chat * s.betadd, betacheck = -shat * s.betadd;
+    const double betahat = c * betaacute;
+    s.betadd = -sn * betaacute;
+    const double thetatildeold = s.thetatilde;
+    const double rhotildeold = sqrt(sqd(s.rhodold) + sqd(thetabar));
+    const double ctildeold = s.rhodold / rhotildeold, stildeold = thetabar / rhotildeold;
+    s.thetatilde = stildeold * rhobar;
+    s.rhodold = ctildeold * rhobar;
+    s.betad = -stildeold * s.betad + ctildeold * betahat;
+    s.tautildeold = (zetaold - thetatildeold * s.tautildeold) / rhotildeold;
+    const double taud = (zeta - s.thetatilde * s.tautildeold) / s.rhodold;
+    s.d = s.d + sqd(betacheck);
+    s.normr = sqrt(s.d + sqd(s.betad - taud) + sqd(s.betadd));
+    // estimate of ‖A‖ and cond(A)
+    s.normA2 = s.normA2 + sqd(beta);
+    s.normA = sqrt(s.normA2);
+    s.normA2 = s.normA2 + sqd(alpha);
+    s.maxrbar = fmax(s.maxrbar, rhobarold);
+    if (s.iter > 1) s.minrbar = fmin(s.minrbar, rhobarold);
+    s.condA = fmax(s.maxrbar, rhotemp) / fmin(s.minrbar, rhotemp);
+    s.normAr = fabs(s.zetabar);
+}
+
+
 // v <- A'u - β v  (lsmr.jl:76,122 through iterative_lsmr.jl:36-51 and :95-109), segments = columns of the CSC image
 struct LsmrAdj {
     LsmrState* st;
@@ -165,74 +238,7 @@ struct LsmrAdj {
     }
     __device__ __forceinline__ double epilogue2(long long, double, double) const { return 0.0; }
     __device__ __forceinline__ double extra(long long) const { return 0.0; }
-    __device__ void finish(double sv, double) const {
-        LsmrState& s = *st;
-        double alpha = s.alpha;
-        if (!skip) {
-            alpha = sqrt(sv);
-            s.alpha = alpha;
-            s.inv_alpha = alpha > 0.0 ? 1.0 / alpha : 1.0;
-            s.v_fresh = 1;
-        } else {
-            s.v_fresh = 0;
-        }
-        const double beta = s.beta;
-        if (init) {                                      // lsmr.jl:80-113
-            s.zetabar = alpha * beta; s.alphabar = alpha; s.rho = 1.0; s.rhobar = 1.0; s.cbar = 1.0; s.sbar = 0.0;
-            s.betadd = beta; s.betad = 0.0; s.rhodold = 1.0; s.tautildeold = 0.0; s.thetatilde = 0.0; s.zeta = 0.0; s.d = 0.0;
-            s.normA2 = alpha * alpha; s.maxrbar = 0.0; s.minrbar = 1e100;
-            s.normb = beta; s.normr = beta; s.normAr = alpha * beta;
-            s.normA = -1.0; s.condA = -1.0;
-            s.c1 = 0.0; s.c2 = 0.0; s.c3 = 0.0;
-            if (!(s.normAr != 0.0)) s.done = 1;          // lsmr.jl:115: exit if b = 0 or A'b = 0
-            return;
-        }
-        s.iter += 1;
-        const double lambda = 0.0;                       // damping lives in the augmented operator
-        // rotation Qhat_{k,2k+1}
-        const double alphahat = sqrt(sqd(s.alphabar) + sqd(lambda));
-        const double chat = s.alphabar / alphahat, shat = lambda / alphahat;
-        // rotation Q_i turning B_i into R_i
-        const double rhoold = s.rho;
-        const double rho = sqrt(sqd(alphahat) + sqd(beta));
-        const double c = alphahat / rho, sn = beta / rho;
-        const double thetanew = sn * alpha;
-        s.alphabar = c * alpha;
-        // rotation Qbar_i turning R_i' into R_i^bar
-        const double rhobarold = s.rhobar, zetaold = s.zeta;
-        const double thetabar = s.sbar * rho, rhotemp = s.cbar * rho;
-        const double rhobar = sqrt(sqd(s.cbar * rho) + sqd(thetanew));
-        s.cbar = s.cbar * rho / rhobar;
-        s.sbar = thetanew / rhobar;
-        const double zeta = s.cbar * s.zetabar;
-        s.zetabar = -s.sbar * s.zetabar;
-        s.rho = rho; s.rhobar = rhobar; s.zeta = zeta;
-        s.c1 = -thetabar * rho / (rhoold * rhobarold);
-        s.c2 = zeta / (rho * rhobar);
-        s.c3 = -thetanew / rho;
-        // estimate of ‖r‖
-        const double betaacute = chat * s.betadd, betacheck = -shat * s.betadd;
-        const double betahat = c * betaacute;
-        s.betadd = -sn * betaacute;
-        const double thetatildeold = s.thetatilde;
-        const double rhotildeold = sqrt(sqd(s.rhodold) + sqd(thetabar));
-        const double ctildeold = s.rhodold / rhotildeold, stildeold = thetabar / rhotildeold;
-        s.thetatilde = stildeold * rhobar;
-        s.rhodold = ctildeold * rhobar;
-        s.betad = -stildeold * s.betad + ctildeold * betahat;
-        s.tautildeold = (zetaold - thetatildeold * s.tautildeold) / rhotildeold;
-        const double taud = (zeta - s.thetatilde * s.tautildeold) / s.rhodold;
-        s.d = s.d + sqd(betacheck);
-        s.normr = sqrt(s.d + sqd(s.betad - taud) + sqd(s.betadd));
-        // estimate of ‖A‖ and cond(A)
-        s.normA2 = s.normA2 + sqd(beta);
-        s.normA = sqrt(s.normA2);
-        s.normA2 = s.normA2 + sqd(alpha);
-        s.maxrbar = fmax(s.maxrbar, rhobarold);
-        if (s.iter > 1) s.minrbar = fmin(s.minrbar, rhobarold);
-        s.condA = fmax(s.maxrbar, rhotemp) / fmin(s.minrbar, rhotemp);
-        s.normAr = fabs(s.zetabar);
-    }
+    __device__ void finish(double sv, double) const { lsmr_recurrences(*st, sv, skip, init); }
 };
 
 // INIT: v /= α ; h = v ; hbar = 0 ; tmp = P∘v                                   (lsmr.jl:78, 89-90)
@@ -368,6 +374,193 @@ static int lsmr_fused_csc(lso_lsmr_ws* ws, lso_csc* A, const double* d_y, double
     *istop_out = ws->h_tail->istop;
     ctx->stat_spmv_bytes += (double)(2 * ws->h_tail->iter + 1) * (12.0 * (double)A->nnz + 8.0 * (double)(m + n));
     LSO_TRY(lso_vec_mul(ctx, n, d_x, d_x, ws->P));        // ldiv!(tmp, P, x); copyto!(x, tmp)
+    ws->last_launches = ctx->launches - launches0;
+    return LSO_OK;
+}
+
+// =====================================================================================================================
+// row-sharded fused driver: every rank holds a block of rows of J (its own CSC + CSR images), u is
+// sharded like the rows, the n-vectors v, h, h̄, x, P and the damping part of u are replicated.  Per iteration
+//     u_k <- J_k (P∘v) - α u_k                 local rows; partial ‖u_k‖² into the packed buffer            (1 launch)
+//     w_k  = J_k' u_k   (u NOT yet normalised)  partial A'u into the packed buffer                            (1 launch)
+//     ONE ncclAllReduce of [ w (n) | ‖u‖² (1) ]
+//     β = sqrt(Σ‖u_k‖² + ‖u.x‖²) ; v <- P∘(w/β + √D∘u.x/β) - β v ; α = ‖v‖ ; rotations (replicated)         (1 launch)
+//     h̄, x, h updates, ‖x‖², stopping tests (replicated)                                                   (1 launch)
+// so the exchange per iteration is n + 1 doubles and every rank takes the same decisions from the same numbers.
+// =====================================================================================================================
+struct LsmrFwdShard {
+    LsmrState* st;
+    const double* tmp;
+    double* uy;
+    double* ux;
+    const double* diag;
+    long long n_extra;
+    double* packed_tail;        // packed[n]: this rank's ‖u_k‖²
+    double alpha_l, inv_beta_prev;
+    static constexpr bool DUAL = false;
+    __device__ __forceinline__ bool begin() {
+        if (st->done) return false;
+        alpha_l = st->alpha;
+        inv_beta_prev = st->inv_beta;
+        return true;
+    }
+    __device__ __forceinline__ bool idle() const { return false; }
+    __device__ __forceinline__ double gather(int c) const { return __ldg(tmp + c); }
+    __device__ __forceinline__ double epilogue(long long i, double a) const {
+        const double uold = uy[i] * inv_beta_prev;
+        const double unew = fma(-alpha_l, uold, a);
+        uy[i] = unew;
+        return unew * unew;
+    }
+    __device__ __forceinline__ double epilogue2(long long, double, double) const { return 0.0; }
+    __device__ __forceinline__ double extra(long long j) const {
+        const double xold = ux[j] * inv_beta_prev;
+        const double xnew = __dadd_rn(__dmul_rn(-alpha_l, xold), __dmul_rn(tmp[j], diag[j]));
+        ux[j] = xnew;
+        return xnew * xnew;
+    }
+    __device__ __forceinline__ void finish(double sy, double sx) const {
+        *packed_tail = sy;              // summed over the ranks by the all-reduce
+        st->ux_sumsq = sx;              // replicated: counted once
+    }
+};
+
+struct LsmrAdjPart {
+    LsmrState* st;
+    const double* uy;
+    double* packed;             // packed[j] = (J_k' u_k)[j]
+    long long n_extra;
+    static constexpr bool DUAL = false;
+    __device__ __forceinline__ bool begin() { return !st->done; }
+    __device__ __forceinline__ bool idle() const { return false; }
+    __device__ __forceinline__ double gather(int r) const { return __ldg(uy + r); }
+    __device__ __forceinline__ double epilogue(long long j, double a) const { packed[j] = a; return 0.0; }
+    __device__ __forceinline__ double epilogue2(long long, double, double) const { return 0.0; }
+    __device__ __forceinline__ double extra(long long) const { return 0.0; }
+    __device__ __forceinline__ void finish(double, double) const {}
+};
+
+// after the all-reduce: β, the new v and α, then the recurrences in the last CTA to retire
+__global__ void __launch_bounds__(256)
+lsmr_vupd_shard_kernel(LsmrState* st, long long n, const double* __restrict__ packed, const double* __restrict__ ux,
+                       const double* __restrict__ diag, const double* __restrict__ P, double* __restrict__ v, int init,
+                       double* __restrict__ partials, unsigned int* __restrict__ counter) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    if (st->done) return;
+    const double ny = sqrt(packed[n]);
+    const double nx = (ux && !init) ? sqrt(st->ux_sumsq) : 0.0;
+    const double beta = ux ? sqrt(ny * ny + nx * nx) : ny;             // iterative_lsmr.jl:72 / plain norm
+    const double inv_beta = beta > 0.0 ? 1.0 / beta : 1.0;
+    const bool skip = !init && !(beta > 0.0);                          // lsmr.jl:120
+    double acc = 0.0;
+    if (!skip) {
+        for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+            double t = packed[j] * inv_beta;
+            if (ux && !init) t = __dadd_rn(t, __dmul_rn(ux[j] * inv_beta, diag[j]));
+            const double t2 = t * P[j];
+            const double vnew = init ? t2 : fma(-beta, v[j], t2);
+            v[j] = vnew;
+            acc = fma(vnew, vnew, acc);
+        }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = acc;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double sv = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) sv += ((volatile double*)partials)[i];
+    sv = block_sum(sv, red);
+    if (threadIdx.x != 0) return;
+    *counter = 0;
+    st->beta = beta;
+    st->inv_beta = inv_beta;
+    lsmr_recurrences(*st, sv, skip, init);
+}
+
+// st->beta etc. are only written by the v-update kernel; the init kernel of the sharded form just sets the controls
+__global__ void lsmr_init_shard_kernel(LsmrState* st, double atol, double btol, double ctol, long long maxiter) {
+    st->beta = 0.0; st->inv_beta = 1.0;              // u = y is read unscaled by the first forward product
+    st->alpha = 0.0; st->inv_alpha = 1.0;
+    st->atol = atol; st->btol = btol; st->ctol = ctol;
+    st->iter = 0; st->maxiter = maxiter; st->istop = 0; st->done = 0; st->v_fresh = 0; st->ux_sumsq = 0.0;
+}
+
+extern "C" int lso_comm_allreduce_sum(lso_ctx* ctx, double* d_buf, int64_t count);
+
+static int lsmr_fused_csc_sharded(lso_lsmr_ws* ws, lso_csc* A, const double* d_y, double* d_damp, double* d_x,
+                                  const double* d_P_user, double atol, double btol, double conlim, int64_t maxiter,
+                                  int64_t m_total, int64_t* iters_out, int* istop_out) {
+    lso_ctx* ctx = ws->ctx;
+    const int64_t m = ws->m, n = ws->n;
+    const int64_t launches0 = ctx->launches;
+    ws->last_syncs = 0;
+    if (!ws->packed) LSO_CHECK_CUDA(ctx, cudaMalloc(&ws->packed, (size_t)(n + 1) * sizeof(double)));
+    double* packed = ws->packed;
+    LSO_CHECK_CUDA(ctx, cudaMemsetAsync(d_x, 0, n * sizeof(double), ctx->stream));
+    LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(ws->u, d_y, m * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_damp) LSO_CHECK_CUDA(ctx, cudaMemsetAsync(ws->zerosvector, 0, n * sizeof(double), ctx->stream));
+    if (d_P_user) {
+        LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(ws->P, d_P_user, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        LSO_TRY(csc_colsumabs2_cached(A, ws->P));                      // this rank's rows ...
+        LSO_TRY(lso_comm_allreduce_sum(ctx, ws->P, n));                // ... summed: colsumabs2 of the whole J
+        precond_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(n, ws->P, d_damp);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    if (d_damp) LSO_TRY(lso_vec_sqrt(ctx, n, d_damp));
+    LSO_TRY(csc_refresh_csr(A));
+    if (m_total < m) m_total = m;
+    if (maxiter <= 0) maxiter = d_damp ? std::max<int64_t>(m_total + n, n) : std::max<int64_t>(m_total, n);
+    const double ctol = conlim > 0 ? 1.0 / conlim : 0.0;
+    LsmrState* st = ws->d_state;
+    lsmr_init_shard_kernel<<<1, 1, 0, ctx->stream>>>(st, atol, btol, ctol, (long long)maxiter);
+    LSO_CHECK_LAUNCH(ctx);
+    double* ux = d_damp ? ws->zerosvector : nullptr;
+    unsigned int* cnt = ctx->d_counters + SP_COUNTER_SLOT;
+    const int ugrid = (int)std::min<int64_t>(cdiv64(n, 256), (int64_t)ctx->num_sms * 8);
+    LsmrAdjPart fp{st, ws->u, packed, 0};
+    {   // β = ‖y‖ over all ranks, v = A'u / β scaled by P, α, recurrences; then v /= α, h = v, h̄ = 0, tmp = P∘v
+        LSO_TRY(lso_dev_sumabs2(ctx, m, ws->u, packed + n));
+        LSO_TRY(spmv_stream_launch(ctx, A->Gc, fp, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk, A->n));
+        LSO_TRY(lso_comm_allreduce_sum(ctx, packed, n + 1));
+        lsmr_vupd_shard_kernel<<<ugrid, 256, 0, ctx->stream>>>(st, n, packed, ux, d_damp, ws->P, ws->v, 1, ctx->d_partials, cnt);
+        LSO_CHECK_LAUNCH(ctx);
+        lsmr_upd_kernel<true><<<ugrid, 256, 0, ctx->stream>>>(st, n, ws->v, ws->h, ws->hbar, d_x, ws->P, ws->tmp, ctx->d_partials, cnt);
+        LSO_CHECK_LAUNCH(ctx);
+    }
+    LsmrFwdShard ff{st, ws->tmp, ws->u, ux, d_damp, d_damp ? n : 0, packed + n, 0.0, 1.0};
+    int64_t enq = 0;
+    int batch = 1;
+    for (;;) {
+        for (int b = 0; b < batch && enq < maxiter; ++b, ++enq) {
+            lso_prof_mark(ctx);
+            LSO_TRY(spmv_stream_launch(ctx, A->Gr, ff, A->d_rowptr, A->d_colidx, A->d_valr, A->d_rblk, A->nrblk, A->m));
+            LSO_TRY(spmv_stream_launch(ctx, A->Gc, fp, A->d_colptr, A->d_rowidx, A->d_val, A->d_cblk, A->ncblk, A->n));
+            lso_prof_mark(ctx);
+            LSO_TRY(lso_comm_allreduce_sum(ctx, packed, n + 1));
+            lsmr_vupd_shard_kernel<<<ugrid, 256, 0, ctx->stream>>>(st, n, packed, ux, d_damp, ws->P, ws->v, 0, ctx->d_partials, cnt);
+            LSO_CHECK_LAUNCH(ctx);
+            lsmr_upd_kernel<false><<<ugrid, 256, 0, ctx->stream>>>(st, n, ws->v, ws->h, ws->hbar, d_x, ws->P, ws->tmp, ctx->d_partials, cnt);
+            LSO_CHECK_LAUNCH(ctx);
+        }
+        lsmr_tail_kernel<<<1, 1, 0, ctx->stream>>>(st, (LsmrTail*)(ctx->d_scalars + 32));
+        LSO_CHECK_LAUNCH(ctx);
+        LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(ws->h_tail, ctx->d_scalars + 32, sizeof(LsmrTail), cudaMemcpyDeviceToHost, ctx->stream));
+        LSO_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ws->last_syncs++;
+        if (ws->h_tail->done || enq >= maxiter) break;
+        if (enq >= 2 && batch < 8) batch *= 2;
+    }
+    *iters_out = ws->h_tail->iter;
+    *istop_out = ws->h_tail->istop;
+    ctx->stat_spmv_bytes += (double)(2 * ws->h_tail->iter + 1) * (12.0 * (double)A->nnz + 8.0 * (double)(m + n));
+    LSO_TRY(lso_vec_mul(ctx, n, d_x, d_x, ws->P));
     ws->last_launches = ctx->launches - launches0;
     return LSO_OK;
 }
@@ -587,7 +780,7 @@ int lso_lsmr_ws_destroy(lso_lsmr_ws* ws) {
     cudaSetDevice(ws->ctx->device);
     cudaStreamSynchronize(ws->ctx->stream);
     cudaFree(ws->P); cudaFree(ws->tmp); cudaFree(ws->tmp2); cudaFree(ws->v); cudaFree(ws->h); cudaFree(ws->hbar);
-    cudaFree(ws->zerosvector); cudaFree(ws->u); cudaFree(ws->d_state);
+    cudaFree(ws->zerosvector); cudaFree(ws->u); cudaFree(ws->d_state); cudaFree(ws->packed);
     if (ws->h_tail) cudaFreeHost(ws->h_tail);
     delete ws;
     return LSO_OK;
@@ -638,6 +831,24 @@ int lso_lsmr_solve(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_J, int64_t l
                    int* istop_out) {
     return lso_lsmr_solve_ex(ws, A_csc, d_J, ld, d_y, d_damp, d_x, atol, btol, conlim, maxiter, nullptr, nullptr, nullptr,
                              iters_out, istop_out);
+}
+
+// Row-sharded LSMR (one process per GPU, NCCL): A_csc / d_y are THIS rank's rows of J and y, d_damp / d_x / d_P_diag are
+// replicated; m_total (rows of the whole J, for the default maxiter of lsmr.jl:57) may be 0 = unknown.  Falls back to
+// lso_lsmr_solve_ex on a context without a communicator.
+int lso_lsmr_solve_sharded(lso_lsmr_ws* ws, lso_csc* A_csc, const double* d_y, double* d_damp, double* d_x, double atol,
+                           double btol, double conlim, int64_t maxiter, int64_t m_total, const double* d_P_diag,
+                           int64_t* iters_out, int* istop_out) {
+    if (!ws) return lso_set_error(nullptr, LSO_ERR_ARG, "ws is NULL");
+    lso_ctx* ctx = ws->ctx;
+    if (ctx->nranks <= 1)
+        return lso_lsmr_solve_ex(ws, A_csc, nullptr, 0, d_y, d_damp, d_x, atol, btol, conlim, maxiter, d_P_diag, nullptr, nullptr,
+                                 iters_out, istop_out);
+    LSO_REQUIRE(ctx, A_csc && d_y && d_x && iters_out && istop_out, "NULL pointer (the sharded LSMR needs a CSC operator)");
+    LSO_REQUIRE(ctx, A_csc->m == ws->m && A_csc->n == ws->n, "operator / workspace dimension mismatch");
+    LSO_REQUIRE(ctx, ctx->opt_spmv >= 1, "the sharded LSMR runs on the fused sparse products (ctx option spmv >= 1)");
+    LSO_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lsmr_fused_csc_sharded(ws, A_csc, d_y, d_damp, d_x, d_P_diag, atol, btol, conlim, maxiter, m_total, iters_out, istop_out);
 }
 
 int lso_lsmr_ws_stats(lso_lsmr_ws* ws, int64_t* launches_out, int64_t* syncs_out) {

@@ -164,8 +164,11 @@ class _LSMRWorkspace:
       callable(x, J, damp) -> DeviceVector     `preconditioner!` producing the vector of an InverseDiagonal each solve
       (callable(x, J, damp), apply(out_ptr, in_ptr, n))   a general P: `apply` is `ldiv!(out, P, in)` on device pointers"""
 
-    def __init__(self, ctx: Context, m: int, n: int, damped: bool, preconditioner=None):
+    def __init__(self, ctx: Context, m: int, n: int, damped: bool, preconditioner=None, sharded: bool = False,
+                 m_total: int = 0):
         self.ctx, self.m, self.n, self.damped = ctx, m, n, damped
+        # sharded: J / y are this rank's rows (CSC), everything of length n is replicated (lso_lsmr_solve_sharded)
+        self.sharded, self.m_total = bool(sharded), int(m_total)
         self._h = C.c_void_p()
         check(lib().lso_lsmr_ws_create(ctx.handle, m, n, int(damped), C.byref(self._h)), ctx.handle)
         self._fin = weakref.finalize(self, lib().lso_lsmr_ws_destroy, self._h)
@@ -201,6 +204,14 @@ class _LSMRWorkspace:
             else:
                 keep = self.preconditioner(x, J, damp)   # keep the vector alive until the solve has been enqueued and read back
                 pdiag = keep.ptr
+        if self.sharded:
+            if csc is None or pfn is not None:
+                raise ValueError("the row-sharded LSMR needs a CSCMatrix and a diagonal (or the default) preconditioner")
+            check(lib().lso_lsmr_solve_sharded(self._h, csc, y.ptr, damp.ptr if damp is not None else None, x.ptr,
+                                               atol, btol, conlim, maxiter, self.m_total, pdiag, C.byref(iters),
+                                               C.byref(istop)), self.ctx.handle)
+            self.last_iters, self.last_istop = iters.value, istop.value
+            return x, 2 * iters.value
         check(lib().lso_lsmr_solve_ex(self._h, csc, dj, ld, y.ptr, damp.ptr if damp is not None else None, x.ptr,
                                       atol, btol, conlim, maxiter, pdiag, pfn, None, C.byref(iters), C.byref(istop)),
               self.ctx.handle)
@@ -211,8 +222,8 @@ class _LSMRWorkspace:
 class LSMRAllocatedSolver(_LSMRWorkspace):
     """iterative_lsmr.jl:161-198 — undamped, lsmr! defaults atol = btol = 1e-6, conlim = 1e8 (lsmr.jl:53-55)."""
 
-    def __init__(self, ctx, m, n, preconditioner=None):
-        super().__init__(ctx, m, n, False, preconditioner)
+    def __init__(self, ctx, m, n, preconditioner=None, sharded=False, m_total=0):
+        super().__init__(ctx, m, n, False, preconditioner, sharded, m_total)
 
     def ldiv(self, x, J, y, damp=None, same_J=False):
         assert damp is None
@@ -222,8 +233,8 @@ class LSMRAllocatedSolver(_LSMRWorkspace):
 class LSMRDampenedAllocatedSolver(_LSMRWorkspace):
     """iterative_lsmr.jl:221-259 — damped, btol = 0.5 (:255); `damp` is overwritten by sqrt(damp) (:252)."""
 
-    def __init__(self, ctx, m, n, preconditioner=None):
-        super().__init__(ctx, m, n, True, preconditioner)
+    def __init__(self, ctx, m, n, preconditioner=None, sharded=False, m_total=0):
+        super().__init__(ctx, m, n, True, preconditioner, sharded, m_total)
 
     def ldiv(self, x, J, y, damp, same_J=False):
         return self._solve(x, J, y, damp, 1e-6, 0.5, 1e8, 0)

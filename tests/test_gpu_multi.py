@@ -1,5 +1,6 @@
-"""Multi-GPU (one process per GPU, NCCL through the C ABI): row-sharded QR (TSQR) and Cholesky (one all-reduce of
-[J'J | J'y]) solves, and a sharded LM run, against the single-process oracle.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+"""Multi-GPU (one process per GPU, NCCL through the C ABI): row-sharded QR (TSQR), Cholesky (one all-reduce of
+[J'J | J'y]) and LSMR (one all-reduce of [J'u | ||u||²] per iteration) solves, and sharded LM / Dogleg runs, against the
+single-process oracle.  Needs >= 2 GPUs (gpurun --gpus 2)."""
 import os
 import sys
 
@@ -75,6 +76,59 @@ def _worker(rank, world, port, out):
     r = L.optimize_(L.allocate(nls, L.Dogleg(L.QR()), sharded=True))
     res["dogleg_qr"] = (r.iterations, rod.iterations, float(np.linalg.norm(r.minimizer.download() - rod.minimizer) /
                                                             np.linalg.norm(rod.minimizer)), r.converged)
+    # ---- row-sharded LSMR on a sparse J: one all-reduce of [J'u | ||u||²] per iteration ----
+    import scipy.sparse as sp
+    m, n = 30011, 900
+    Asp = sp.random(m, n, density=0.01, random_state=17, format="csr")
+    Asp.data = Asp.data * 2 - 1
+    yh = np.random.default_rng(8).standard_normal(m)
+    row0, rows = row_partition(m, world)[rank]
+    Ak = Asp[row0:row0 + rows].tocsc()
+    Ak.sort_indices()
+    Jk, yk = L.CSCMatrix.from_scipy(ctx, Ak), L.DeviceVector(ctx, rows, yh[row0:row0 + rows])
+    for damped in (True, False):
+        damp = np.asarray(Asp.multiply(Asp).sum(axis=0)).ravel() / 10 + 1e-3
+        xr, nmul_r, it_r, istop_r = O.lsmr_ldiv(Asp.tocsc(), yh, damp.copy() if damped else None)
+        ws = (L.LSMRDampenedAllocatedSolver if damped else L.LSMRAllocatedSolver)(ctx, rows, n, sharded=True, m_total=m)
+        x = L.DeviceVector(ctx, n)
+        if damped:
+            _, nmul = ws.ldiv(x, Jk, yk, L.DeviceVector(ctx, n, damp))
+        else:
+            _, nmul = ws.ldiv(x, Jk, yk)
+        res["lsmr_damped" if damped else "lsmr"] = (ws.last_iters, it_r, ws.last_istop, istop_r, nmul, nmul_r,
+                                                    float(np.linalg.norm(x.download() - xr) / np.linalg.norm(xr)), ws.stats())
+    # ---- sharded LM(LSMR) from host callbacks on this rank's rows: r_i(x) = (A x)_i + c (A x)_i² - b_i ----
+    xs = np.random.default_rng(9).standard_normal(n)
+    t_star = Asp @ xs
+    bh = t_star + 0.05 * t_star ** 2
+    Ak_csr = Asp[row0:row0 + rows].tocsr()
+    bk = bh[row0:row0 + rows]
+
+    def f_loc(out_, xx):
+        t = Ak_csr @ xx
+        out_[:] = t + 0.05 * t * t - bk
+
+    def g_loc(JJ, xx):
+        t = Ak_csr @ xx
+        JJ.data[:] = sp.diags(1 + 0.1 * t).dot(Ak_csr).tocsc().data
+
+    def f_all(out_, xx):
+        t = Asp @ xx
+        out_[:] = t + 0.05 * t * t - bh
+
+    def g_all(JJ, xx):
+        t = Asp @ xx
+        JJ.data[:] = sp.diags(1 + 0.1 * t).dot(Asp).tocsc().data
+
+    x0 = xs + 0.1 * np.random.default_rng(10).standard_normal(n)
+    Jall = Asp.tocsc().copy(); Jall.sort_indices()
+    ro = O.levenberg_marquardt(f_all, g_all, x0.copy(), Jall, m, solver="lsmr")
+    Jloc = Ak.copy()
+    nls = L.LeastSquaresProblem(x=x0.copy(), y=np.zeros(rows), f_=f_loc, g_=g_loc, J=Jloc, ctx=ctx)
+    r = L.optimize_(L.allocate(nls, L.LevenbergMarquardt(L.LSMR()), sharded=True))
+    xm = r.minimizer.download() if hasattr(r.minimizer, "download") else np.asarray(r.minimizer)
+    res["lm_lsmr"] = (r.iterations, ro.iterations, float(np.linalg.norm(xm - ro.minimizer) / np.linalg.norm(ro.minimizer)),
+                      r.converged)
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
@@ -94,3 +148,9 @@ def test_sharded_solves_and_lm(world):
         for k in ("lm_qr", "lm_chol", "dogleg_qr"):
             it, it_ref, err, conv = res[k]
             assert conv and it == it_ref and err <= 1e-9, (k, res[k])
+        for k in ("lsmr_damped", "lsmr"):
+            it, it_r, istop, istop_r, nmul, nmul_r, err, (launches, syncs) = res[k]
+            assert (it, istop, nmul) == (it_r, istop_r, nmul_r) and err <= 2e-5, (k, res[k])
+            assert syncs <= max(it, 1) + 1
+        it, it_ref, err, conv = res["lm_lsmr"]
+        assert conv and it == it_ref and err <= 1e-6, res["lm_lsmr"]

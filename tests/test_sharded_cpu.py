@@ -91,3 +91,73 @@ def test_world2_gloo_tsqr_and_allreduce():
         e_tsqr, e_chol, rows = out[rank]
         assert e_tsqr <= 1e-12 and e_chol <= 1e-11
     assert sum(out[r][2] for r in range(world)) == 1003
+
+
+def _lsmr_worker(rank, world, port, out):
+    """Row-sharded LSMR (lso_lsmr_solve_sharded's algebra) on the oracle's own recurrences: u is sharded like the rows, the
+    n-vectors are replicated, J'u and ||u||² are summed over the ranks; the damping part of u is replicated and counted once."""
+    sys.path.insert(0, ROOT)
+    import math
+    import torch
+    import scipy.sparse as sp
+    from lsob200.sharding import row_partition
+    from oracle import reference_port as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, n = 2003, 150
+    J = sp.random(m, n, density=0.03, random_state=11, format="csr")
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(m)
+    res = {}
+    for damped in (True, False):
+        damp = np.asarray(J.multiply(J).sum(axis=0)).ravel() / 10 + 1e-3
+        x_ref, _, it_ref, istop_ref = O.lsmr_ldiv(J.tocsc(), y, damp.copy() if damped else None)
+        row0, rows = row_partition(m, world)[rank]
+        Jk, yk = J[row0:row0 + rows], y[row0:row0 + rows]
+
+        def allsum(a):
+            t = torch.from_numpy(np.atleast_1d(np.asarray(a, dtype=np.float64)).copy())
+            dist.all_reduce(t)
+            return t.numpy()
+
+        class Shard(O._Precond):                       # vectors: [y_k (this rank's rows) ; x (replicated)]
+            def mul_t(self, b, a, alpha, beta):
+                tmp = allsum(self.J.T @ a[:self.m])     # the ONE exchange of an iteration (n doubles) ...
+                if self.diag is not None:
+                    tmp = tmp + 1.0 * a[self.m:] * self.diag
+                tmp2 = tmp * self.P
+                if beta != 1:
+                    b *= beta
+                b += alpha * tmp2
+                return b
+
+            def norm(self, b):                          # ... with ||u_k||² riding along
+                sy = float(allsum(np.dot(b[:self.m], b[:self.m]))[0])
+                sx = float(np.dot(b[self.m:], b[self.m:])) if self.diag is not None else 0.0
+                return math.sqrt(sy + sx)
+
+        P = allsum(np.asarray(Jk.multiply(Jk).sum(axis=0)).ravel())
+        if damped:
+            P = P + damp
+        P = np.where(P > 0, 1.0 / np.sqrt(np.where(P > 0, P, 1.0)), 0.0)
+        A = Shard(Jk, P, np.sqrt(damp) if damped else None)
+        b = np.concatenate([yk, np.zeros(n)]) if damped else yk.copy()
+        x, it, istop = O.lsmr(np.zeros(n), A, b, btol=0.5 if damped else 1e-6, maxiter=max(m + (n if damped else 0), n))
+        x = x * P
+        res[damped] = (it, it_ref, istop, istop_ref, float(np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref)))
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_row_sharded_lsmr():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_lsmr_worker, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        for damped in (True, False):
+            it, it_ref, istop, istop_ref, err = out[rank][damped]
+            assert (it, istop) == (it_ref, istop_ref) and err <= 1e-10, (rank, damped, out[rank][damped])
