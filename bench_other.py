@@ -32,7 +32,7 @@ def _hbm_peak():
 def run_all(env, only, dmma_peak):
     out = {}
     want = (lambda k: (not only) or k in only)
-    if env.world == 1 and want("c3"):
+    if want("c3"):
         out["c3"] = _guard(run_c3, env)
     if want("c4"):
         out["c4"] = _guard(run_c4, env, dmma_peak)
@@ -65,25 +65,45 @@ def _guard(fn, *a):
 # c3: sparse LM(LSMR)
 # ---------------------------------------------------------------------------------------------------------------
 def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
+    """N = 1: the config as BASELINE.json names it.  N > 1 (beyond the north star's single-GPU LSMR): the
+    ROWS of the same pattern are sharded over the ranks (strong scaling) and LSMR exchanges [J'u | ||u||²] once per
+    iteration (lso_lsmr_solve_sharded)."""
     from lsob200._lib import check, lib
     L, ctx = env.L, env.ctx
+    world, rank = env.world, env.rank
     h = ctx.handle
     nnz = n * k
+    m_glob, nnz_glob = m, nnz
     colptr = np.zeros(n + 1, dtype=np.int64)
     rowval = np.zeros(nnz, dtype=np.int64)
     check(lib().lso_synth_csc_pattern(m, n, k, 20240609, colptr.ctypes.data, rowval.ctypes.data))
     colptr -= 1
     rowval -= 1
-    A0 = L.CSCMatrix(ctx, m, n, colptr, rowval)          # A  (f! needs t = A x)
-    Jac = L.CSCMatrix(ctx, m, n, colptr, rowval)         # J = diag(1 + 2 c t) A
-    aval, aval_r = L.DeviceVector(ctx, nnz), L.DeviceVector(ctx, nnz)
-    check(lib().lso_synth_vector(h, nnz, 0, 99, 1.0, aval.ptr), h)
+    if world > 1:
+        row0, row1 = (m * rank) // world, (m * (rank + 1)) // world
+        mask = (rowval >= row0) & (rowval < row1)
+        cs = np.zeros(nnz + 1, dtype=np.int64)
+        np.cumsum(mask, out=cs[1:])
+        colptr = cs[colptr]
+        rowval = rowval[mask] - row0
+        del mask, cs
+        m, nnz = row1 - row0, int(rowval.size)
+    err = None
+    try:
+        A0 = L.CSCMatrix(ctx, m, n, colptr, rowval)          # A  (f! needs t = A x)
+        Jac = L.CSCMatrix(ctx, m, n, colptr, rowval)         # J = diag(1 + 2 c t) A
+        aval, aval_r = L.DeviceVector(ctx, nnz), L.DeviceVector(ctx, nnz)
+    except Exception as e:
+        err = f"{type(e).__name__}: {e}"
+    if not _all_ok(env, err is None):
+        return {"error": err or "another rank failed to allocate"}
+    check(lib().lso_synth_vector(h, nnz, 0, 99 + rank, 1.0, aval.ptr), h)
     check(lib().lso_csc_set_values_dev(A0.handle, aval.ptr), h)
     A0.gather_csr(aval, aval_r)
     xs, x, pert = (L.DeviceVector(ctx, n) for _ in range(3))
     t, b, noise = (L.DeviceVector(ctx, m) for _ in range(3))
     check(lib().lso_synth_vector(h, n, 0, 7, 1.0, xs.ptr), h)
-    check(lib().lso_synth_vector(h, m, 0, 12, NOISE, noise.ptr), h)
+    check(lib().lso_synth_vector(h, m, 0, 12 + 1000 * rank, NOISE, noise.ptr), h)
     check(lib().lso_synth_vector(h, n, 0, 13, 0.1, pert.ptr), h)
     zero = L.DeviceVector(ctx, m)
     A0.mul(t, xs, 1.0, 0.0)
@@ -102,7 +122,7 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
         check(lib().lso_synth_csc_jacobian_both(JJ.handle, aval.ptr, aval_r.ptr, t.ptr, C_MODEL), h)
 
     nls = L.LeastSquaresProblem(x=x, y=L.DeviceVector(ctx, m), f_=f_, g_=g_, J=Jac, device_callbacks=True, ctx=ctx)
-    anls = L.allocate(nls, L.LevenbergMarquardt(L.LSMR()))
+    anls = L.allocate(nls, L.LevenbergMarquardt(L.LSMR()), sharded=(world > 1))
     st = {"run": None, "iters": [], "acc": 0}
 
     def one_step():
@@ -127,10 +147,16 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
 
     def fixed_iters():
         Jac.colsumabs2(dtd)
+        if world > 1:
+            ctx.allreduce(dtd)
         check(lib().lso_lm_damping(h, n, dtd.ptr, 1e-6, 1e32, 0.1), h)
         it, istop = C.c_int64(), C.c_int()
-        check(lib().lso_lsmr_solve(ws._h, Jac.handle, None, 0, fcur.ptr, dtd.ptr, dx.ptr, 0.0, 0.0, 0.0, NIT,
-                                   C.byref(it), C.byref(istop)), h)
+        if world > 1:
+            check(lib().lso_lsmr_solve_sharded(ws._h, Jac.handle, fcur.ptr, dtd.ptr, dx.ptr, 0.0, 0.0, 0.0, NIT, m_glob, None,
+                                               C.byref(it), C.byref(istop)), h)
+        else:
+            check(lib().lso_lsmr_solve(ws._h, Jac.handle, None, 0, fcur.ptr, dtd.ptr, dx.ptr, 0.0, 0.0, 0.0, NIT,
+                                       C.byref(it), C.byref(istop)), h)
         assert it.value == NIT, (it.value, istop.value)
 
     fixed_iters()
@@ -145,10 +171,16 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
     peak, peak_src = _hbm_peak()
     achieved = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
     ms_per_it = ms_fix / 3 / NIT
+    if rank != 0:
+        return None
     res = {
-        "workload": f"sparse CSC J {m}x{n}, {k} entries per column (~{nnz // m} per row, nnz {nnz:.0e}) fp64, "
+        "workload": f"sparse CSC J {m_glob}x{n}, {k} entries per column (~{nnz_glob // m_glob} per row, nnz {nnz_glob:.0e}) fp64, "
                     "LevenbergMarquardt(LSMR())",
-        "baseline_config": "BASELINE.json configs[2]", "n_gpus": 1,
+        "baseline_config": "BASELINE.json configs[2]" + ("" if world == 1 else " with the rows sharded over the ranks (SURVEY §8 f4; "
+                                                                              "the north star keeps LSMR on one GPU)"),
+        "n_gpus": world, "scaling": "strong", "rows_per_gpu": m,
+        "collective": ({"what": "ONE ncclAllReduce of [J'u | ||u||²] per LSMR iteration (+ colsumabs2 once per solve)",
+                        "doubles": n + 1, "bytes": 8 * (n + 1)} if world > 1 else None),
         "metric": "trust-region steps/sec (fp64)", "value": steps / (ms * 1e-3), "unit": "steps/s",
         "ms_per_step": ms / steps, "wall_ms_per_step": wall / steps, "steps": steps, "warmup": warmup,
         "steps_accepted": st["acc"], "lsmr_iterations_per_step": st["iters"], "gpu_launches": launches,
@@ -164,10 +196,13 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
                      "binding_resource": "L2 sector bandwidth / L1TEX wavefronts of the random gathers: one 32-byte sector per "
                                          "gathered double (ncu: 1.75e8 sectors = 5.6 GB through L2 per product, ~11.7 TB/s vs the "
                                          "~12.4 TB/s LTS cap), not HBM — profiles/r2_ncu_spmv_warp.txt",
-                     "traffic": 1.38e9},
+                     "traffic": 1.38e9 if world == 1 else None},
         "last_ssr": st["run"].ssr,
     }
     # cpu baseline: the reference's serial CSC products (SparseArrays mul! is single-threaded), two LSMR iterations' worth
+    if world > 1:
+        res["cpu_baseline"] = {"note": "timed at N = 1 (same pattern): see that line"}
+        return res
     try:
         import scipy.sparse as sp
         vals = Jac_values_host(L, ctx, Jac, nnz)
