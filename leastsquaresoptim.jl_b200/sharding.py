@@ -7,6 +7,7 @@ the multi-GPU tests and the CPU (gloo) tests.
   * `stack_layout(n, world)`             the row-interleaved stack of the R_k factors and the sqrt(D) triangle that
                                          `lso_qr_solve_sharded` factorises on every rank
   * `packed_upper_layout(n)`             the packed [upper(J'J) | J'y] buffer of the sharded Cholesky path's all-reduce
+  * `lsmr_packed_layout(n)`              the [J'u | ||u||²] buffer the row-sharded LSMR all-reduces once per iteration
 """
 from __future__ import annotations
 
@@ -35,6 +36,12 @@ def packed_upper_layout(n: int):
     """The buffer of the ONE all-reduce of the row-sharded Cholesky path (`chol_pack_kernel`, csrc/chol.cu):
     [upper(J'J) by columns | J'y]: entry (i, j), i <= j, at j*(j+1)//2 + i; J'y at n*(n+1)//2 + i; n(n+1)/2 + n doubles."""
     return {"len": n * (n + 1) // 2 + n, "index": (lambda i, j: j * (j + 1) // 2 + i), "rhs0": n * (n + 1) // 2}
+
+
+def lsmr_packed_layout(n: int):
+    """The buffer of the ONE all-reduce per iteration of `lso_lsmr_solve_sharded` (csrc/lsmr.cu): this rank's J_k'u_k (u not yet
+    normalised) in [0, n) and its ||u_k||² at n; the damping part of u is replicated and is added AFTER the sum, once."""
+    return {"len": n + 1, "adjoint0": 0, "sumsq": n}
 
 
 def init_comm(ctx, dist=None):

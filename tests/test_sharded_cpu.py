@@ -70,7 +70,8 @@ def _worker(rank, world, port, out):
 
 def test_row_partition():
     sys.path.insert(0, ROOT)
-    from lsob200.sharding import row_partition
+    from lsob200.sharding import lsmr_packed_layout, row_partition
+    assert lsmr_packed_layout(500000) == {"len": 500001, "adjoint0": 0, "sumsq": 500000}
     for m, w in [(100000, 8), (1003, 2), (7, 7), (2_000_000, 8)]:
         parts = row_partition(m, w)
         assert parts[0][0] == 0 and sum(r for _, r in parts) == m
