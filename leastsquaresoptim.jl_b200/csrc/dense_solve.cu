@@ -703,8 +703,8 @@ int lso_qr_factor_keep_host_chunks(lso_dense_ws* ws, int P, const int64_t* chunk
     for (int k = 0; k < P; ++k) {            // chunks cross PCIe in the order given
         const int64_t rows = chunk_rows[k];
         LSO_CHECK_CUDA(ctx, cudaMemcpy2DAsync(d_J + r0, ld_d * sizeof(double), h_J + r0, ld_h * sizeof(double), rows * sizeof(double),
-                                              n, cudaMemcpyHostToDevice, ctx->copy_stream));
-        LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_y + r0, h_y + r0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+                                              n, cudaMemcpyDefault, ctx->copy_stream));
+        LSO_CHECK_CUDA(ctx, cudaMemcpyAsync(d_y + r0, h_y + r0, rows * sizeof(double), cudaMemcpyDefault, ctx->copy_stream));
         LSO_CHECK_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1 + k], ctx->copy_stream));
         r0 += rows;
     }
