@@ -69,6 +69,8 @@ void*       lso_ctx_stream(lso_ctx* ctx);          /* cudaStream_t, for CUDA-eve
  *                  2 tcgen05 syrk always: int8 digit matrices (Ozaki scheme) multiplied by
  *                  tcgen05.mma.kind::i8 into TMEM, operands fed by TMA, fp64 reconstructed exactly
  *   "ozaki_slices" 7-bit digits per value for "syrk" = 2 (2..8, default 8: representation error 2^-57)
+ *   "trisolve"     1 (default) = the triangular solves behind every dense solve run on n/32 CTAs (diagonal blocks chained
+ *                  through an L2 mailbox), 0 = the single-CTA left-looking kernel
  *   "spmv"         0 first-generation sparse products, 1 stream kernels (shared-memory staging), 2 warp kernels (default)
  *   "lsmr_fused"   0 LSMR with host-side scalars (3 syncs per iteration), 1 fused device-resident LSMR (default)
  *   "profile"      see lso_ctx_profile_read */

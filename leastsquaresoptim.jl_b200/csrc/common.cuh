@@ -45,6 +45,9 @@ struct lso_ctx {
                                        // all-gather per panel), 0 = local QR, one all-gather, stack QR
     int64_t opt_qr_twin = 2;           // host-fed chunked factorisation: extra workspaces / streams the chunks rotate through
     int64_t opt_qr_lookahead = 0;      // 1 = panel trees on a second stream under the previous update (+2% at C2)
+    int64_t opt_trisolve = 1;          // 1 = multi-CTA triangular solves (mailbox-chained diagonal blocks), 0 = one CTA
+    void* d_trimail = nullptr;         // mailbox of the multi-CTA triangular solve: 24 032 x {lo32, tag, hi32, tag}
+    unsigned tri_tag = 0, tri_ticket_base = 0;
     int64_t opt_spmv = 2;              // 0 = first-generation sparse products, 1 = stream kernels (shared-memory staging),
                                        // 2 = warp kernels (registers + shuffles, persistent grid; default)
     int64_t opt_lsmr_fused = 1;        // 0 = LSMR scalars on the host, 1 = fused device-resident LSMR (sparse operator)

@@ -68,6 +68,7 @@ int lso_ctx_destroy(lso_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_trimail);
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_finish);
     cudaFree(ctx->d_gemv);
@@ -103,6 +104,7 @@ int lso_ctx_set_option(lso_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "qr_twin")) ctx->opt_qr_twin = value;
     else if (!strcmp(key, "qr_shard_pipeline")) ctx->opt_qr_shard_pipeline = value;
     else if (!strcmp(key, "spmv")) ctx->opt_spmv = value;
+    else if (!strcmp(key, "trisolve")) ctx->opt_trisolve = value;
     else if (!strcmp(key, "ozaki_slices")) { if (value < 2 || value > 8) return lso_set_error(ctx, LSO_ERR_ARG, "ozaki_slices must be 2..8"); ctx->opt_ozaki_slices = value; }
     else if (!strcmp(key, "lsmr_fused")) ctx->opt_lsmr_fused = value;
     else if (!strcmp(key, "profile")) { ctx->opt_profile = value; ctx->prof_used = 0; ctx->prof2_used = 0; }

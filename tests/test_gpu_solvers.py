@@ -647,3 +647,30 @@ def test_host_chunks_pipelined_stack_is_bit_identical_and_keeps_its_factor(ctx, 
     xr2, _ = O.qr_ldiv(Jh, fh, dtd / 3.0)
     xr3, _ = O.qr_ldiv(Jh, fh, dtd * 2.0)
     assert rel(got[1][1], xr2) <= 1e-10 and rel(got[1][2], xr3) <= 1e-10 and rel(got[0][2], xr3) <= 1e-10
+
+
+@pytest.mark.parametrize("m,n", [(200, 33), (700, 100), (5000, 1000), (6000, 2500), (4100, 4097)])
+def test_multi_cta_triangular_solves_match_the_single_cta_kernel(ctx, m, n):
+    """R x = c (QR finish, Cholesky) and R'z = c (Cholesky) on n/32 CTAs chained through the mailbox ("trisolve" = 1, default)
+    against the single-CTA kernel and the oracle; sizes that are not multiples of 32 included."""
+    import lsob200 as L
+    rng = np.random.default_rng(n)
+    Jh = np.asfortranarray(rng.standard_normal((m, n)) * np.exp2(rng.integers(-3, 4, n)))
+    yh = rng.standard_normal(m)
+    damp = np.einsum("ij,ij->j", Jh, Jh) / 7
+    xr, _ = O.qr_ldiv(Jh, yh, damp.copy())
+    J, y, d = L.DenseMatrix(ctx, m, n, Jh), L.DeviceVector(ctx, m, yh), L.DeviceVector(ctx, n, damp)
+    got = {}
+    try:
+        for opt in (1, 0):
+            ctx.set_option("trisolve", opt)
+            xq, xc = L.DeviceVector(ctx, n), L.DeviceVector(ctx, n)
+            L.DenseQRAllocatedSolver(ctx, m, n, damped=True).ldiv(xq, J, y, d)
+            L.DenseCholeskyAllocatedSolver(ctx, m, n, damped=True).ldiv(xc, J, y, d)
+            for _ in range(3):                                   # repeated launches: tags and tickets advance
+                L.DenseCholeskyAllocatedSolver(ctx, m, n, damped=True).ldiv(xc, J, y, d)
+            got[opt] = (xq.download(), xc.download())
+    finally:
+        ctx.set_option("trisolve", 1)
+    assert rel(got[1][0], xr) <= 1e-10 and rel(got[1][1], xr) <= 1e-9
+    assert rel(got[1][0], got[0][0]) <= 1e-12 and rel(got[1][1], got[0][1]) <= 1e-11
