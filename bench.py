@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-resolve", action="store_true", help="skip the rejected-step re-solve measurement (ncu launch-list passes)")
     ap.add_argument("--only", default="", help="comma list of other configs to run (c3,c4,c5); default: all that apply")
     return ap.parse_args()
 
@@ -314,7 +315,7 @@ def main():
 
     # ---- (f3) what a REJECTED step's solve costs: same J and f, larger damping (levenberg_marquardt.jl:77-87,135) ----
     resolve = None
-    if world == 1:
+    if world == 1 and not args.no_resolve:
         resolve = measure_resolve(env, prob, anls, n)
 
     # ---- e2e: hot-path body from HOST buffers (J + f uploaded each step, δ + scalars downloaded) ----

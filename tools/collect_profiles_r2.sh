@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference.
 OMP_NUM_THREADS=1 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference_omp1env.json 2>> $O/${T}_bench_n1.err
 # launch list of the headline bench command (per-launch times are cold-cache and serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_bench.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-other-configs > /dev/null 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-other-configs --no-resolve > /dev/null 2>&1
 python tools/launch_summary.py $O/${T}_launches_bench.csv > $O/${T}_launches_bench_lm_qr_c2.txt 2>&1
 # full captures: panel-0 tree kernel + the trailing-update launches of panel 0
 ncu --set full --import-source on --clock-control none -k regex:"qr_tree|qr_apply_pp" -c 5 -o $O/${T}_tree_pp -f \
