@@ -118,7 +118,10 @@ oz_colexp_kernel(long long m, long long n, const double* __restrict__ J, long lo
     }
 }
 
-// each thread converts 16 consecutive rows of one column: one 128-byte read, one 16-byte write per digit matrix.
+// each thread converts 16 consecutive rows of one column (one 16-byte write per digit matrix).  The rows come in through
+// shared memory: a warp reads its 512 rows of the column with 8 fully coalesced 16-byte loads per lane (4 cache lines per
+// instruction; reading 128 contiguous bytes per LANE costs 32 L1 tag look-ups per instruction and made the kernel
+// L1-bound at 3.6 TB/s), parks them with one pad double per 16 and every lane picks up its 16 rows.
 // Digit extraction without conversion instructions: adding 1.5 * 2^52 rounds x (|x| <= 64) to the nearest integer (ties to
 // even, like rint) and leaves that integer in two's complement in the low mantissa bits, so the digit byte is the low
 // byte of the sum and the rounded value is recovered by subtracting the constant again — 4 fp64 adds / multiplies per digit.
@@ -126,28 +129,36 @@ template <int S>
 __global__ void __launch_bounds__(256)
 oz_split_kernel(long long m, long long n, long long kpad, const double* __restrict__ J, long long ld,
                 const int* __restrict__ expo, signed char* __restrict__ slices) {
+    __shared__ double stage[8][512 + 32];
     const long long j = blockIdx.y;
-    const long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (k0 >= kpad) return;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const long long w0 = ((long long)blockIdx.x * 8 + wrp) * 512;       // first row of this warp's 512
+    if (w0 >= kpad) return;                                             // whole warp
+    const long long k0 = w0 + 16 * lane;
     const int e = expo[j];
     const double* col = J + j * ld;
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
     const bool direct = (e > -1000 && e < 1000);                       // 2^-e is a normal double
     const double scale = (e == INT_MIN) ? 0.0 : (direct ? scalbn(1.0, -e) : 1.0);
+    double* st = stage[wrp];
+    const bool fast = (w0 + 512 <= m) && ((reinterpret_cast<uintptr_t>(col + w0) & 15) == 0);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int i = 2 * (32 * t + lane);                              // element pair (i, i+1) of the warp's 512
+        double2 v;
+        if (fast) v = __ldg(reinterpret_cast<const double2*>(col + w0 + i));
+        else { v.x = (w0 + i < m) ? col[w0 + i] : 0.0; v.y = (w0 + i + 1 < m) ? col[w0 + i + 1] : 0.0; }
+        const int q = i + (i >> 4);
+        st[q] = v.x; st[q + 1] = v.y;
+    }
+    __syncwarp();
+    if (k0 >= kpad) return;
     uint32_t w[S][4];
 #pragma unroll
     for (int p = 0; p < S; ++p) { w[p][0] = 0u; w[p][1] = 0u; w[p][2] = 0u; w[p][3] = 0u; }
     double xin[16];
-    if (k0 + 16 <= m && ((reinterpret_cast<uintptr_t>(col + k0) & 15) == 0)) {
 #pragma unroll
-        for (int t = 0; t < 16; t += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(col + k0 + t);
-            xin[t] = v.x; xin[t + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) xin[t] = (k0 + t < m) ? col[k0 + t] : 0.0;
-    }
+    for (int t = 0; t < 16; ++t) xin[t] = st[17 * lane + t];
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         double f = (direct || e == INT_MIN) ? xin[t] * scale : scalbn(xin[t], -e);     // |f| <= 1/2
@@ -402,7 +413,7 @@ int oz_syrk_upper(lso_ctx* ctx, OzPlan** pp, int S, int64_t m, int64_t n, const 
     oz_colexp_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(m, n, d_J, ld, p->expo);
     LSO_CHECK_LAUNCH(ctx);
     {
-        dim3 grid((unsigned)cdiv64(kpad / 16, 256), (unsigned)n);
+        dim3 grid((unsigned)cdiv64(kpad, 8 * 512), (unsigned)n);
         switch (S) {
             case 2: oz_split_kernel<2><<<grid, 256, 0, ctx->stream>>>(m, n, kpad, d_J, ld, p->expo, p->slices); break;
             case 3: oz_split_kernel<3><<<grid, 256, 0, ctx->stream>>>(m, n, kpad, d_J, ld, p->expo, p->slices); break;
