@@ -639,6 +639,27 @@ def _optimize_dogleg(anls: _Allocated, **kw):
 AUTO_CHUNK_SHARES = (0.30, 0.30, 0.25, 0.15)
 
 
+def host_chunk_rows(m: int, chunks) -> list:
+    """Row counts of the chunks in which a host-resident J crosses PCIe (`lso_qr_factor_keep_host_chunks`), in transfer
+    order: an int = that many (near-)equal chunks, a sequence of positive shares = those fractions of the m rows.  Every
+    row belongs to exactly one chunk and no chunk is empty."""
+    if isinstance(chunks, (int, np.integer)):
+        k = int(chunks)
+        if k <= 1:
+            return [int(m)]
+        k = min(k, int(m))
+        return [(m * (i + 1)) // k - (m * i) // k for i in range(k)]
+    shares = [float(c) for c in chunks]
+    if not shares or min(shares) <= 0:
+        raise ValueError("chunk shares must be positive")
+    edges = np.rint(np.cumsum([0.0] + shares) / float(sum(shares)) * m).astype(np.int64)
+    edges[-1] = m
+    rows = [int(b - a) for a, b in zip(edges[:-1], edges[1:])]
+    if min(rows) <= 0:
+        raise ValueError(f"chunk shares {shares} leave an empty chunk at m = {m}")
+    return rows
+
+
 class HostStep:
     """Hot-path body of one LevenbergMarquardt iteration driven from HOST buffers (the e2e path of bench.py and
     what the Julia glue does when `J` / `f` are plain host Arrays): H2D of J and f, colsumabs2! + damping (LM:82-86),
@@ -664,12 +685,7 @@ class HostStep:
         if auto:
             ok = not self.sharded and isinstance(anls.solver, DenseQRAllocatedSolver) and m >= 40 * n and m >= 50000
             chunks = list(AUTO_CHUNK_SHARES) if ok else 1
-        if isinstance(chunks, int):
-            self.chunk_rows = [m] if chunks <= 1 else [(m * (k + 1)) // chunks - (m * k) // chunks for k in range(chunks)]
-        else:
-            edges = np.rint(np.cumsum([0.0] + [float(c) for c in chunks]) / float(sum(chunks)) * m).astype(np.int64)
-            edges[-1] = m
-            self.chunk_rows = [int(b - a) for a, b in zip(edges[:-1], edges[1:])]
+        self.chunk_rows = host_chunk_rows(m, chunks)
         self.chunks = len(self.chunk_rows)
         if self.chunks > 1:
             self.chunk_solver = DenseQRAllocatedSolver(ctx, max(max(self.chunk_rows), n), n, damped=False)

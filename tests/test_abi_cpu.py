@@ -54,3 +54,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "reference_port" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_chunk_rows_partition_every_row_once():
+    """Host logic of the chunked upload (HostStep / lso_qr_factor_keep_host_chunks): the chunk sizes cover the m rows exactly,
+    in order, with no empty chunk; bad shares are rejected before anything is enqueued."""
+    import pytest
+    from lsob200.api import AUTO_CHUNK_SHARES, host_chunk_rows
+    assert host_chunk_rows(100000, 1) == [100000]
+    assert host_chunk_rows(100000, list(AUTO_CHUNK_SHARES)) == [30000, 30000, 25000, 15000]
+    for m, c in [(60001, 2), (60001, 3), (60001, 7), (7, 16), (100003, [0.3, 0.3, 0.25, 0.15]), (12345, [5, 1, 1])]:
+        rows = host_chunk_rows(m, c)
+        assert sum(rows) == m and min(rows) >= 1
+        if isinstance(c, int):
+            assert len(rows) == min(c, m) and max(rows) - min(rows) <= 1
+    with pytest.raises(ValueError):
+        host_chunk_rows(100, [0.5, 0.0, 0.5])
+    with pytest.raises(ValueError):
+        host_chunk_rows(2, [1, 1, 1])
