@@ -190,6 +190,24 @@ class OptimizationState:
     g_norm: float
 
 
+def format_trace(states, show_every: int = 1) -> str:
+    """`show(os::OptimizationState)` for every state with `iteration % show_every == 0` (utils.jl:104-108, 124-127:
+    `@printf "%6d   %14e   %14e\n" iteration value g_norm`)."""
+    def e14(v):                         # Julia's Printf writes Inf / NaN where C writes inf / nan
+        v = float(v)
+        if math.isnan(v):
+            return "NaN".rjust(14)
+        if math.isinf(v):
+            return ("Inf" if v > 0 else "-Inf").rjust(14)
+        return "%14e" % v
+
+    out = []
+    for st in states:
+        if st.iteration % max(int(show_every), 1) == 0:
+            out.append("%6d   %s   %s\n" % (st.iteration, e14(st.value), e14(st.g_norm)))
+    return "".join(out)
+
+
 @dataclass
 class LeastSquaresResult:
     optimizer: str
@@ -720,11 +738,21 @@ class HostStep:
 def optimize_(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, **kwargs) -> LeastSquaresResult:
     """`optimize!(nls, optimizer; kwargs...)` — types.jl:207-209 + LeastSquaresProblemAllocated (:152-157)."""
     anls = nls if isinstance(nls, _Allocated) else allocate(nls, optimizer)
-    kwargs.pop("show_trace", None)      # printing the trace (utils.jl:116-128) is host-side display, off the path
-    kwargs.pop("show_every", None)
-    if isinstance(anls.optimizer, LevenbergMarquardt):
-        return _optimize_lm(anls, **kwargs)
-    return _optimize_dogleg(anls, **kwargs)
+    # show_trace / show_every (utils.jl:97-128) are host-side display, off the path: the states are stored during the run
+    # and printed in the reference's format afterwards (the reference prints them as it goes)
+    show = bool(kwargs.pop("show_trace", False))
+    every = int(kwargs.pop("show_every", 1) or 1)
+    if not show:
+        if isinstance(anls.optimizer, LevenbergMarquardt):
+            return _optimize_lm(anls, **kwargs)
+        return _optimize_dogleg(anls, **kwargs)
+    keep = bool(kwargs.get("store_trace", False))
+    kwargs["store_trace"] = True
+    r = _optimize_lm(anls, **kwargs) if isinstance(anls.optimizer, LevenbergMarquardt) else _optimize_dogleg(anls, **kwargs)
+    print(format_trace(r.tr, every), end="")
+    if not keep:
+        r.tr = []
+    return r
 
 
 def allocate(nls: LeastSquaresProblem, optimizer: Optional[AbstractOptimizer] = None, sharded: bool = False) -> "_Allocated":

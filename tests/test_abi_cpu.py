@@ -72,3 +72,13 @@ def test_host_chunk_rows_partition_every_row_once():
         host_chunk_rows(100, [0.5, 0.0, 0.5])
     with pytest.raises(ValueError):
         host_chunk_rows(2, [1, 1, 1])
+
+
+def test_trace_lines_have_the_reference_format():
+    """utils.jl:124-127: `@printf "%6d   %14e   %14e\n"`; show_every filters on iteration % show_every (utils.jl:104-108)."""
+    from lsob200.api import OptimizationState, format_trace
+    st = [OptimizationState(0, 24.2, float("inf")), OptimizationState(1, 4.731884e+00, 3.0), OptimizationState(2, 1e-30, 0.0)]
+    assert format_trace(st) == ("     0     2.420000e+01              Inf\n"
+                                "     1     4.731884e+00     3.000000e+00\n"
+                                "     2     1.000000e-30     0.000000e+00\n")
+    assert format_trace(st, 2).count("\n") == 2 and format_trace([], 1) == ""
