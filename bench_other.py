@@ -74,25 +74,28 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
     h = ctx.handle
     nnz = n * k
     m_glob, nnz_glob = m, nnz
-    colptr = np.zeros(n + 1, dtype=np.int64)
-    rowval = np.zeros(nnz, dtype=np.int64)
-    check(lib().lso_synth_csc_pattern(m, n, k, 20240609, colptr.ctypes.data, rowval.ctypes.data))
-    colptr -= 1
-    rowval -= 1
-    if world > 1:
-        row0, row1 = (m * rank) // world, (m * (rank + 1)) // world
-        mask = (rowval >= row0) & (rowval < row1)
-        cs = np.zeros(nnz + 1, dtype=np.int64)
-        np.cumsum(mask, out=cs[1:])
-        colptr = cs[colptr]
-        rowval = rowval[mask] - row0
-        del mask, cs
-        m, nnz = row1 - row0, int(rowval.size)
     err = None
-    try:
+    try:        # everything that can fail on ONE rank (host or device memory) happens before the ranks agree to go on
+        colptr = np.zeros(n + 1, dtype=np.int64)
+        rowval = np.zeros(nnz, dtype=np.int64)
+        check(lib().lso_synth_csc_pattern(m, n, k, 20240609, colptr.ctypes.data, rowval.ctypes.data))
+        colptr -= 1
+        rowval -= 1
+        if world > 1:
+            row0, row1 = (m * rank) // world, (m * (rank + 1)) // world
+            mask = (rowval >= row0) & (rowval < row1)
+            cs = np.zeros(nnz + 1, dtype=np.int64)
+            np.cumsum(mask, out=cs[1:])
+            colptr = cs[colptr]
+            rowval = rowval[mask] - row0
+            del mask, cs
+            m, nnz = row1 - row0, int(rowval.size)
         A0 = L.CSCMatrix(ctx, m, n, colptr, rowval)          # A  (f! needs t = A x)
         Jac = L.CSCMatrix(ctx, m, n, colptr, rowval)         # J = diag(1 + 2 c t) A
         aval, aval_r = L.DeviceVector(ctx, nnz), L.DeviceVector(ctx, nnz)
+        xs, x, pert = (L.DeviceVector(ctx, n) for _ in range(3))
+        t, b, noise = (L.DeviceVector(ctx, m) for _ in range(3))
+        zero = L.DeviceVector(ctx, m)
     except Exception as e:
         err = f"{type(e).__name__}: {e}"
     if not _all_ok(env, err is None):
@@ -100,12 +103,9 @@ def run_c3(env, m=5_000_000, n=500_000, k=200, steps=10, warmup=2):
     check(lib().lso_synth_vector(h, nnz, 0, 99 + rank, 1.0, aval.ptr), h)
     check(lib().lso_csc_set_values_dev(A0.handle, aval.ptr), h)
     A0.gather_csr(aval, aval_r)
-    xs, x, pert = (L.DeviceVector(ctx, n) for _ in range(3))
-    t, b, noise = (L.DeviceVector(ctx, m) for _ in range(3))
     check(lib().lso_synth_vector(h, n, 0, 7, 1.0, xs.ptr), h)
     check(lib().lso_synth_vector(h, m, 0, 12 + 1000 * rank, NOISE, noise.ptr), h)
     check(lib().lso_synth_vector(h, n, 0, 13, 0.1, pert.ptr), h)
-    zero = L.DeviceVector(ctx, m)
     A0.mul(t, xs, 1.0, 0.0)
     check(lib().lso_synth_residual_from_t(h, m, t.ptr, zero.ptr, C_MODEL, b.ptr), h)      # b = t + c t^2 at x*
     b.axpy(1.0, noise)
